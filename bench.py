@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""Benchmark of the Pixel-Embedded-Affinity hot path on B200 (see BASELINE.json / SURVEY.md 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg1] [--impl ours|reference]
+
+A "step" is one fused forward+backward of embedding -> multi-offset affinities -> weighted-MSE loss -> gradient
+w.r.t. the embedding on one synthetic batch.  Metric: affinity-voxels/s (B*K*prod(spatial) per step), whole job.
+Prints ONE JSON line on rank 0.  N > 1: launched under torchrun, one rank per GPU, every rank processes its own
+batch (data-parallel, weak scaling, no data-path collective -- SURVEY.md 8e); time = max over ranks.
+
+--impl reference times the reference's CPU implementation of the same path (the oracle port: the reference is
+Python/torch-CPU and cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "affinity_voxels_per_s_fwd_bwd"
+UNIT = "aff-voxels/s"
+C = 16
+
+WORKLOADS = {
+    # name: (ndim, B, spatial, shifts / offsets descr)
+    "cfg1": dict(nd=2, B=1, spatial=(544, 512), shifts=[1, 3, 5, 9, 27],
+                 descr="CVPPP-shaped 2D: B=1, 16ch 544x512, multi_offset([1,3,5,9,27],4), K=10"),
+    "cfg2": dict(nd=2, B=8, spatial=(520, 696), shifts=[1, 3, 5, 9, 11],
+                 descr="BBBC039V1-shaped 2D batch: B=8, 16ch 520x696, multi_offset([1,3,5,9,11],4), K=10"),
+    "cfg3": dict(nd=3, B=4, spatial=(18, 160, 160), shifts=None,
+                 descr="AC3/AC4-shaped 3D patch: B=4, 16ch 18x160x160, 12 anisotropic offsets (norm5), K=12"),
+}
+
+
+def algorithmic_bytes_per_step(w):
+    """read E 4C + target 4K + weight 4K (+ mask K, 2D) + write grad 4C + affs 4K, per spatial voxel."""
+    K = 12 if w["nd"] == 3 else 2 * len(w["shifts"])
+    per_voxel = 4 * C + 4 * K + 4 * K + (K if w["nd"] == 2 else 0) + 4 * C + 4 * K
+    return per_voxel * w["B"] * int(np.prod(w["spatial"])), K
+
+
+# ------------------------------------------------------------------------------------------ synthetic inputs
+def make_labels(w, seed):
+    from oracle import pea_oracle as O
+    out = []
+    for b in range(w["B"]):
+        if w["nd"] == 2:
+            out.append(O.voronoi_labels(w["spatial"], 20, seed * 100 + b, background_frac=0.3, dtype=np.uint8))
+        else:
+            out.append(O.voronoi_labels(w["spatial"], 60, seed * 100 + b, background_frac=0.1, z_scale=8.0, dtype=np.uint16))
+    return np.stack(out)
+
+
+def host_inputs_oracle(w, seed, B=None):
+    """Everything on the host through the oracle (reference arm / cpu_baseline)."""
+    from oracle import pea_oracle as O
+    B = B or w["B"]
+    lab = make_labels(dict(w, B=B), seed)
+    g = torch.Generator().manual_seed(seed)
+    emb = torch.randn((B, C) + tuple(w["spatial"]), generator=g)
+    if w["nd"] == 2:
+        offsets = O.multi_offset(w["shifts"], 4)
+        pairs = [O.gen_affs_ours(l, offsets, ignore=False, padding=True) for l in lab]
+        tgt = np.stack([p[0] for p in pairs])
+        msk = np.stack([p[1] for p in pairs])
+    else:
+        offsets = None
+        tgt = np.stack([O.seg_to_aff_norm5(l) for l in lab])
+        msk = None
+    wgt = np.stack([np.stack([O.weight_binary_ratio(c) for c in t]) for t in tgt])
+    return emb, torch.tensor(tgt), torch.tensor(wgt), (torch.tensor(msk) if msk is not None else None), offsets
+
+
+def oracle_step(w, emb, tgt, wgt, msk, offsets):
+    from oracle import pea_oracle as O
+    e = emb.detach().requires_grad_(True)
+    if w["nd"] == 2:
+        loss, _, _ = O.embedding_loss(e, tgt, wgt, msk, O.WeightedMSE(), offsets)
+    else:
+        loss, _ = O.embedding_loss_norm5(e, tgt, wgt, O.WeightedMSE())
+    loss.backward()
+    return float(loss.detach())
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    alg_bytes, K = algorithmic_bytes_per_step(w)
+    # bounded sample: shrink the batch until K steps fit in the budget
+    B = w["B"]
+    emb, tgt, wgt, msk, offsets = host_inputs_oracle(w, 0, B)
+    t0 = time.perf_counter()
+    oracle_step(w, emb, tgt, wgt, msk, offsets)
+    t1 = time.perf_counter() - t0
+    budget = 240.0
+    while B > 1 and t1 * (B / w["B"]) * (args.steps + args.warmup) > budget:
+        B //= 2
+    if B != w["B"]:
+        emb, tgt, wgt, msk, offsets = host_inputs_oracle(w, 0, B)
+    for _ in range(max(args.warmup - 1, 0)):
+        oracle_step(w, emb, tgt, wgt, msk, offsets)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(w, emb, tgt, wgt, msk, offsets)
+    dt = time.perf_counter() - t0
+    vox = B * K * int(np.prod(w["spatial"]))
+    value = vox * args.steps / dt
+    sample = f"{args.steps} fwd+bwd calls of the oracle port (torch CPU) at B={B} of the workload's B={w['B']}"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["descr"], "name": args.workload, "sample_batch": B},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def device_inputs(P, w, seed, device):
+    lab = make_labels(w, seed)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    emb = torch.randn((w["B"], C) + tuple(w["spatial"]), generator=g).to(device)
+    if w["nd"] == 2:
+        offsets = P.multi_offset(w["shifts"], 4)
+        tgt, msk, wgt = P.make_targets_2d(torch.tensor(lab).to(device), offsets)
+    else:
+        offsets = None
+        tgt, wgt = P.make_targets_3d(torch.tensor(lab.astype(np.int32)).to(device))
+        msk = None
+    return lab, emb, tgt, wgt, msk, offsets
+
+
+def our_step(P, w, e, tgt, wgt, msk, offsets, crit):
+    if w["nd"] == 2:
+        loss, _, _ = P.embedding_loss(e, tgt, wgt, msk, crit, offsets)
+    else:
+        loss, _ = P.embedding_loss_norm5(e, tgt, wgt, crit)
+    loss.backward()
+    return loss
+
+
+LAUNCHES_PER_STEP = 4  # rinv, fused, finalize_loss, scale_inplace (see DESIGN.md "kernels per step")
+
+
+def time_workload(P, w, steps, warmup, device, flush, dist_on):
+    """Device-resident throughput: CUDA graph of one public-API fwd+bwd, replayed; L2 flushed between steps."""
+    lab, emb, tgt, wgt, msk, offsets = device_inputs(P, w, 0, device)
+    crit = P.WeightedMSE()
+    e = emb.clone().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            our_step(P, w, e, tgt, wgt, msk, offsets, crit)
+            e.grad = None
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss = our_step(P, w, e, tgt, wgt, msk, offsets, crit)
+    for _ in range(max(warmup, 3)):
+        flush.zero_()
+        graph.replay()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+    for i in range(steps):
+        flush.zero_()            # evict the previous step's lines from the 126 MB L2 (untimed)
+        starts[i].record()
+        graph.replay()
+        ends[i].record()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+    per = [s.elapsed_time(t) for s, t in zip(starts, ends)]  # ms
+    return dict(total_ms=sum(per), per_ms=per, loss=float(loss), inputs=(lab, emb, tgt, wgt, msk, offsets))
+
+
+def time_e2e(P, w, steps, warmup, device, inputs):
+    """Public API with HOST buffers: every step copies embedding/target/weight(/mask) from pinned host memory,
+    runs fwd+bwd and reads the loss back."""
+    lab, emb, tgt, wgt, msk, offsets = inputs
+    host = [t.cpu().pin_memory() if t is not None else None for t in (emb, tgt, wgt, msk)]
+    dev = [torch.empty_like(t, device=device) if t is not None else None for t in host]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    crit = P.WeightedMSE()
+    h2d = sum(t.numel() * t.element_size() for t in host if t is not None)
+
+    def step():
+        for h, d in zip(host, dev):
+            if h is not None:
+                d.copy_(h, non_blocking=True)
+        e = dev[0].requires_grad_(True)
+        loss = our_step(P, w, e, dev[1], dev[2], dev[3], offsets, crit)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.synchronize()
+        dev[0].requires_grad_(False)
+        e.grad = None
+        return float(loss_host)
+
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) * 1e3, h2d, 4
+
+
+def time_e2e_labels_only(P, w, steps, device, inputs):
+    """B200-native pipeline: only the label map crosses PCIe; target/mask/weight are generated on the device."""
+    lab, emb, _, _, _, offsets = inputs
+    lab_t = torch.tensor(lab if w["nd"] == 2 else lab.astype(np.int32))
+    host = lab_t.pin_memory()
+    dev_lab = torch.empty_like(host, device=device)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    crit = P.WeightedMSE()
+    e = emb.clone().requires_grad_(True)
+
+    def step():
+        dev_lab.copy_(host, non_blocking=True)
+        if w["nd"] == 2:
+            tgt, msk, wgt = P.make_targets_2d(dev_lab, offsets)
+        else:
+            tgt, wgt = P.make_targets_3d(dev_lab)
+            msk = None
+        loss = our_step(P, w, e, tgt, wgt, msk, offsets, crit)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.synchronize()
+        e.grad = None
+
+    for _ in range(3):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) * 1e3, host.numel() * host.element_size()
+
+
+def time_fwd_volume(P, device, steps, shape=(100, 1024, 1024)):
+    """cfg4 on one GPU: forward-only 12-channel affinities of a full AC3/AC4 volume (112 B/voxel algorithmic)."""
+    emb = torch.randn((1, C) + shape, device=device)
+    for _ in range(2):
+        out = P.inf_embedding_loss_norm5(emb)
+        del out
+    torch.cuda.synchronize()
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        out = P.inf_embedding_loss_norm5(emb)
+        del out
+    t.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(t) / steps
+    vox = int(np.prod(shape))
+    return {"workload": "cfg4 AC3/AC4 full volume 100x1024x1024 forward-only, 1 GPU", "ms_per_step": ms,
+            "value": 12 * vox / (ms * 1e-3), "unit": "aff-voxels/s (forward only)",
+            "hbm_gbs": 112 * vox / (ms * 1e-3) / 1e9}
+
+
+def cpu_baseline(w, seconds=12.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    emb, tgt, wgt, msk, offsets = host_inputs_oracle(w, 0)
+    oracle_step(w, emb, tgt, wgt, msk, offsets)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        oracle_step(w, emb, tgt, wgt, msk, offsets)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds or n >= 20:
+            break
+    _, K = algorithmic_bytes_per_step(w)
+    vox = w["B"] * K * int(np.prod(w["spatial"]))
+    return {"value": vox * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} full-batch fwd+bwd calls of the oracle port (torch CPU, {cores} threads), {dt:.1f} s"}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args, rank, world, local_rank):
+    import pea_b200 as P
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    w = WORKLOADS[args.workload]
+    alg_bytes, K = algorithmic_bytes_per_step(w)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res = time_workload(P, w, args.steps, args.warmup, device, flush, dist_on)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([res["total_ms"]], device=device, dtype=torch.float64)
+    if dist_on:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    vox_step = w["B"] * K * int(np.prod(w["spatial"]))
+    value = world * vox_step * args.steps / (total_ms * 1e-3)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms, h2d, d2h = time_e2e(P, w, e2e_steps, args.warmup, device, res["inputs"])
+    e2e_t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+    if dist_on:
+        torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * vox_step * e2e_steps / (float(e2e_t) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_step = total_ms / args.steps
+        achieved = alg_bytes / (statistics.mean(res["per_ms"]) * 1e-3) / 1e9
+        lab_ms, lab_bytes = time_e2e_labels_only(P, w, e2e_steps, device, res["inputs"])
+        also = {}
+        if world == 1 and not args.quick:
+            for name in ("cfg1", "cfg2", "cfg3"):
+                if name == args.workload:
+                    continue
+                ww = WORKLOADS[name]
+                r = time_workload(P, ww, args.steps, args.warmup, device, flush, False)
+                ab, kk = algorithmic_bytes_per_step(ww)
+                ms = r["total_ms"] / args.steps
+                also[name] = {"workload": ww["descr"], "ms_per_step": ms,
+                              "value": ww["B"] * kk * int(np.prod(ww["spatial"])) / (ms * 1e-3), "unit": UNIT,
+                              "hbm_gbs": ab / (ms * 1e-3) / 1e9, "roofline_frac": ab / (ms * 1e-3) / 1e9 / peak}
+                del r
+            torch.cuda.empty_cache()
+            try:
+                also["cfg4"] = time_fwd_volume(P, device, 3)
+                also["cfg4"]["roofline_frac"] = also["cfg4"]["hbm_gbs"] / peak
+            except torch.OutOfMemoryError as exc:  # pragma: no cover
+                also["cfg4"] = {"error": str(exc)[:80]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": w["descr"], "name": args.workload, "per_gpu_batch": w["B"],
+                       "parallelism": f"dp{world} (independent batches, no data-path collective)",
+                       "l2": "flushed between timed steps (256 MiB memset, untimed); step working set also exceeds L2",
+                       "timing": "CUDA events around a CUDA-graph replay of the public-API fwd+bwd, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": args.traffic, "peak_source": peak_src,
+                         "kernel": "whole fused step (all pea kernels of one fwd+bwd)",
+                         "algorithmic_bytes_per_step": alg_bytes},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "what": "embedding+target+weight(+mask) from pinned host each step, loss read back"},
+            "e2e_labels_only": {"value": vox_step * e2e_steps / (lab_ms * 1e-3), "unit": UNIT,
+                                "h2d_bytes_per_step": lab_bytes,
+                                "what": "embedding resident (backbone output); labels uploaded, GT generated on device"},
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "clocks": clocks,
+            "loss": res["loss"],
+        }
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline(w)
+        else:
+            line["cpu_baseline"] = None
+        if also:
+            line["also"] = also
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="skip the other workloads (the `also` block)")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from an ncu capture (for the roofline object)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+/* pea_b200.h -- C ABI of the B200-native Pixel-Embedded-Affinity hot path.
+ *
+ * The reference (weih527/Pixel-Embedded-Affinity) has no FFI: its boundary for this path is a set
+ * of Python callables.  Each entry point below is the device-side replacement of one (group of)
+ * reference callable(s), cited as file:line under the reference tree.  The Python drop-in layer
+ * (the .py files in pixel-embedded-affinity_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  No torch / C++ types cross this boundary.
+ *   - Every data pointer is a DEVICE pointer owned by the caller; `offsets`, `loss_norm`,
+ *     `loss_coef` are small HOST arrays that are copied into kernel parameters during the call.
+ *   - The library allocates nothing, keeps no global mutable state, and enqueues all work on the
+ *     `stream` argument (a cudaStream_t passed as void*).  No call synchronises the device.
+ *     Calls are re-entrant and CUDA-graph capturable.
+ *   - Return value: 0 on success, a negative PEA_E_* code for a rejected argument, or a positive
+ *     cudaError_t if a launch failed.  Nothing throws, nothing exits.
+ *   - Volumes are channel-planar, contiguous: embedding (B, C, D, H, W) float32, 2-D callers pass
+ *     D = 1.  Per-offset tensors (target / weight / mask / affs) are (B, K, D, H, W).
+ *   - Built for sm_100a only.  There is no CPU path.
+ */
+#ifndef PEA_B200_H_
+#define PEA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEA_ABI_VERSION 1
+#define PEA_MAX_OFFSETS 64
+
+/* error codes (negative); positive return values are cudaError_t */
+#define PEA_OK 0
+#define PEA_E_NULL (-1)         /* a required pointer is NULL */
+#define PEA_E_SHAPE (-2)        /* non-positive or overflowing extent */
+#define PEA_E_CHANNELS (-3)     /* embedding channel count not one of 4, 8, 16, 32 */
+#define PEA_E_OFFSETS (-4)      /* K outside [1, PEA_MAX_OFFSETS] */
+#define PEA_E_WORKSPACE (-5)    /* workspace smaller than pea_workspace_bytes() */
+#define PEA_E_DTYPE (-6)        /* unknown mask / label dtype code */
+#define PEA_E_ALIGN (-7)        /* pointer not aligned for its element type */
+#define PEA_E_MODE (-8)         /* unknown border / variant code */
+
+/* border rule for the neighbour p + offset */
+#define PEA_BORDER_WRAP 0 /* circular, torch.roll semantics: scripts_cvppp/loss/loss_embedding_mse.py:8 */
+#define PEA_BORDER_ZERO 1 /* valid region only, affinity 0 elsewhere: scripts_ac3ac4/loss/loss_embedding_mse.py:147-151,186-190 */
+
+/* dtype codes */
+#define PEA_MASK_NONE 0
+#define PEA_MASK_U8 1
+#define PEA_MASK_F32 2
+#define PEA_LABEL_U8 0
+#define PEA_LABEL_U16 1
+#define PEA_LABEL_U32 2
+#define PEA_LABEL_U64 3
+#define PEA_LABEL_F32 4
+#define PEA_LABEL_S8 5
+#define PEA_LABEL_S16 6
+#define PEA_LABEL_S32 7
+#define PEA_LABEL_S64 8
+
+/* kernel-selection hint for pea_affs_loss_fwd_bwd / pea_affs_fwd (results are identical) */
+#define PEA_IMPL_AUTO 0
+#define PEA_IMPL_GENERIC 1 /* table-driven gather kernel, any offsets */
+#define PEA_IMPL_TILED 2   /* shared-memory / register-tiled kernels for axis-aligned offset sets */
+
+int pea_abi_version(void);
+const char* pea_strerror(int code);
+
+/* Bytes of device workspace the affinity entry points need for a problem of this size.
+ * `cross` != 0 when a partner (second-view) embedding is passed. */
+size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, int cross);
+
+/* embedding -> affinities, forward only.
+ *   replaces  embedding2affs                 scripts_cvppp/loss/loss_embedding_mse.py:58-66   (border = WRAP)
+ *             inf_embedding_loss_norm1/5     scripts_ac3ac4/loss/loss_embedding_mse.py:54-67,212-234 (border = ZERO)
+ * affs[b,k,p] = <e^[b,:,p], u^[b,:,p+o_k]>,  e^ = emb / max(|emb|_2, 1e-12), u^ likewise from `partner`
+ * (or e^ itself when partner == NULL).  offsets: host int32[K*3] as (dz, dy, dx). */
+int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
+                 const int32_t* offsets, int K, int border, int impl,
+                 float* affs, void* workspace, size_t ws_bytes, void* stream);
+
+/* Fused embedding -> affinities -> weighted-MSE loss -> d loss / d embedding, one pass.
+ *   replaces  embedding_loss / ema_embedding_loss      scripts_cvppp/loss/loss_embedding_mse.py:18-47,79-95
+ *             embedding_loss_norm1/5, ema_* variants   scripts_ac3ac4/loss/loss_embedding_mse.py:7-51,169-194,263-289
+ *             WeightedMSE                              scripts_cvppp/loss/loss.py:106-124
+ *             and the autograd replay of all of the above.
+ * Per offset k:  S_k = sum_p w (a m - t m)^2  over the pairs the border rule keeps;
+ *                loss_k = S_k / loss_norm[k];   loss = sum_k loss_coef[k] * loss_k  (float32, in offset order).
+ * loss_out (device, 1 + K floats) receives [loss, loss_0 .. loss_{K-1}].
+ * grad_emb (B,C,D,H,W) receives d loss / d emb for an upstream gradient of 1; grad_partner likewise for
+ * the partner embedding; either may be NULL (not computed).  affs may be NULL (not stored).
+ * mask may be NULL with mask_dtype = PEA_MASK_NONE. */
+int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
+                          const int32_t* offsets, int K, int border, int impl,
+                          const float* target, const float* weight, const void* mask, int mask_dtype,
+                          const float* loss_norm, const float* loss_coef,
+                          float* affs, float* loss_out, float* grad_emb, float* grad_partner,
+                          void* workspace, size_t ws_bytes, void* stream);
+
+/* Backward of pea_affs_fwd for an arbitrary upstream gradient (criterion other than WeightedMSE, or a
+ * caller that back-propagates through the returned 2-D affs, scripts_cvppp/loss/loss_embedding_mse.py:46).
+ * grad_affs is (B,K,D,H,W); grad_emb / grad_partner are overwritten (either may be NULL). */
+int pea_affs_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
+                 const int32_t* offsets, int K, int border,
+                 const float* grad_affs, float* grad_emb, float* grad_partner,
+                 void* workspace, size_t ws_bytes, void* stream);
+
+/* buf[i] *= *scale (a device scalar), in place; exits without touching memory when *scale == 1.
+ * Used by the autograd backward to apply the upstream gradient of the scalar loss to the gradient the
+ * fused forward already produced (the common `loss.backward()` case costs one empty launch). */
+int pea_scale_inplace(float* buf, int64_t n, const float* scale, void* stream);
+
+/* labels -> (affinity float32, validity mask uint8), 2-D, per offset (dy, dx).
+ *   replaces  gen_affs_ours   scripts_cvppp/utils/affinity_ours.py:17-39
+ * labels (B,H,W) of `label_dtype`; offsets host int32[K*2]; affs/mask (B,K,H,W). mask may be NULL. */
+int pea_gt_affs2d(const void* labels, int label_dtype, int B, int H, int W,
+                  const int32_t* offsets, int K, int ignore, int padding,
+                  float* affs, uint8_t* mask, void* stream);
+
+/* segmentation -> background-aware affinities by neighbourhood (dz, dy, dx); 2-D callers pass D = 1.
+ *   replaces  seg_to_aff      scripts_cvppp/data/data_affinity.py:53-102
+ * replicate_pad applies the `pad == 'replicate'` border rule (:94-100): 0 = off, 3 = three edges of a 3-D
+ * volume (K must be 3), 2 = two edges of a 2-D image passed as D = 1 (K must be 2).
+ * seg (B,D,H,W); affs (B,K,D,H,W).  Signed label codes make the `seg > 0` test signed, as NumPy's is. */
+int pea_gt_affs3d(const void* seg, int label_dtype, int B, int D, int H, int W,
+                  const int32_t* nhood, int K, int replicate_pad,
+                  float* affs, void* stream);
+
+/* Class-balance weights, one independent problem per channel.
+ *   replaces  weight_binary_ratio   scripts_cvppp/data/data_segmentation.py:205-228   (mask=None)
+ * label (n_channels, n_per_channel) float32 -> weight, same shape.  stats: device scratch of
+ * pea_wbr_stats_bytes(n_channels) bytes. */
+size_t pea_wbr_stats_bytes(int n_channels);
+int pea_weight_binary_ratio(const float* label, int n_channels, int64_t n_per_channel, double alpha,
+                            float* weight, void* stats, size_t stats_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEA_B200_H_ */

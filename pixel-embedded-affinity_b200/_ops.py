@@ -1,0 +1,214 @@
+"""Tensor-level wrappers over the C ABI: validation, workspace from torch's caching allocator, current stream.
+
+PyTorch is plumbing here (device memory + streams); every computation is a pea_* call into libpea_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, c_float_p, c_int32_p
+
+BORDER_WRAP, BORDER_ZERO = 0, 1
+MASK_NONE, MASK_U8, MASK_F32 = 0, 1, 2
+IMPL_AUTO, IMPL_GENERIC, IMPL_TILED = 0, 1, 2
+MAX_OFFSETS = 64
+
+_LABEL_CODES = {
+    torch.uint8: 0, torch.float32: 4, torch.int8: 5, torch.int16: 6, torch.int32: 7, torch.int64: 8,
+}
+for _n, _c in (("uint16", 1), ("uint32", 2), ("uint64", 3)):
+    if hasattr(torch, _n):
+        _LABEL_CODES[getattr(torch, _n)] = _c
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _i32(values):
+    arr = np.ascontiguousarray(np.asarray(values, dtype=np.int32).reshape(-1))
+    return arr, arr.ctypes.data_as(c_int32_p)
+
+
+def _f32(values):
+    arr = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(-1))
+    return arr, arr.ctypes.data_as(c_float_p)
+
+
+def check_embedding(name, t, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: pea_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dimensions, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def check_like(name, t, shape, dtypes=(torch.float32,)):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: pea_b200 has no CPU path")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.dtype not in dtypes:
+        t = t.to(dtypes[0])
+    return t.contiguous()
+
+
+def offsets3(offsets, ndim_spatial):
+    """list[[dy,dx]] or list[[dz,dy,dx]] -> (K,3) int32."""
+    arr = np.asarray(offsets, dtype=np.int64)
+    if arr.ndim != 2 or arr.shape[1] != ndim_spatial:
+        raise ValueError(f"offsets must be a list of {ndim_spatial}-element offsets, got shape {arr.shape}")
+    if not 1 <= arr.shape[0] <= MAX_OFFSETS:
+        raise ValueError(f"between 1 and {MAX_OFFSETS} offsets are supported, got {arr.shape[0]}")
+    if ndim_spatial == 2:
+        arr = np.concatenate([np.zeros((arr.shape[0], 1), np.int64), arr], axis=1)
+    return arr.astype(np.int32)
+
+
+def _dims5(emb):
+    if emb.dim() == 4:
+        B, C, H, W = emb.shape
+        return B, C, 1, H, W
+    B, C, D, H, W = emb.shape
+    return B, C, D, H, W
+
+
+def _workspace(B, C, D, H, W, K, cross, device):
+    n = lib.pea_workspace_bytes(B, C, D, H, W, K, int(cross))
+    if n == 0:
+        raise ValueError(f"unsupported problem: B={B} C={C} D={D} H={H} W={W} K={K} (C must be 4, 8, 16 or 32)")
+    return torch.empty(n, dtype=torch.uint8, device=device), n
+
+
+def affs_fwd(emb, partner, offs3, border, impl=IMPL_AUTO):
+    """(B,C,[D,]H,W) -> (B,K,[D,]H,W) affinities.  emb/partner already validated + contiguous."""
+    B, C, D, H, W = _dims5(emb)
+    K = offs3.shape[0]
+    spatial = emb.shape[2:]
+    affs = torch.empty((B, K) + tuple(spatial), dtype=torch.float32, device=emb.device)
+    ws, n = _workspace(B, C, D, H, W, K, partner is not None, emb.device)
+    keep, optr = _i32(offs3)
+    with torch.cuda.device(emb.device):
+        rc = lib.pea_affs_fwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, _ptr(affs), _ptr(ws), n,
+                              _stream())
+    check("pea_affs_fwd", rc)
+    return affs
+
+
+def affs_loss_fwd_bwd(emb, partner, offs3, border, target, weight, mask, loss_norm, loss_coef, want_affs=True,
+                      want_grad=True, want_grad_partner=False, impl=IMPL_AUTO):
+    """One fused launch sequence.  Returns (loss_out (1+K,), affs or None, grad_emb or None, grad_partner or None)."""
+    B, C, D, H, W = _dims5(emb)
+    K = offs3.shape[0]
+    dev = emb.device
+    spatial = tuple(emb.shape[2:])
+    if mask is None:
+        mdt = MASK_NONE
+    elif mask.dtype == torch.uint8:
+        mdt = MASK_U8
+    elif mask.dtype == torch.float32:
+        mdt = MASK_F32
+    else:
+        raise TypeError(f"mask must be uint8 or float32 here, got {mask.dtype}")
+    affs = torch.empty((B, K) + spatial, dtype=torch.float32, device=dev) if want_affs else None
+    grad = torch.empty_like(emb) if want_grad else None
+    gpar = torch.empty_like(partner) if (want_grad_partner and partner is not None) else None
+    loss_out = torch.empty(1 + K, dtype=torch.float32, device=dev)
+    ws, n = _workspace(B, C, D, H, W, K, partner is not None, dev)
+    keep_o, optr = _i32(offs3)
+    keep_n, nptr = _f32(loss_norm)
+    keep_c, cptr = _f32(loss_coef)
+    with torch.cuda.device(dev):
+        rc = lib.pea_affs_loss_fwd_bwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, _ptr(target),
+                                       _ptr(weight), _ptr(mask), mdt, nptr, cptr, _ptr(affs), _ptr(loss_out), _ptr(grad),
+                                       _ptr(gpar), _ptr(ws), n, _stream())
+    check("pea_affs_loss_fwd_bwd", rc)
+    return loss_out, affs, grad, gpar
+
+
+def affs_bwd(emb, partner, offs3, border, grad_affs, want_grad=True, want_grad_partner=False):
+    B, C, D, H, W = _dims5(emb)
+    K = offs3.shape[0]
+    dev = emb.device
+    grad_affs = check_like("grad_affs", grad_affs, (B, K) + tuple(emb.shape[2:]))
+    grad = torch.empty_like(emb) if want_grad else None
+    gpar = torch.empty_like(partner) if (want_grad_partner and partner is not None) else None
+    ws, n = _workspace(B, C, D, H, W, K, partner is not None, dev)
+    keep_o, optr = _i32(offs3)
+    with torch.cuda.device(dev):
+        rc = lib.pea_affs_bwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, _ptr(grad_affs), _ptr(grad),
+                              _ptr(gpar), _ptr(ws), n, _stream())
+    check("pea_affs_bwd", rc)
+    return grad, gpar
+
+
+def scale_inplace(buf, scale):
+    """buf *= scale (0-dim float32 CUDA tensor); no-op launch when the scalar is exactly 1."""
+    with torch.cuda.device(buf.device):
+        rc = lib.pea_scale_inplace(_ptr(buf), buf.numel(), _ptr(scale), _stream())
+    check("pea_scale_inplace", rc)
+    return buf
+
+
+# ------------------------------------------------------------------------------------------- ground truth
+def label_code(t):
+    try:
+        return _LABEL_CODES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported label dtype {t.dtype}") from None
+
+
+def gt_affs2d(labels, offsets2, ignore, padding, want_mask=True):
+    """labels (B,H,W) CUDA tensor -> (affs (B,K,H,W) f32, mask (B,K,H,W) u8)."""
+    B, H, W = labels.shape
+    offs = np.asarray(offsets2, dtype=np.int32).reshape(-1, 2)
+    K = offs.shape[0]
+    if not 1 <= K <= MAX_OFFSETS:
+        raise ValueError(f"between 1 and {MAX_OFFSETS} offsets are supported, got {K}")
+    affs = torch.empty((B, K, H, W), dtype=torch.float32, device=labels.device)
+    mask = torch.empty((B, K, H, W), dtype=torch.uint8, device=labels.device) if want_mask else None
+    keep, optr = _i32(offs)
+    with torch.cuda.device(labels.device):
+        rc = lib.pea_gt_affs2d(_ptr(labels), label_code(labels), B, H, W, optr, K, int(bool(ignore)), int(bool(padding)),
+                               _ptr(affs), _ptr(mask), _stream())
+    check("pea_gt_affs2d", rc)
+    return affs, mask
+
+
+def gt_affs3d(seg, nhood3, replicate_pad):
+    """seg (B,D,H,W) CUDA tensor, nhood (K,3) -> affs (B,K,D,H,W) f32.  replicate_pad in {0, 2, 3}."""
+    B, D, H, W = seg.shape
+    nh = np.asarray(nhood3, dtype=np.int32).reshape(-1, 3)
+    K = nh.shape[0]
+    if not 1 <= K <= MAX_OFFSETS:
+        raise ValueError(f"between 1 and {MAX_OFFSETS} edges are supported, got {K}")
+    affs = torch.empty((B, K, D, H, W), dtype=torch.float32, device=seg.device)
+    keep, optr = _i32(nh)
+    with torch.cuda.device(seg.device):
+        rc = lib.pea_gt_affs3d(_ptr(seg), label_code(seg), B, D, H, W, optr, K, int(replicate_pad), _ptr(affs), _stream())
+    check("pea_gt_affs3d", rc)
+    return affs
+
+
+def weight_binary_ratio(label, n_channels, alpha=1.0):
+    """label: contiguous float32 CUDA tensor viewed as (n_channels, -1); one independent problem per channel."""
+    n_per = label.numel() // n_channels
+    weight = torch.empty_like(label)
+    nbytes = lib.pea_wbr_stats_bytes(n_channels)
+    stats = torch.empty(nbytes // 8, dtype=torch.int64, device=label.device)
+    with torch.cuda.device(label.device):
+        rc = lib.pea_weight_binary_ratio(_ptr(label), n_channels, n_per, float(alpha), _ptr(weight), _ptr(stats), nbytes,
+                                         _stream())
+    check("pea_weight_binary_ratio", rc)
+    return weight

@@ -1,0 +1,223 @@
+// extern "C" entry points for the affinity ops (declared in include/pea_b200.h): argument validation,
+// workspace carving, kernel selection.  No allocation, no global state, everything on the caller's stream.
+#include "pea_common.cuh"
+
+namespace pea {
+
+// pea_affs_generic.cu
+int generic_partial_blocks(int64_t total);
+int launch_rinv(const float* emb, int C, const Dims& d, float* rinv, cudaStream_t st);
+int launch_fwd_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C, const Dims& d,
+                       const OffsetTable& tab, int wrap, float* affs, cudaStream_t st);
+int launch_fused_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C,
+                         const Dims& d, const OffsetTable& tab, int wrap, int cross, const float* target,
+                         const float* weight, const void* mask, int mask_dtype, const float* upstream, float* affs,
+                         float* partials, float* grad_emb, float* grad_par, cudaStream_t st);
+
+struct LossScale {
+    float norm[PEA_MAX_OFFSETS];
+    float coef[PEA_MAX_OFFSETS];
+};
+
+// partials[blk][k] -> loss_out[0] = sum_k coef_k * (S_k / norm_k), loss_out[1+k] = S_k / norm_k.
+// Fixed summation order (double accumulation over blocks) => run-to-run reproducible loss.
+__global__ void __launch_bounds__(1024) finalize_loss_kernel(const float* __restrict__ partials, int nblocks, int K,
+                                                             LossScale sc, float* __restrict__ loss_out) {
+    __shared__ float s_loss[PEA_MAX_OFFSETS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < K; k += 32) {
+        double acc = 0.0;
+        for (int b = lane; b < nblocks; b += 32) acc += (double)partials[(int64_t)b * K + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_loss[k] = (float)acc / sc.norm[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float total = 0.f;
+        for (int k = 0; k < K; ++k) {
+            loss_out[1 + k] = s_loss[k];
+            total += s_loss[k] * sc.coef[k];
+        }
+        loss_out[0] = total;
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ buf, int64_t n,
+                                                            const float* __restrict__ scale) {
+    const float s = __ldg(scale);
+    if (s == 1.0f) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(buf) & 15) == 0) {
+        float4* b4 = reinterpret_cast<float4*>(buf);
+        for (int64_t i = tid; i < n / 4; i += stride) {
+            float4 v = b4[i];
+            v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+            b4[i] = v;
+        }
+        for (int64_t i = (n / 4) * 4 + tid; i < n; i += stride) buf[i] *= s;
+    } else {
+        for (int64_t i = tid; i < n; i += stride) buf[i] *= s;
+    }
+}
+
+struct Workspace {
+    float* rinvE;
+    float* rinvU;
+    float* partials;
+    size_t bytes;
+};
+
+static bool carve(void* ws, int B, int64_t N, int K, int cross, Workspace& out) {
+    const size_t plane = align_up((size_t)B * (size_t)N * sizeof(float), 256);
+    const size_t parts = align_up((size_t)generic_partial_blocks((int64_t)B * N) * (size_t)K * sizeof(float), 256);
+    char* p = static_cast<char*>(ws);
+    out.rinvE = reinterpret_cast<float*>(p);
+    out.rinvU = cross ? reinterpret_cast<float*>(p + plane) : out.rinvE;
+    out.partials = reinterpret_cast<float*>(p + plane * (cross ? 2 : 1));
+    out.bytes = plane * (cross ? 2 : 1) + parts;
+    return true;
+}
+
+static int check_volume(int B, int C, int D, int H, int W, int K, Dims& d) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return PEA_E_SHAPE;
+    if (C != 4 && C != 8 && C != 16 && C != 32) return PEA_E_CHANNELS;
+    if (K < 1 || K > PEA_MAX_OFFSETS) return PEA_E_OFFSETS;
+    d.B = B; d.D = D; d.H = H; d.W = W;
+    d.N = (int64_t)D * H * W;
+    if (d.N > (int64_t)1 << 40) return PEA_E_SHAPE;
+    return PEA_OK;
+}
+
+static void fill_offsets(const int32_t* offsets, int K, OffsetTable& tab) {
+    tab.K = K;
+    for (int k = 0; k < K; ++k) {
+        tab.dz[k] = offsets[3 * k];
+        tab.dy[k] = offsets[3 * k + 1];
+        tab.dx[k] = offsets[3 * k + 2];
+        tab.gcoef[k] = 0.f;
+    }
+}
+
+}  // namespace pea
+
+using namespace pea;
+
+extern "C" int pea_abi_version(void) { return PEA_ABI_VERSION; }
+
+extern "C" const char* pea_strerror(int code) {
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    switch (code) {
+        case PEA_OK: return "ok";
+        case PEA_E_NULL: return "a required pointer is NULL";
+        case PEA_E_SHAPE: return "non-positive or overflowing extent";
+        case PEA_E_CHANNELS: return "embedding channel count must be 4, 8, 16 or 32";
+        case PEA_E_OFFSETS: return "number of offsets must be in [1, 64]";
+        case PEA_E_WORKSPACE: return "workspace smaller than pea_workspace_bytes()";
+        case PEA_E_DTYPE: return "unknown mask / label dtype code";
+        case PEA_E_ALIGN: return "pointer not aligned for its element type";
+        case PEA_E_MODE: return "unknown border / variant code";
+        default: return "unknown pea error";
+    }
+}
+
+extern "C" size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, int cross) {
+    Dims d;
+    if (check_volume(B, C, D, H, W, K, d) != PEA_OK) return 0;
+    Workspace w;
+    carve(nullptr, B, d.N, K, cross, w);
+    return w.bytes;
+}
+
+extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
+                            const int32_t* offsets, int K, int border, int impl, float* affs, void* workspace,
+                            size_t ws_bytes, void* stream) {
+    (void)impl;
+    if (!emb || !offsets || !affs || !workspace) return PEA_E_NULL;
+    Dims d;
+    int rc = check_volume(B, C, D, H, W, K, d);
+    if (rc) return rc;
+    if (border != PEA_BORDER_WRAP && border != PEA_BORDER_ZERO) return PEA_E_MODE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
+    const int cross = partner != nullptr;
+    Workspace ws;
+    carve(workspace, B, d.N, K, cross, ws);
+    if (ws_bytes < ws.bytes) return PEA_E_WORKSPACE;
+    OffsetTable tab;
+    fill_offsets(offsets, K, tab);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
+    if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
+    return launch_fwd_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP, affs,
+                              st);
+}
+
+extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
+                                     const int32_t* offsets, int K, int border, int impl, const float* target,
+                                     const float* weight, const void* mask, int mask_dtype, const float* loss_norm,
+                                     const float* loss_coef, float* affs, float* loss_out, float* grad_emb,
+                                     float* grad_partner, void* workspace, size_t ws_bytes, void* stream) {
+    (void)impl;
+    if (!emb || !offsets || !target || !weight || !loss_norm || !loss_coef || !loss_out || !workspace) return PEA_E_NULL;
+    Dims d;
+    int rc = check_volume(B, C, D, H, W, K, d);
+    if (rc) return rc;
+    if (border != PEA_BORDER_WRAP && border != PEA_BORDER_ZERO) return PEA_E_MODE;
+    if (mask_dtype != PEA_MASK_NONE && mask_dtype != PEA_MASK_U8 && mask_dtype != PEA_MASK_F32) return PEA_E_DTYPE;
+    if (mask_dtype != PEA_MASK_NONE && !mask) return PEA_E_NULL;
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
+    const int cross = partner != nullptr;
+    if (!cross && grad_partner) return PEA_E_MODE;
+    Workspace ws;
+    carve(workspace, B, d.N, K, cross, ws);
+    if (ws_bytes < ws.bytes) return PEA_E_WORKSPACE;
+    OffsetTable tab;
+    fill_offsets(offsets, K, tab);
+    LossScale sc;
+    for (int k = 0; k < K; ++k) {
+        sc.norm[k] = loss_norm[k];
+        sc.coef[k] = loss_coef[k];
+        tab.gcoef[k] = (float)(2.0 * (double)loss_coef[k] / (double)loss_norm[k]);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
+    if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
+    rc = launch_fused_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP, cross,
+                              target, weight, mask, mask_dtype, nullptr, affs, ws.partials, grad_emb, grad_partner, st);
+    if (rc) return rc;
+    finalize_loss_kernel<<<1, 1024, 0, st>>>(ws.partials, generic_partial_blocks((int64_t)B * d.N), K, sc, loss_out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pea_affs_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
+                            const int32_t* offsets, int K, int border, const float* grad_affs, float* grad_emb,
+                            float* grad_partner, void* workspace, size_t ws_bytes, void* stream) {
+    if (!emb || !offsets || !grad_affs || !workspace) return PEA_E_NULL;
+    Dims d;
+    int rc = check_volume(B, C, D, H, W, K, d);
+    if (rc) return rc;
+    if (border != PEA_BORDER_WRAP && border != PEA_BORDER_ZERO) return PEA_E_MODE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
+    const int cross = partner != nullptr;
+    if (!cross && grad_partner) return PEA_E_MODE;
+    Workspace ws;
+    carve(workspace, B, d.N, K, cross, ws);
+    if (ws_bytes < ws.bytes) return PEA_E_WORKSPACE;
+    OffsetTable tab;
+    fill_offsets(offsets, K, tab);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
+    if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
+    return launch_fused_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP,
+                                cross, nullptr, nullptr, nullptr, PEA_MASK_NONE, grad_affs, nullptr, nullptr, grad_emb,
+                                grad_partner, st);
+}
+
+extern "C" int pea_scale_inplace(float* buf, int64_t n, const float* scale, void* stream) {
+    if (!buf || !scale) return PEA_E_NULL;
+    if (n <= 0) return PEA_E_SHAPE;
+    int64_t g = (n / 4 + 255) / 256;
+    const int grid = (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+    scale_inplace_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, n, scale);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,246 @@
+// Ground-truth generation on device: instance labels -> affinities / validity masks / class-balance weights.
+// Integer compares and exact counts: results are bit-identical to the reference's NumPy/SciPy code.
+//   gen_affs_ours        scripts_cvppp/utils/affinity_ours.py:17-39
+//   seg_to_aff           scripts_cvppp/data/data_affinity.py:53-102
+//   weight_binary_ratio  scripts_cvppp/data/data_segmentation.py:205-228
+#include "pea_common.cuh"
+
+namespace pea {
+
+struct GtTable {
+    int K;
+    int dz[PEA_MAX_OFFSETS];
+    int dy[PEA_MAX_OFFSETS];
+    int dx[PEA_MAX_OFFSETS];
+};
+
+// 2-D: aff = 1 where label == neighbour label (an out-of-image neighbour reads as 0, as scipy.ndimage.shift
+// with cval=0 does), optional `ignore` of pairs touching label 0, then the padding rule on out-of-image pairs.
+template <typename L>
+__global__ void __launch_bounds__(256)
+gt_affs2d_kernel(const L* __restrict__ labels, int B, int H, int W, GtTable tab, int ignore, int padding,
+                 float* __restrict__ affs, uint8_t* __restrict__ mask) {
+    const int64_t N = (int64_t)H * W, total = (int64_t)B * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / N, p = i - b * N;
+        const int x = (int)(p % W), y = (int)(p / W);
+        const L* lab = labels + b * N;
+        const L here = lab[p];
+        for (int k = 0; k < tab.K; ++k) {
+            const int qy = y + tab.dy[k], qx = x + tab.dx[k];
+            const bool inb = (unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W;
+            float a;
+            if (inb) {
+                const L there = __ldg(lab + (int64_t)qy * W + qx);
+                bool same = (here == there);
+                if (ignore) same = same && (here != (L)0) && (there != (L)0);
+                a = same ? 1.f : 0.f;
+            } else {
+                a = padding ? 1.f : 0.f;
+            }
+            const int64_t o = (b * tab.K + k) * N + p;
+            affs[o] = a;
+            if (mask != nullptr) mask[o] = inb ? 1 : 0;
+        }
+    }
+}
+
+// 3-D (or 2-D with D = 1): aff = (seg[p] == seg[p+n]) & seg[p] > 0 & seg[p+n] > 0 on the in-volume pairs, 0 elsewhere;
+// replicate_pad overwrites the first slice along axis e of channel e with seg > 0 (channels 0..2 only).
+// Signed label types compare `> 0` as the reference's NumPy does.
+template <typename L>
+__global__ void __launch_bounds__(256)
+gt_affs3d_kernel(const L* __restrict__ seg, int B, int D, int H, int W, GtTable tab, int replicate_pad, int nd,
+                 float* __restrict__ affs) {
+    const int64_t N = (int64_t)D * H * W, total = (int64_t)B * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / N, p = i - b * N;
+        const int x = (int)(p % W), y = (int)((p / W) % H), z = (int)(p / ((int64_t)W * H));
+        const L* s = seg + b * N;
+        const L here = s[p];
+        const bool fg = here > (L)0;
+        for (int k = 0; k < tab.K; ++k) {
+            const int qz = z + tab.dz[k], qy = y + tab.dy[k], qx = x + tab.dx[k];
+            float a = 0.f;
+            if ((unsigned)qz < (unsigned)D && (unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W) {
+                const L there = __ldg(s + ((int64_t)qz * H + qy) * W + qx);
+                a = (fg && there > (L)0 && here == there) ? 1.f : 0.f;
+            }
+            if (replicate_pad) {
+                // nd == 3: channel 0/1/2 <-> first slice along z/y/x;  nd == 2 (D == 1): channel 0/1 <-> y/x
+                const int first = (nd == 3) ? (k == 0 ? z : (k == 1 ? y : x)) : (k == 0 ? y : x);
+                if (first == 0) a = fg ? 1.f : 0.f;
+            }
+            affs[(b * tab.K + k) * N + p] = a;
+        }
+    }
+}
+
+// ---- weight_binary_ratio ------------------------------------------------------------------------
+// stats per channel: [0] count of non-zeros (u64), [1] ordered-int max, [2] ordered-int min (stored as u64)
+__device__ __forceinline__ int ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+
+__global__ void wbr_init_kernel(unsigned long long* stats, int n_channels) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_channels) {
+        stats[3 * c + 0] = 0ull;
+        reinterpret_cast<long long*>(stats)[3 * c + 1] = (long long)INT32_MIN;
+        reinterpret_cast<long long*>(stats)[3 * c + 2] = (long long)INT32_MAX;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wbr_count_kernel(const float* __restrict__ label, int64_t n, int chunks, unsigned long long* __restrict__ stats) {
+    const int ch = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const float* src = label + (int64_t)ch * n;
+    const int64_t per = (n + chunks - 1) / chunks;
+    const int64_t lo = (int64_t)chunk * per, hi = (lo + per < n) ? lo + per : n;
+    unsigned int cnt = 0;
+    int mx = INT32_MIN, mn = INT32_MAX;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float v = __ldg(src + i);
+        cnt += (v != 0.f) ? 1u : 0u;
+        const int o = ordered(v + 0.f);  // +0.f folds -0 onto +0 so that max == min matches float equality
+        mx = max(mx, o);
+        mn = min(mn, o);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats + 3 * ch + 0, (unsigned long long)cnt);
+        atomicMax(reinterpret_cast<long long*>(stats) + 3 * ch + 1, (long long)mx);
+        atomicMin(reinterpret_cast<long long*>(stats) + 3 * ch + 2, (long long)mn);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wbr_write_kernel(const float* __restrict__ label, int64_t n, int chunks, const unsigned long long* __restrict__ stats,
+                 double alpha, float* __restrict__ weight) {
+    const int ch = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const unsigned long long cnt = stats[3 * ch + 0];
+    const bool uniform = reinterpret_cast<const long long*>(stats)[3 * ch + 1] ==
+                         reinterpret_cast<const long long*>(stats)[3 * ch + 2];
+    float w_pos = 1.f, w_neg = 1.f;
+    if (!uniform) {
+        // Python float64 arithmetic of the reference, evaluated left to right
+        double wf = (double)cnt / (double)n;
+        wf = fmin(fmax(wf, 5e-2), 0.99);
+        if (wf > 0.5) {
+            w_pos = 1.f;
+            w_neg = (float)(alpha * wf / (1.0 - wf));
+        } else {
+            w_pos = (float)(alpha * (1.0 - wf) / wf);
+            w_neg = 1.f;
+        }
+    }
+    const float* src = label + (int64_t)ch * n;
+    float* dst = weight + (int64_t)ch * n;
+    const int64_t per = (n + chunks - 1) / chunks;
+    const int64_t lo = (int64_t)chunk * per, hi = (lo + per < n) ? lo + per : n;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = (__ldg(src + i) != 0.f) ? w_pos : w_neg;
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+static int grid1d(int64_t total) {
+    int64_t g = (total + 255) / 256;
+    return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+template <typename L>
+static int run_gt2d(const void* labels, int B, int H, int W, const GtTable& tab, int ignore, int padding, float* affs,
+                    uint8_t* mask, cudaStream_t st) {
+    gt_affs2d_kernel<L><<<grid1d((int64_t)B * H * W), 256, 0, st>>>(static_cast<const L*>(labels), B, H, W, tab, ignore,
+                                                                   padding, affs, mask);
+    return (int)cudaGetLastError();
+}
+
+template <typename L>
+static int run_gt3d(const void* seg, int B, int D, int H, int W, const GtTable& tab, int replicate_pad, int nd,
+                    float* affs, cudaStream_t st) {
+    gt_affs3d_kernel<L><<<grid1d((int64_t)B * D * H * W), 256, 0, st>>>(static_cast<const L*>(seg), B, D, H, W, tab,
+                                                                       replicate_pad, nd, affs);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pea
+
+using namespace pea;
+
+extern "C" int pea_gt_affs2d(const void* labels, int label_dtype, int B, int H, int W, const int32_t* offsets, int K,
+                             int ignore, int padding, float* affs, uint8_t* mask, void* stream) {
+    if (!labels || !offsets || !affs) return PEA_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0) return PEA_E_SHAPE;
+    if (K < 1 || K > PEA_MAX_OFFSETS) return PEA_E_OFFSETS;
+    GtTable tab;
+    tab.K = K;
+    for (int k = 0; k < K; ++k) { tab.dz[k] = 0; tab.dy[k] = offsets[2 * k]; tab.dx[k] = offsets[2 * k + 1]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (label_dtype) {
+        // equality and `!= 0` do not depend on signedness: same-width codes share a kernel
+        case PEA_LABEL_U8: case PEA_LABEL_S8: return run_gt2d<uint8_t>(labels, B, H, W, tab, ignore, padding, affs, mask, st);
+        case PEA_LABEL_U16: case PEA_LABEL_S16: return run_gt2d<uint16_t>(labels, B, H, W, tab, ignore, padding, affs, mask, st);
+        case PEA_LABEL_U32: case PEA_LABEL_S32: return run_gt2d<uint32_t>(labels, B, H, W, tab, ignore, padding, affs, mask, st);
+        case PEA_LABEL_U64: case PEA_LABEL_S64: return run_gt2d<uint64_t>(labels, B, H, W, tab, ignore, padding, affs, mask, st);
+        case PEA_LABEL_F32: return run_gt2d<float>(labels, B, H, W, tab, ignore, padding, affs, mask, st);
+        default: return PEA_E_DTYPE;
+    }
+}
+
+extern "C" int pea_gt_affs3d(const void* seg, int label_dtype, int B, int D, int H, int W, const int32_t* nhood, int K,
+                             int replicate_pad, float* affs, void* stream) {
+    if (!seg || !nhood || !affs) return PEA_E_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return PEA_E_SHAPE;
+    if (K < 1 || K > PEA_MAX_OFFSETS) return PEA_E_OFFSETS;
+    GtTable tab;
+    tab.K = K;
+    for (int k = 0; k < K; ++k) { tab.dz[k] = nhood[3 * k]; tab.dy[k] = nhood[3 * k + 1]; tab.dx[k] = nhood[3 * k + 2]; }
+    // replicate_pad: 3 -> three edges of a 3-D volume, 2 -> two edges of a 2-D image passed as D = 1
+    const int nd = (replicate_pad == 2) ? 2 : 3;
+    if (replicate_pad && K != nd) return PEA_E_MODE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the `seg > 0` test is signed exactly when the caller's dtype is
+    switch (label_dtype) {
+        case PEA_LABEL_U8: return run_gt3d<uint8_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_U16: return run_gt3d<uint16_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_U32: return run_gt3d<uint32_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_U64: return run_gt3d<uint64_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_S8: return run_gt3d<int8_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_S16: return run_gt3d<int16_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_S32: return run_gt3d<int32_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_S64: return run_gt3d<int64_t>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        case PEA_LABEL_F32: return run_gt3d<float>(seg, B, D, H, W, tab, replicate_pad, nd, affs, st);
+        default: return PEA_E_DTYPE;
+    }
+}
+
+extern "C" size_t pea_wbr_stats_bytes(int n_channels) {
+    return n_channels > 0 ? (size_t)n_channels * 3 * sizeof(unsigned long long) : 0;
+}
+
+extern "C" int pea_weight_binary_ratio(const float* label, int n_channels, int64_t n_per_channel, double alpha,
+                                       float* weight, void* stats, size_t stats_bytes, void* stream) {
+    if (!label || !weight || !stats) return PEA_E_NULL;
+    if (n_channels <= 0 || n_per_channel <= 0) return PEA_E_SHAPE;
+    if (stats_bytes < pea_wbr_stats_bytes(n_channels)) return PEA_E_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(stats) % 8) return PEA_E_ALIGN;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* s = static_cast<unsigned long long*>(stats);
+    // enough blocks per channel to fill the machine, at least ~16 K elements each
+    int64_t chunks = (148 * 8 + n_channels - 1) / n_channels;
+    const int64_t max_chunks = (n_per_channel + 16383) / 16384;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    if ((int64_t)n_channels * chunks > 0x7fffffffLL) return PEA_E_SHAPE;
+    wbr_init_kernel<<<(n_channels + 127) / 128, 128, 0, st>>>(s, n_channels);
+    wbr_count_kernel<<<(unsigned)(n_channels * chunks), 256, 0, st>>>(label, n_per_channel, (int)chunks, s);
+    wbr_write_kernel<<<(unsigned)(n_channels * chunks), 256, 0, st>>>(label, n_per_channel, (int)chunks, s, alpha,
+                                                                      weight);
+    return (int)cudaGetLastError();
+}

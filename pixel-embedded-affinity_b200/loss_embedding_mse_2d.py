@@ -1,0 +1,95 @@
+"""Drop-in for ``scripts_cvppp/loss/loss_embedding_mse.py`` and ``scripts_bbbc039v1/loss/loss_embedding_mse.py``.
+
+Same function names, positional order, defaults and return tuples as the reference (file:line below are under
+``scripts_cvppp/loss/loss_embedding_mse.py``); the work is done by the sm_100a kernels behind
+``include/pea_b200.h``.  One-line switch in ``scripts_cvppp/main.py:31``:
+
+    from pea_b200.loss_embedding_mse_2d import embedding_loss, ema_embedding_loss
+"""
+import numpy as np
+import torch
+
+from . import _ops as ops
+from ._autograd import Affinities, FusedAffinityLoss, LossList, OpSpec
+from .loss import is_weighted_mse
+
+
+def _check_mode(mode):
+    if mode != 'ours':
+        # the reference's other branch (nn.CosineSimilarity on un-normalised embeddings, :11-13) is not
+        # selected by any shipped config (cvppp.yaml:25, bbbc039v1.yaml dis_mode: 'ours')
+        raise NotImplementedError("pea_b200 implements mode='ours' (normalised dot product) only")
+
+
+def _norms_2d(B, W, K):
+    # WeightedMSE sees a (B, H, W) prediction: prod(size()[2:]) * size()[0] == W * B, in float32 (loss.py:114-116)
+    return np.full(K, np.float32(W) * np.float32(B), dtype=np.float32)
+
+
+def _prep(embedding, target, weightmap, mask, offsets):
+    embedding = ops.check_embedding("embedding", embedding, 4)
+    B, C, H, W = embedding.shape
+    offs3 = ops.offsets3(offsets, 2)
+    K = offs3.shape[0]
+    target = ops.check_like("target", target, (B, K, H, W))
+    weightmap = ops.check_like("weightmap", weightmap, (B, K, H, W))
+    mask = ops.check_like("mask", mask, (B, K, H, W), dtypes=(torch.float32, torch.uint8))
+    return embedding, target, weightmap, mask, offs3
+
+
+def embedding2affs(embedding, offsets, mode='ours'):
+    """:58-66.  (B,C,H,W) -> (B,K,H,W); affs[:,k][y,x] = <e^[y,x], e^[(y+dy)%H,(x+dx)%W]>."""
+    _check_mode(mode)
+    embedding = ops.check_embedding("embedding", embedding, 4)
+    return Affinities.apply(embedding, None, ops.offsets3(offsets, 2), ops.BORDER_WRAP, ops.IMPL_AUTO)
+
+
+def _generic_criterion(affs, target, weightmap, mask, criterion, coef):
+    """The reference loop (:35-46 / :87-94) for criteria the fused kernel does not implement."""
+    maskf = mask.float()
+    loss = torch.tensor(0, dtype=affs.dtype, device=affs.device)
+    each = []
+    for k in range(affs.shape[1]):
+        lk = criterion(affs[:, k] * maskf[:, k], target[:, k] * maskf[:, k], weightmap[:, k])
+        loss = loss + lk * coef[k] if coef[k] != 1 else loss + lk
+        each.append(lk)
+    return loss, each
+
+
+def embedding_loss(embedding, target, weightmap, mask, criterion, offsets, affs0_weight=1, mode='ours'):
+    """:18-47.  Returns (loss 0-dim tensor, affs (B,K,H,W) carrying grad, all_loss sequence of K floats).
+
+    ``affs0_weight`` is accepted and ignored, as in the reference (:26-33 vs the commented-out :38)."""
+    _check_mode(mode)
+    embedding, target, weightmap, mask, offs3 = _prep(embedding, target, weightmap, mask, offsets)
+    B, C, H, W = embedding.shape
+    K = offs3.shape[0]
+    if is_weighted_mse(criterion):
+        spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), np.ones(K, np.float32), affs_differentiable=True)
+        loss, affs, each = FusedAffinityLoss.apply(embedding, None, target, weightmap, mask, spec)
+        return loss, affs, LossList(each)
+    affs = Affinities.apply(embedding, None, offs3, ops.BORDER_WRAP, ops.IMPL_AUTO)
+    loss, each = _generic_criterion(affs, target, weightmap, mask, criterion, [1] * K)
+    return loss, affs, LossList(torch.stack([e.detach() for e in each]))
+
+
+def ema_embedding_loss(embedding, ema_embedding, target, weightmap, mask, criterion, offsets, affs0_weight=1,
+                       mode='ours'):
+    """:79-95.  Two-view variant: a = <e^[p], u^[p+o]>; offsets 0 and 1 are scaled by ``affs0_weight``.
+    Returns (loss, affs)."""
+    _check_mode(mode)
+    embedding, target, weightmap, mask, offs3 = _prep(embedding, target, weightmap, mask, offsets)
+    ema_embedding = ops.check_embedding("ema_embedding", ema_embedding, 4)
+    if ema_embedding.shape != embedding.shape:
+        raise ValueError(f"ema_embedding shape {tuple(ema_embedding.shape)} != embedding shape {tuple(embedding.shape)}")
+    B, C, H, W = embedding.shape
+    K = offs3.shape[0]
+    coef = np.ones(K, np.float32)
+    coef[:2] = affs0_weight
+    if is_weighted_mse(criterion):
+        spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), coef, affs_differentiable=True)
+        loss, affs, _ = FusedAffinityLoss.apply(embedding, ema_embedding, target, weightmap, mask, spec)
+        return loss, affs
+    affs = Affinities.apply(embedding, ema_embedding, offs3, ops.BORDER_WRAP, ops.IMPL_AUTO)
+    loss, _ = _generic_criterion(affs, target, weightmap, mask, criterion, [affs0_weight if k < 2 else 1 for k in range(K)])
+    return loss, affs

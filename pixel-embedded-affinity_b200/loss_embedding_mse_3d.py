@@ -1,0 +1,110 @@
+"""Drop-in for ``scripts_ac3ac4/loss/loss_embedding_mse.py`` (the functions main.py / inference.py import).
+
+Same names, positional order, defaults and return tuples as the reference (file:line below are under that
+file).  One-line switch in ``scripts_ac3ac4/main.py:36-37``:
+
+    from pea_b200.loss_embedding_mse_3d import embedding_loss_norm1, embedding_loss_norm5
+    from pea_b200.loss_embedding_mse_3d import ema_embedding_loss_norm1, ema_embedding_loss_norm5
+
+Channel i pairs voxel p with p - shift_i along axis i % 3 (0 = z, 1 = y, 2 = x); outside the valid region the
+returned affinity is 0 and nothing contributes to the loss; every channel has its own normaliser
+B * prod(cropped D,H,W); the returned affinities are detached (:186-190).
+"""
+import numpy as np
+import torch
+
+from . import _ops as ops
+from ._autograd import Affinities, FusedAffinityLoss, OpSpec
+from .loss import is_weighted_mse
+
+SHIFTS_NORM5 = [1, 1, 1, 2, 3, 3, 3, 9, 9, 4, 27, 27]  # :176
+
+
+def offsets_from_shifts(shifts):
+    """shift list -> (K,3) offsets: channel i looks back by shifts[i] along axis i % 3."""
+    offs = np.zeros((len(shifts), 3), dtype=np.int32)
+    for i, s in enumerate(shifts):
+        offs[i, i % 3] = -int(s)
+    return offs
+
+
+def _norms_3d(shape5, shifts):
+    B, _, D, H, W = shape5
+    norms = []
+    for i, s in enumerate(shifts):
+        ext = [D, H, W]
+        ext[i % 3] -= int(s)
+        if ext[i % 3] <= 0:
+            raise ValueError(f"shift {s} of channel {i} is not smaller than the axis length {ext[i % 3] + int(s)}; "
+                             "the reference's loss is undefined (0/0) for such a volume")
+        # torch.prod(torch.tensor(size()[2:]).float()) * size()[0], float32 (loss.py:114-116)
+        norms.append(np.prod(np.asarray(ext, dtype=np.float32), dtype=np.float32) * np.float32(B))
+    return np.asarray(norms, dtype=np.float32)
+
+
+def _loss3d(embedding, ema_embedding, target, weightmap, criterion, shifts, affs0_weight, weighted_upto):
+    embedding = ops.check_embedding("embedding", embedding, 5)
+    if ema_embedding is not None:
+        ema_embedding = ops.check_embedding("ema_embedding", ema_embedding, 5)
+        if ema_embedding.shape != embedding.shape:
+            raise ValueError("ema_embedding and embedding shapes differ")
+    B, C, D, H, W = embedding.shape
+    K = len(shifts)
+    target = ops.check_like("target", target, (B, K, D, H, W))
+    weightmap = ops.check_like("weightmap", weightmap, (B, K, D, H, W))
+    offs3 = offsets_from_shifts(shifts)
+    norms = _norms_3d(embedding.shape, shifts)
+    coef = np.ones(K, np.float32)
+    coef[:weighted_upto] = affs0_weight
+    if is_weighted_mse(criterion):
+        spec = OpSpec(offs3, ops.BORDER_ZERO, norms, coef, affs_differentiable=False)
+        loss, affs, _ = FusedAffinityLoss.apply(embedding, ema_embedding, target, weightmap, None, spec)
+        return loss, affs
+    # any other criterion: CUDA affinity op + the reference's per-channel cropped criterion calls (:159-163)
+    affs = Affinities.apply(embedding, ema_embedding, offs3, ops.BORDER_ZERO, ops.IMPL_AUTO)
+    loss = 0
+    for i, s in enumerate(shifts):
+        idx = [slice(None), slice(i, i + 1), slice(None), slice(None), slice(None)]
+        idx[2 + i % 3] = slice(int(s), None)
+        idx = tuple(idx)
+        li = criterion(affs[idx], target[idx], weightmap[idx])
+        loss = loss + (li * affs0_weight if i < weighted_upto else li)
+    return loss, affs.detach()
+
+
+def embedding_loss_norm5(embedding, target, weightmap, criterion, affs0_weight=1, shift=1, fill=True):
+    """:169-194 -- 12 channels; ``shift`` and ``fill`` are accepted and unused, as in the reference."""
+    return _loss3d(embedding, None, target, weightmap, criterion, SHIFTS_NORM5, affs0_weight, 3)
+
+
+def embedding_loss_norm1(embedding, target, weightmap, criterion, affs0_weight=1, shift=1, fill=True):
+    """:7-27 -- 3 channels at one shift; only the z channel is scaled by ``affs0_weight`` (:20)."""
+    return _loss3d(embedding, None, target, weightmap, criterion, [shift] * 3, affs0_weight, 1)
+
+
+def ema_embedding_loss_norm5(embedding, ema_embedding, target, weightmap, criterion, affs0_weight=1, shift=1,
+                             fill=True):
+    """:263-289 -- a_i[p] = <e^[p], u^[p - s_i]>."""
+    return _loss3d(embedding, ema_embedding, target, weightmap, criterion, SHIFTS_NORM5, affs0_weight, 3)
+
+
+def ema_embedding_loss_norm1(embedding, ema_embedding, target, weightmap, criterion, affs0_weight=1, shift=1,
+                             fill=True):
+    """:30-51"""
+    return _loss3d(embedding, ema_embedding, target, weightmap, criterion, [shift] * 3, affs0_weight, 1)
+
+
+def _inf3d(embedding, shifts):
+    embedding = ops.check_embedding("embedding", embedding, 5)
+    with torch.no_grad():
+        return ops.affs_fwd(embedding.detach(), None, offsets_from_shifts(shifts), ops.BORDER_ZERO)
+
+
+def inf_embedding_loss_norm5(embedding):
+    """:212-234 -- forward only, (B,12,D,H,W)."""
+    return _inf3d(embedding, SHIFTS_NORM5)
+
+
+def inf_embedding_loss_norm1(embedding, shift=1):
+    """:54-67 -- forward only, (B,3,D,H,W)."""
+    return _inf3d(embedding, [shift] * 3)

@@ -1,0 +1,95 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/pea_b200.h declares, the host-side
+logic (offset tables, normalisers, argument validation) matches the reference's conventions.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "pea_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pea_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import pea_b200
+    lib = ctypes.CDLL(pea_b200._lib.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 11
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pea_b200.h but not exported"
+        assert n in pea_b200._lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert set(pea_b200._lib.SIGNATURES) == set(names)
+
+
+def test_abi_version_and_strerror():
+    import pea_b200
+    lib = pea_b200._lib.lib
+    assert lib.pea_abi_version() == 1
+    assert lib.pea_strerror(0) == b"ok"
+    assert b"channel" in lib.pea_strerror(-3)
+    assert lib.pea_workspace_bytes(1, 16, 1, 8, 8, 2, 0) > 0
+    assert lib.pea_workspace_bytes(1, 7, 1, 8, 8, 2, 0) == 0      # unsupported channel count
+    assert lib.pea_workspace_bytes(1, 16, 1, 8, 8, 65, 0) == 0    # too many offsets
+    assert lib.pea_wbr_stats_bytes(12) == 12 * 24
+
+
+def test_argument_rejection_without_touching_the_device():
+    """NULL pointers / bad shapes are refused before any CUDA call."""
+    import pea_b200
+    lib = pea_b200._lib.lib
+    offs = (ctypes.c_int32 * 6)(0, -1, 0, 0, 0, -1)
+    assert lib.pea_affs_fwd(None, None, 1, 16, 1, 8, 8, offs, 2, 0, 0, None, None, 0, None) == -1
+    one = ctypes.c_void_p(16)
+    assert lib.pea_affs_fwd(one, None, 0, 16, 1, 8, 8, offs, 2, 0, 0, one, one, 0, None) == -2
+    assert lib.pea_affs_fwd(one, None, 1, 5, 1, 8, 8, offs, 2, 0, 0, one, one, 0, None) == -3
+    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 0, 0, 0, one, one, 0, None) == -4
+    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 2, 7, 0, one, one, 0, None) == -8
+    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 2, 0, 0, one, one, 0, None) == -5
+    assert lib.pea_gt_affs2d(one, 99, 1, 8, 8, offs, 2, 0, 1, one, one, None) == -6
+
+
+def test_offset_tables_match_reference_convention(golden):
+    import pea_b200
+    g = golden["gt"]
+    np.testing.assert_array_equal(np.asarray(pea_b200.multi_offset([1, 3, 5, 9, 27], neighbor=4)), g["multi_offset_cvppp"])
+    np.testing.assert_array_equal(np.asarray(pea_b200.multi_offset([1, 2], neighbor=8)), g["multi_offset_n8"])
+    np.testing.assert_array_equal(pea_b200.mknhood3d(1), g["mknhood3d"])
+    with pytest.raises(AssertionError):
+        pea_b200.gen_offsets(1, neighbor=6)
+    from pea_b200.loss_embedding_mse_3d import offsets_from_shifts, SHIFTS_NORM5, _norms_3d
+    from pea_b200.data_affinity import NHOOD_NORM5
+    np.testing.assert_array_equal(offsets_from_shifts(SHIFTS_NORM5), NHOOD_NORM5)
+    norms = _norms_3d((4, 16, 18, 160, 160), SHIFTS_NORM5)
+    assert norms[0] == 4 * 17 * 160 * 160 and norms[10] == 4 * 18 * 133 * 160 and norms[11] == 4 * 18 * 160 * 133
+    with pytest.raises(ValueError):
+        _norms_3d((1, 16, 4, 30, 30), SHIFTS_NORM5)
+
+
+def test_cpu_tensors_are_refused_loudly():
+    import pea_b200
+    e = torch.randn(1, 16, 8, 8)
+    t = torch.zeros(1, 2, 8, 8)
+    with pytest.raises(ValueError, match="no CPU path"):
+        pea_b200.embedding_loss(e, t, t, t, pea_b200.WeightedMSE(), [[-1, 0], [0, -1]])
+    with pytest.raises(ValueError, match="no CPU path"):
+        pea_b200.embedding2affs(e, [[-1, 0]])
+    with pytest.raises(TypeError):
+        pea_b200.embedding2affs(np.zeros((1, 16, 8, 8), np.float32), [[-1, 0]])
+    with pytest.raises(NotImplementedError):
+        pea_b200.embedding2affs(e, [[-1, 0]], mode='cos')
+
+
+def test_weighted_mse_matches_oracle_criterion():
+    import pea_b200
+    from oracle import pea_oracle as O
+    p, t, w = torch.randn(2, 5, 7), torch.rand(2, 5, 7), torch.rand(2, 5, 7)
+    assert torch.equal(pea_b200.WeightedMSE()(p, t, w), O.WeightedMSE()(p, t, w))
+    p5 = torch.randn(2, 1, 3, 5, 7)
+    assert torch.equal(pea_b200.WeightedMSE()(p5, p5 * 0, None), O.WeightedMSE()(p5, p5 * 0, None))

@@ -1,0 +1,427 @@
+"""GPU parity: the CUDA path (through the C ABI) against (1) the committed golden vectors produced by the real
+reference and (2) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): ground-truth affinities, masks and weights bit-exact; affinities, loss and
+embedding gradients within 1e-5 relative in fp32.  "Relative" for a tensor is measured against its largest
+magnitude (inf-norm): |ours - ref|_inf <= 1e-5 * |ref|_inf; scalar losses use plain relative error.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def dev(a, grad=False):
+    t = torch.tensor(np.asarray(a)).cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+def close_t(ours, ref, rtol=RTOL, what=""):
+    ours = ours.detach().cpu().numpy() if isinstance(ours, torch.Tensor) else np.asarray(ours)
+    ref = ref.detach().cpu().numpy() if isinstance(ref, torch.Tensor) else np.asarray(ref)
+    assert ours.shape == ref.shape, (what, ours.shape, ref.shape)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    err = float(np.abs(ours.astype(np.float64) - ref.astype(np.float64)).max())
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} > {rtol:g} * {scale:.3e}"
+
+
+def close_s(ours, ref, rtol=RTOL, what=""):
+    ours, ref = float(ours), float(ref)
+    assert abs(ours - ref) <= rtol * max(abs(ref), 1e-30), f"{what}: {ours!r} vs {ref!r}"
+
+
+def same(ours, ref, what=""):
+    ours = ours.detach().cpu().numpy() if isinstance(ours, torch.Tensor) else np.asarray(ours)
+    assert ours.dtype == np.asarray(ref).dtype, (what, ours.dtype, np.asarray(ref).dtype)
+    np.testing.assert_array_equal(ours, np.asarray(ref), err_msg=what)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pea_b200
+    return pea_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pea_oracle
+    return pea_oracle
+
+
+# =========================================================================== golden vectors: 2D
+def test_golden_embedding_loss_2d(P, golden):
+    g = golden["loss2d"]
+    offsets = g["offsets"].tolist()
+    e = dev(g["embedding"], True)
+    loss, affs, all_loss = P.embedding_loss(e, dev(g["target"]), dev(g["weightmap"]), dev(g["mask"]), P.WeightedMSE(),
+                                            offsets, affs0_weight=3)
+    assert loss.dim() == 0 and loss.dtype == torch.float32 and affs.requires_grad
+    loss.backward()
+    close_s(loss, g["loss"], what="loss")
+    close_t(affs, g["affs"], what="affs")
+    assert len(all_loss) == len(offsets)
+    for k in range(len(offsets)):
+        close_s(all_loss[k], g["all_loss"][k], what=f"all_loss[{k}]")
+    # the golden batch contains one exact-zero pixel (F.normalize eps branch, gradient ~1e12 * G): check it apart
+    zero = np.broadcast_to((g["embedding"] == 0).all(axis=1, keepdims=True), g["grad"].shape)
+    ours = e.grad.cpu().numpy()
+    close_t(np.where(zero, 0, ours), np.where(zero, 0, g["grad"]), what="grad")
+    close_t(ours[zero], g["grad"][zero], rtol=1e-4, what="grad at the zero-norm pixel")
+    close_t(P.embedding2affs(dev(g["embedding"]), offsets), g["embedding2affs"], what="embedding2affs")
+
+
+def test_golden_embedding_loss_2d_float_mask_and_affs_grad(P, golden):
+    g = golden["loss2d"]
+    offsets = g["offsets"].tolist()
+    crit = P.WeightedMSE()
+    loss, _, _ = P.embedding_loss(dev(g["embedding"]), dev(g["target"]), dev(g["weightmap"]), dev(g["mask"]).float(),
+                                  crit, offsets)
+    close_s(loss, g["loss_fmask"], what="loss with float mask")
+    e = dev(g["embedding"], True)
+    loss, affs, _ = P.embedding_loss(e, dev(g["target"]), dev(g["weightmap"]), dev(g["mask"]), crit, offsets)
+    (0.5 * loss + (affs * dev(g["affs_upstream"])).sum()).backward()
+    zero = np.broadcast_to((g["embedding"] == 0).all(axis=1, keepdims=True), g["grad"].shape)
+    close_t(np.where(zero, 0, e.grad.cpu().numpy()), np.where(zero, 0, g["grad_with_affs"]), what="grad through loss+affs")
+
+
+def test_golden_ema_embedding_loss_2d(P, golden):
+    g = golden["loss2d"]
+    offsets = g["offsets"].tolist()
+    e, u = dev(g["embedding"], True), dev(g["ema_embedding"], True)
+    loss, affs = P.ema_embedding_loss(e, u, dev(g["target"]), dev(g["weightmap"]), dev(g["mask"]), P.WeightedMSE(),
+                                      offsets, affs0_weight=3)
+    loss.backward()
+    close_s(loss, g["ema_loss"], what="ema loss")
+    close_t(affs, g["ema_affs"], what="ema affs")
+    zero = np.broadcast_to((g["embedding"] == 0).all(axis=1, keepdims=True), g["grad"].shape)
+    close_t(np.where(zero, 0, e.grad.cpu().numpy()), np.where(zero, 0, g["ema_grad"]), what="ema grad")
+    close_t(u.grad, g["ema_grad_partner"], what="ema grad wrt partner")
+
+
+# =========================================================================== golden vectors: 3D
+def test_golden_norm5_family(P, golden):
+    g = golden["loss3d"]
+    crit = P.WeightedMSE()
+    e = dev(g["A_embedding"], True)
+    loss, affs = P.embedding_loss_norm5(e, dev(g["A_target"]), dev(g["A_weightmap"]), crit, affs0_weight=2)
+    assert not affs.requires_grad
+    loss.backward()
+    close_s(loss, g["A_n5_loss"], what="norm5 loss")
+    close_t(affs, g["A_n5_affs"], what="norm5 affs")
+    close_t(e.grad, g["A_n5_grad"], what="norm5 grad")
+
+    e, u = dev(g["A_embedding"], True), dev(g["A_ema_embedding"], True)
+    loss, affs = P.ema_embedding_loss_norm5(e, u, dev(g["A_target"]), dev(g["A_weightmap"]), crit, affs0_weight=2)
+    loss.backward()
+    close_s(loss, g["A_ema5_loss"], what="ema5 loss")
+    close_t(affs, g["A_ema5_affs"], what="ema5 affs")
+    close_t(e.grad, g["A_ema5_grad"], what="ema5 grad")
+    close_t(u.grad, g["A_ema5_grad_partner"], what="ema5 grad wrt partner")
+    close_t(P.inf_embedding_loss_norm5(dev(g["A_embedding"])), g["A_inf5"], what="inf5")
+
+
+def test_golden_norm1_family(P, golden):
+    g = golden["loss3d"]
+    crit = P.WeightedMSE()
+    T, W = dev(g["B_target"]), dev(g["B_weightmap"])
+    e = dev(g["B_embedding"], True)
+    loss, affs = P.embedding_loss_norm1(e, T, W, crit, affs0_weight=2)
+    loss.backward()
+    close_s(loss, g["B_n1_loss"], what="norm1 loss")
+    close_t(affs, g["B_n1_affs"], what="norm1 affs")
+    close_t(e.grad, g["B_n1_grad"], what="norm1 grad")
+
+    e = dev(g["B_embedding"], True)
+    loss, affs = P.embedding_loss_norm1(e, T, W, crit, affs0_weight=0.5, shift=2)
+    loss.backward()
+    close_s(loss, g["B_n1s2_loss"], what="norm1 shift 2 loss")
+    close_t(affs, g["B_n1s2_affs"], what="norm1 shift 2 affs")
+    close_t(e.grad, g["B_n1s2_grad"], what="norm1 shift 2 grad")
+
+    e, u = dev(g["B_embedding"], True), dev(g["B_ema_embedding"], True)
+    loss, affs = P.ema_embedding_loss_norm1(e, u, T, W, crit, affs0_weight=2)
+    loss.backward()
+    close_s(loss, g["B_ema1_loss"], what="ema1 loss")
+    close_t(affs, g["B_ema1_affs"], what="ema1 affs")
+    close_t(e.grad, g["B_ema1_grad"], what="ema1 grad")
+    close_t(u.grad, g["B_ema1_grad_partner"], what="ema1 grad wrt partner")
+    close_t(P.inf_embedding_loss_norm1(dev(g["B_embedding"])), g["B_inf1"], what="inf1")
+
+
+# =========================================================================== golden vectors: ground truth (bit exact)
+def test_golden_gen_affs_ours(P, golden):
+    g = golden["gt"]
+    lab, offsets = g["gt2d_labels"], g["gt2d_offsets"].tolist()
+    for ig in (False, True):
+        for pd in (False, True):
+            a, m = P.gen_affs_ours(lab, offsets, ignore=ig, padding=pd)            # NumPy in -> NumPy out
+            assert isinstance(a, np.ndarray) and isinstance(m, np.ndarray)
+            same(a, g[f"gt2d_aff_i{int(ig)}_p{int(pd)}"], "aff")
+            same(m, g[f"gt2d_msk_i{int(ig)}_p{int(pd)}"], "mask")
+            a, m = P.gen_affs_ours(torch.tensor(lab).cuda(), offsets, ignore=ig, padding=pd)  # tensor in -> tensor out
+            assert a.is_cuda and m.is_cuda
+            same(a, g[f"gt2d_aff_i{int(ig)}_p{int(pd)}"], "aff (device)")
+            same(m, g[f"gt2d_msk_i{int(ig)}_p{int(pd)}"], "mask (device)")
+    a, m = P.gen_affs_ours(lab.astype(np.float32), offsets, ignore=False, padding=True)
+    same(a, g["gt2d_aff_float_labels"])
+    same(m, g["gt2d_msk_float_labels"].astype(np.uint8))
+    for dt in (np.int16, np.int32, np.int64, np.uint16):
+        a, m = P.gen_affs_ours(lab.astype(dt), offsets, ignore=True, padding=False)
+        same(a, g["gt2d_aff_i1_p0"], f"labels as {dt.__name__}")
+
+
+def test_golden_seg_to_aff(P, golden):
+    g = golden["gt"]
+    lab3 = g["gt3d_labels"]
+    from pea_b200.data_affinity import NHOOD_NORM5
+    same(P.seg_to_aff(lab3, NHOOD_NORM5, pad=''), g["gt3d_aff12"], "12-channel")
+    for i in range(4):
+        same(P.seg_to_aff(lab3, NHOOD_NORM5[3 * i:3 * i + 3], pad=''), g["gt3d_aff12"][3 * i:3 * i + 3], f"nhood {i}")
+    same(P.seg_to_aff(lab3), g["gt3d_aff3_replicate"], "replicate")
+    same(P.seg_to_aff(lab3, pad=''), g["gt3d_aff3_nopad"], "no pad")
+    same(P.seg_to_aff(g["gt2d_labels"], np.asarray([[-1, 0], [0, -1]])), g["gt3d_aff_2dseg_replicate"], "2-D seg")
+    same(P.seg_to_aff(torch.tensor(lab3.astype(np.int32)).cuda()), g["gt3d_aff3_replicate"], "device int32")
+    same(P.seg_to_aff(lab3.astype(np.int64)), g["gt3d_aff3_replicate"], "int64")
+
+
+def test_golden_weight_binary_ratio(P, golden):
+    g = golden["gt"]
+    for cin, cout in zip(g["wbr_in"], g["wbr_out"]):
+        same(P.weight_binary_ratio(cin), cout)
+    same(np.stack([P.weight_binary_ratio(c) for c in g["gt3d_aff12"]]), g["gt3d_w12"])
+    same(np.stack([P.weight_binary_ratio(c) for c in g["gt2d_aff_i0_p1"]]), g["gt2d_w"])
+    # batched device path: one problem per (sample, channel)
+    lab3 = torch.tensor(g["gt3d_labels"].astype(np.int32)).cuda()
+    tgt, w = P.make_targets_3d(torch.stack([lab3, lab3]))
+    same(tgt[1], g["gt3d_aff12"])
+    same(w[0], g["gt3d_w12"])
+    same(w[1], g["gt3d_w12"])
+    lab2 = torch.tensor(g["gt2d_labels"]).cuda()
+    tgt, msk, w = P.make_targets_2d(lab2[None], g["gt2d_offsets"].tolist())
+    same(tgt[0], g["gt2d_aff_i0_p1"])
+    same(msk[0], g["gt2d_msk_i0_p1"])
+    same(w[0], g["gt2d_w"])
+
+
+# =========================================================================== CUDA vs oracle on seeded inputs
+def _inputs_2d(O, B, C, H, W, offsets, seed, float_mask=False):
+    rng = np.random.RandomState(seed)
+    emb = rng.randn(B, C, H, W).astype(np.float32) * rng.uniform(0.2, 3.0)
+    ema = rng.randn(B, C, H, W).astype(np.float32)
+    K = len(offsets)
+    tgt = np.zeros((B, K, H, W), np.float32)
+    msk = np.zeros((B, K, H, W), np.uint8)
+    wgt = np.zeros((B, K, H, W), np.float32)
+    for b in range(B):
+        lab = O.voronoi_labels((H, W), 9, seed * 10 + b)
+        tgt[b], msk[b] = O.gen_affs_ours(lab, offsets, ignore=False, padding=True)
+        wgt[b] = np.stack([O.weight_binary_ratio(c) for c in tgt[b]])
+    return emb, ema, tgt, wgt, (msk.astype(np.float32) if float_mask else msk)
+
+
+@pytest.mark.parametrize("B,C,H,W,shifts,nb,seed", [
+    (2, 16, 37, 53, [1, 3, 5, 9, 27], 4, 1),      # odd extents, CVPPP offsets
+    (1, 16, 40, 48, [1, 3, 5, 9, 11], 8, 2),      # BBBC offsets with diagonals
+    (3, 8, 16, 16, [1, 20], 4, 3),                # shift larger than the image (wraps modulo)
+    (1, 4, 9, 130, [2], 4, 4),
+    (2, 32, 21, 33, [1, 4], 8, 5),
+])
+def test_oracle_2d(P, O, B, C, H, W, shifts, nb, seed):
+    offsets = O.multi_offset(shifts, neighbor=nb)
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, B, C, H, W, offsets, seed, float_mask=(seed % 2 == 0))
+    # oracle (CPU)
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao, allo = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), O.WeightedMSE(), offsets)
+    lo.backward()
+    # CUDA
+    e = dev(emb, True)
+    l, a, al = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    l.backward()
+    close_s(l, lo, what="loss")
+    close_t(a, ao, what="affs")
+    close_t(np.asarray(list(al)), np.asarray(allo), what="all_loss")
+    close_t(e.grad, eo.grad, what="grad")
+    # cross variant, gradient wrt both views
+    eo, uo = torch.tensor(emb, requires_grad=True), torch.tensor(ema, requires_grad=True)
+    lo, ao = O.ema_embedding_loss(eo, uo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), O.WeightedMSE(),
+                                  offsets, affs0_weight=0.25)
+    lo.backward()
+    e, u = dev(emb, True), dev(ema, True)
+    l, a = P.ema_embedding_loss(e, u, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets, affs0_weight=0.25)
+    l.backward()
+    close_s(l, lo, what="ema loss")
+    close_t(a, ao, what="ema affs")
+    close_t(e.grad, eo.grad, what="ema grad")
+    close_t(u.grad, uo.grad, what="ema grad partner")
+    # detached partner (the shipped training loops, data_consistency.py:36): only the first view gets a gradient
+    e = dev(emb, True)
+    l, _ = P.ema_embedding_loss(e, dev(ema), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets, affs0_weight=0.25)
+    (3.0 * l).backward()
+    close_t(e.grad, 3.0 * eo.grad, what="ema grad, scaled upstream")
+
+
+def test_non_fused_criterion_2d(P, O):
+    """Criteria other than WeightedMSE run the CUDA affinity op + the criterion in PyTorch, like the reference loop."""
+    offsets = O.multi_offset([1, 3], neighbor=4)
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, 2, 16, 20, 24, offsets, 7)
+    for crit_o, crit_p in ((torch.nn.MSELoss(), P.MSELoss()),):
+        eo = torch.tensor(emb, requires_grad=True)
+        lo, ao, allo = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk),
+                                        lambda p, t, w: crit_o(p, t), offsets)
+        lo.backward()
+        e = dev(emb, True)
+        l, a, al = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), crit_p, offsets)
+        l.backward()
+        close_s(l, lo, what="MSELoss loss")
+        close_t(e.grad, eo.grad, what="MSELoss grad")
+        close_t(np.asarray(list(al)), np.asarray(allo), what="MSELoss all_loss")
+
+
+def _inputs_3d(O, B, C, D, H, W, K, seed, replicate=False):
+    rng = np.random.RandomState(seed)
+    emb = rng.randn(B, C, D, H, W).astype(np.float32) * rng.uniform(0.2, 3.0)
+    ema = rng.randn(B, C, D, H, W).astype(np.float32)
+    tgt = np.zeros((B, K, D, H, W), np.float32)
+    wgt = np.zeros_like(tgt)
+    for b in range(B):
+        lab = O.voronoi_labels((D, H, W), 12, seed * 10 + b, z_scale=4.0, dtype=np.uint16)
+        tgt[b] = O.seg_to_aff_norm5(lab) if K == 12 else O.seg_to_aff(lab, pad='replicate' if replicate else '')
+        wgt[b] = np.stack([O.weight_binary_ratio(c) for c in tgt[b]])
+    return emb, ema, tgt, wgt
+
+
+@pytest.mark.parametrize("B,C,D,H,W,seed", [(2, 16, 7, 31, 45, 11), (1, 16, 18, 40, 36, 12), (1, 8, 5, 28, 28, 13)])
+def test_oracle_norm5(P, O, B, C, D, H, W, seed):
+    emb, ema, tgt, wgt = _inputs_3d(O, B, C, D, H, W, 12, seed)
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao = O.embedding_loss_norm5(eo, torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(), affs0_weight=1.5)
+    lo.backward()
+    e = dev(emb, True)
+    l, a = P.embedding_loss_norm5(e, dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=1.5)
+    l.backward()
+    close_s(l, lo, what="loss")
+    close_t(a, ao, what="affs")
+    close_t(e.grad, eo.grad, what="grad")
+    close_t(P.inf_embedding_loss_norm5(dev(emb)), ao, what="inf5 == loss affs")
+    eo, uo = torch.tensor(emb, requires_grad=True), torch.tensor(ema, requires_grad=True)
+    lo, ao = O.ema_embedding_loss_norm5(eo, uo, torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(), affs0_weight=1.5)
+    lo.backward()
+    e, u = dev(emb, True), dev(ema, True)
+    l, a = P.ema_embedding_loss_norm5(e, u, dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=1.5)
+    l.backward()
+    close_s(l, lo, what="ema loss")
+    close_t(a, ao, what="ema affs")
+    close_t(e.grad, eo.grad, what="ema grad")
+    close_t(u.grad, uo.grad, what="ema grad partner")
+
+
+@pytest.mark.parametrize("B,C,D,H,W,shift,seed", [(2, 16, 18, 10, 10, 1, 21), (2, 16, 18, 20, 20, 1, 22),
+                                                   (1, 16, 6, 17, 23, 2, 23)])
+def test_oracle_norm1_deep_supervision_scales(P, O, B, C, D, H, W, shift, seed):
+    """The /16 and /8 deep-supervision volumes of scripts_ac3ac4/main.py:227-230 (18 x 10 x 10, 18 x 20 x 20)."""
+    emb, ema, tgt, wgt = _inputs_3d(O, B, C, D, H, W, 3, seed, replicate=True)
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao = O.embedding_loss_norm1(eo, torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(), affs0_weight=2, shift=shift)
+    lo.backward()
+    e = dev(emb, True)
+    l, a = P.embedding_loss_norm1(e, dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=2, shift=shift)
+    l.backward()
+    close_s(l, lo, what="loss")
+    close_t(a, ao, what="affs")
+    close_t(e.grad, eo.grad, what="grad")
+    close_t(P.inf_embedding_loss_norm1(dev(emb), shift=shift), ao, what="inf1")
+
+
+def test_oracle_gt_random_shapes(P, O):
+    rng = np.random.RandomState(5)
+    for trial in range(6):
+        H, W = int(rng.randint(1, 70)), int(rng.randint(1, 90))
+        lab = O.voronoi_labels((H, W), 6, 100 + trial)
+        offsets = O.multi_offset([1, 3, 9, 27], neighbor=8) + [[int(rng.randint(-80, 80)), int(rng.randint(-80, 80))]]
+        for ig in (False, True):
+            a, m = P.gen_affs_ours(lab, offsets, ignore=ig, padding=True)
+            ao, mo = O.gen_affs_ours(lab, offsets, ignore=ig, padding=True)
+            same(a, ao)
+            same(m, mo)
+        for k in range(0, len(offsets), 5):
+            same(P.weight_binary_ratio(ao[k]), O.weight_binary_ratio(ao[k]))
+    for trial in range(3):
+        D, H, W = int(rng.randint(5, 12)), int(rng.randint(28, 50)), int(rng.randint(28, 50))
+        lab = O.voronoi_labels((D, H, W), 15, 200 + trial, z_scale=3.0, dtype=np.uint16)
+        from pea_b200.data_affinity import NHOOD_NORM5
+        same(P.seg_to_aff(lab, NHOOD_NORM5, pad=''), O.seg_to_aff_norm5(lab))
+        same(P.seg_to_aff(lab), O.seg_to_aff(lab))
+    # all-background and single-label volumes
+    z = np.zeros((4, 6, 7), np.uint8)
+    same(P.seg_to_aff(z), O.seg_to_aff(z))
+    same(P.weight_binary_ratio(O.seg_to_aff(z)[0]), O.weight_binary_ratio(O.seg_to_aff(z)[0]))
+    one = np.full((4, 6, 7), 3, np.uint8)
+    same(P.seg_to_aff(one), O.seg_to_aff(one))
+    a, m = P.gen_affs_ours(one[0], [[-1, 0], [0, 2]], padding=True)
+    ao, mo = O.gen_affs_ours(one[0], [[-1, 0], [0, 2]], padding=True)
+    same(a, ao)
+    same(m, mo)
+
+
+# =========================================================================== autograd plumbing
+def test_backward_scaling_retain_graph_and_no_grad(P, O):
+    offsets = O.multi_offset([1, 3], neighbor=4)
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, 1, 16, 24, 28, offsets, 31)
+    e = dev(emb, True)
+    l, _, _ = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    l.backward(retain_graph=True)
+    g1 = e.grad.clone()
+    e.grad = None
+    (2.5 * l).backward()           # second backward through the same node: recomputed, then scaled
+    close_t(e.grad, 2.5 * g1, what="retain_graph + scaled upstream")
+    with torch.no_grad():
+        l2, a2, _ = P.embedding_loss(dev(emb), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    assert not l2.requires_grad and not a2.requires_grad
+    close_s(l2, l, rtol=1e-7)
+    # determinism: the loss reduction has a fixed order
+    l3, _, _ = P.embedding_loss(dev(emb), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    assert float(l3) == float(l2)
+
+
+def test_non_contiguous_and_wrong_inputs(P, O):
+    offsets = [[-1, 0], [0, -1]]
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, 2, 16, 12, 14, offsets, 41)
+    e_nc = dev(np.ascontiguousarray(emb.transpose(0, 1, 3, 2))).transpose(2, 3)   # non-contiguous view
+    assert not e_nc.is_contiguous()
+    l1, a1, _ = P.embedding_loss(e_nc, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    l2, a2, _ = P.embedding_loss(dev(emb), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    assert float(l1) == float(l2) and torch.equal(a1, a2)
+    with pytest.raises(ValueError):
+        P.embedding_loss(dev(emb), dev(tgt[:, :1]), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    with pytest.raises(TypeError):
+        P.embedding_loss(dev(emb).double(), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+    with pytest.raises(ValueError):
+        P.embedding_loss(dev(emb[:, :5]), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)  # C = 5
+
+
+def test_cuda_graph_capture(P, O):
+    """No host synchronisation inside forward or backward: the whole step captures into a CUDA graph."""
+    offsets = O.multi_offset([1, 3], neighbor=4)
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, 1, 16, 32, 32, offsets, 51)
+    e = dev(emb, True)
+    T, Wm, M = dev(tgt), dev(wgt), dev(msk)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            l, _, _ = P.embedding_loss(e, T, Wm, M, P.WeightedMSE(), offsets)
+            l.backward()
+    torch.cuda.current_stream().wait_stream(s)
+    ref_grad = e.grad.clone() / 2
+    e.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        l, _, _ = P.embedding_loss(e, T, Wm, M, P.WeightedMSE(), offsets)
+        l.backward()
+    e.grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    close_t(e.grad, ref_grad, what="graph replay grad")
