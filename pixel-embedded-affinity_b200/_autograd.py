@@ -18,13 +18,13 @@ from . import _ops as ops
 class OpSpec:
     """Static description of one fused call (everything that is not a tensor)."""
 
-    def __init__(self, offs3, border, loss_norm, loss_coef, affs_differentiable, impl=ops.IMPL_AUTO):
+    def __init__(self, offs3, border, loss_norm, loss_coef, affs_differentiable, impl=None):
         self.offs3 = np.ascontiguousarray(offs3, dtype=np.int32)
         self.border = border
         self.loss_norm = np.asarray(loss_norm, dtype=np.float32)
         self.loss_coef = np.asarray(loss_coef, dtype=np.float32)
         self.affs_differentiable = affs_differentiable
-        self.impl = impl
+        self.impl = ops.DEFAULT_IMPL if impl is None else impl
 
 
 class LossList(collections.abc.Sequence):

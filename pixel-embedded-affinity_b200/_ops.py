@@ -14,6 +14,17 @@ MASK_NONE, MASK_U8, MASK_F32 = 0, 1, 2
 IMPL_AUTO, IMPL_GENERIC, IMPL_TILED = 0, 1, 2
 MAX_OFFSETS = 64
 
+# Kernel-selection hint forwarded to the C ABI (PEA_IMPL_*).  AUTO picks the tiled kernels when the offset set /
+# shape qualifies and the table-driven kernel otherwise; tests flip this to compare the two on the same inputs.
+DEFAULT_IMPL = IMPL_AUTO
+
+
+def set_default_impl(impl):
+    global DEFAULT_IMPL
+    if impl not in (IMPL_AUTO, IMPL_GENERIC, IMPL_TILED):
+        raise ValueError(f"unknown impl {impl}")
+    DEFAULT_IMPL = impl
+
 _LABEL_CODES = {
     torch.uint8: 0, torch.float32: 4, torch.int8: 5, torch.int16: 6, torch.int32: 7, torch.int64: 8,
 }

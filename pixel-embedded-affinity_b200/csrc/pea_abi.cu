@@ -14,6 +14,13 @@ int launch_fused_generic(const float* emb, const float* par, const float* rinvE,
                          const float* weight, const void* mask, int mask_dtype, const float* upstream, float* affs,
                          float* partials, float* grad_emb, float* grad_par, cudaStream_t st);
 
+// pea_affs3d_tiled.cu
+bool tiled3d_norm5_eligible(int C, int D, int H, int W, const OffsetTable& tab, int border, int mask_dtype, bool cross,
+                            const float* emb);
+int tiled3d_norm5_blocks(int B, int H, int W);
+int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
+                         const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
+
 struct LossScale {
     float norm[PEA_MAX_OFFSETS];
     float coef[PEA_MAX_OFFSETS];
@@ -157,8 +164,8 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
                                      const float* weight, const void* mask, int mask_dtype, const float* loss_norm,
                                      const float* loss_coef, float* affs, float* loss_out, float* grad_emb,
                                      float* grad_partner, void* workspace, size_t ws_bytes, void* stream) {
-    (void)impl;
     if (!emb || !offsets || !target || !weight || !loss_norm || !loss_coef || !loss_out || !workspace) return PEA_E_NULL;
+    if (impl != PEA_IMPL_AUTO && impl != PEA_IMPL_GENERIC && impl != PEA_IMPL_TILED) return PEA_E_MODE;
     Dims d;
     int rc = check_volume(B, C, D, H, W, K, d);
     if (rc) return rc;
@@ -180,6 +187,16 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         tab.gcoef[k] = (float)(2.0 * (double)loss_coef[k] / (double)loss_norm[k]);
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // ---- tiled single-kernel path for the offset sets it specialises (same results, see tests)
+    const bool tiled_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb);
+    if (impl == PEA_IMPL_TILED && !tiled_ok) return PEA_E_MODE;
+    if (tiled_ok && impl != PEA_IMPL_GENERIC) {
+        // the per-voxel plane at the head of the workspace doubles as the (much smaller) partials array
+        float* parts = ws.rinvE;
+        if ((rc = launch_fused3d_norm5(emb, d, tab, target, weight, affs, parts, grad_emb, st))) return rc;
+        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, tiled3d_norm5_blocks(B, H, W), K, sc, loss_out);
+        return (int)cudaGetLastError();
+    }
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
     rc = launch_fused_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP, cross,

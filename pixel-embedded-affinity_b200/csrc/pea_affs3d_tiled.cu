@@ -1,0 +1,348 @@
+// Fused 3-D kernel for the AC3/AC4 12-offset set (embedding_loss_norm5, scripts_ac3ac4/loss/loss_embedding_mse.py:169-194):
+// embedding -> 12 axis-aligned affinities -> per-channel weighted MSE -> d loss / d embedding, ONE pass over HBM.
+//
+// Design (DESIGN.md "K4"):
+//   * one CTA owns an in-plane tile of TY x 32 voxel columns of one sample and MARCHES along z;
+//     each thread owns one column and keeps the last 5 slices' unit vectors e^ and gradient accumulators G in
+//     REGISTER RINGS, so the four z-pairs (shift 1..4) are evaluated once each with no neighbour traffic at all;
+//   * the eight in-plane offsets (y, x shifts 1/3/9/27, both directions in the gather-form backward) read RAW
+//     neighbour vectors from shared memory, staged per slice by TMA (cp.async.bulk.tensor, 5-D map, zero fill
+//     outside the volume == the reference's "valid region only" rule) into a y-column box, two y+-27 arm boxes
+//     and an x-row box; the neighbour's 1/|x| is recomputed in registers (16 FMA + MUFU) instead of being
+//     staged, so no normalised copy of the embedding ever exists in HBM;
+//   * TMA for slice z+1 is issued as soon as the last reader of a buffer has passed (two mbarriers, two
+//     __syncthreads per slice): copies overlap the x-part / z-part / epilogue of slice z;
+//   * loss: 12 per-thread accumulators over the march -> warp shuffle -> one row of partials per CTA ->
+//     fixed-order finalize kernel (deterministic).
+#include "pea_common.cuh"
+#include "pea_tma.cuh"
+
+namespace pea {
+
+namespace t3 {
+
+constexpr int kC = 16;
+constexpr int TX = 32;
+constexpr int HY = 9;               // near y halo rows on each side of the tile in the y-column box
+constexpr int FAR = 27;             // far shift served by the arm boxes / x-row box
+constexpr int XPAD = 28;            // x halo columns on each side of the x-row box (27 rounded up to 16 B)
+constexpr int XW = TX + 2 * XPAD;   // 88
+
+template <int TY>
+struct alignas(1024) Stage {
+    float sY[kC][TY + 2 * HY][TX];  // rows y0-9 .. y0+TY+8
+    float sAm[kC][TY][TX];          // rows y0-27 ..
+    float sAp[kC][TY][TX];          // rows y0+27 ..
+    float sX[kC][TY][XW];           // cols x0-28 .. x0+59
+};
+
+struct Params {
+    int B, D, H, W;
+    const float* target;
+    const float* weight;
+    float* affs;      // may be null
+    float* grad;      // may be null
+    float* partials;  // [gridDim.x][12]
+    float gcoef[12];
+};
+
+// channel layout of the 12-offset set: k = 3*g + axis, shift of (group g, axis): z {1,2,3,4}, y/x {1,3,9,27}
+__device__ __forceinline__ constexpr int shift_yx(int g) { return g == 0 ? 1 : (g == 1 ? 3 : (g == 2 ? 9 : 27)); }
+
+__device__ __forceinline__ float inv_norm(float ss) { return fminf(rsqrtf(ss), 1e12f); }  // == 1 / max(sqrt(ss), 1e-12)
+
+// One in-plane neighbour q of the own voxel p.  `nb` points at channel 0 of q in shared memory (raw values),
+// channels are `chs` floats apart.  Computes a = <e^_p, e^_q>, g = gcoef * w * (a - t) and G += g * e^_q.
+template <bool GRAD>
+__device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int chs, const float (&e)[kC], float (&G)[kC],
+                                              float t, float w, float gco, float& a_out) {
+    float xq[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) xq[c] = nb[c * chs];
+    float ss0 = 0.f, ss1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kC; c += 2) {
+        ss0 = fmaf(xq[c], xq[c], ss0);
+        ss1 = fmaf(xq[c + 1], xq[c + 1], ss1);
+        d0 = fmaf(e[c], xq[c], d0);
+        d1 = fmaf(e[c + 1], xq[c + 1], d1);
+    }
+    const float rq = inv_norm(ss0 + ss1);
+    const float a = (d0 + d1) * rq;
+    a_out = a;
+    const float diff = a - t;
+    if (GRAD) {
+        const float gr = gco * w * diff * rq;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) G[c] = fmaf(gr, xq[c], G[c]);
+    }
+    return w * diff * diff;
+}
+
+template <int TY, bool GRAD>
+__global__ void __launch_bounds__(TY * 32, 1)
+fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
+              const __grid_constant__ CUtensorMap mapX, const Params P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Stage<TY>& S = *reinterpret_cast<Stage<TY>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t barY, barX;
+    __shared__ float s_red[12][TY];
+
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp);
+    constexpr uint32_t kBytesX = sizeof(S.sX);
+    constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int D = P.D, H = P.H, W = P.W;
+    const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+    int bid = blockIdx.x;
+    const int tix = bid % tiles_x;
+    bid /= tiles_x;
+    const int tiy = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int x0 = tix * TX, y0 = tiy * TY;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool live = (x < W) && (y < H);
+    const int64_t HW = (int64_t)H * W, N = HW * D;
+    const int64_t pix = (int64_t)y * W + x;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&barY, 1);
+        mbar_init(&barX, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapX);
+    }
+    __syncthreads();
+
+    auto issueY = [&](int z) {
+        mbar_arrive_expect_tx(&barY, kBytesY);
+        tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
+        tma_load_5d(&S.sAm[0][0][0], &mapA, &barY, x0, y0 - FAR, z, 0, b);
+        tma_load_5d(&S.sAp[0][0][0], &mapA, &barY, x0, y0 + FAR, z, 0, b);
+    };
+    auto issueX = [&](int z) {
+        mbar_arrive_expect_tx(&barX, kBytesX);
+        tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
+    };
+    if (threadIdx.x == 0) {
+        issueY(0);
+        issueX(0);
+    }
+
+    // register rings over z: slot j holds slice z - j (slot 0 = the slice being processed); shifted once per slice
+    float re[5][kC], rG[5][kC], rr[5];
+    float lossacc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) lossacc[k] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        rr[s] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) re[s][c] = rG[s][c] = 0.f;
+    }
+
+    const float* tgt_b = P.target + (int64_t)b * 12 * N + pix;
+    const float* wgt_b = P.weight + (int64_t)b * 12 * N + pix;
+    float* affs_b = P.affs ? P.affs + (int64_t)b * 12 * N + pix : nullptr;
+    float* grad_b = P.grad ? P.grad + (int64_t)b * kC * N + pix : nullptr;
+
+    // back through the normalisation:  (G - e^ <e^, G>) / |x|   (eps branch of F.normalize: G / eps)
+    auto finalize = [&](const float (&e)[kC], const float (&G)[kC], float r, int zf) {
+        if (!GRAD || !live) return;
+        float eg = 0.f;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) eg = fmaf(e[c], G[c], eg);
+        if (!(r < 1e12f)) eg = 0.f;
+        float* dst = grad_b + (int64_t)zf * HW;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) dst[(int64_t)c * N] = (G[c] - e[c] * eg) * r;
+    };
+
+    for (int z = 0; z < D; ++z) {
+        const uint32_t par = (uint32_t)(z & 1);
+        const int64_t zoff = (int64_t)z * HW;
+        // own target / weight for the 12 channels of this voxel
+        float t[12], w[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            t[k] = live ? __ldg(tgt_b + (int64_t)k * N + zoff) : 0.f;
+            w[k] = live ? __ldg(wgt_b + (int64_t)k * N + zoff) : 0.f;
+        }
+
+        float (&e)[kC] = re[0];
+        float (&G)[kC] = rG[0];
+        // ---------------- y part (needs the y-column box and the arms)
+        mbar_wait(&barY, par);
+        {
+            const float* own = &S.sY[0][ty + HY][tx];
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                e[c] = own[c * CHS_Y];
+                ss = fmaf(e[c], e[c], ss);
+            }
+            const float rp = inv_norm(ss);
+            rr[0] = rp;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                e[c] *= rp;
+                G[c] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const int k = 3 * g + 1;
+            const float* nb_m = (g < 3) ? &S.sY[0][ty + HY - s][tx] : &S.sAm[0][ty][tx];
+            const float* nb_p = (g < 3) ? &S.sY[0][ty + HY + s][tx] : &S.sAp[0][ty][tx];
+            const int chs = (g < 3) ? CHS_Y : CHS_A;
+            // pair anchored here: partner y - s
+            const bool vf = live && (y >= s);
+            float a;
+            const float l = inplane_pair<GRAD>(nb_m, chs, e, G, t[k], vf ? w[k] : 0.f, P.gcoef[k], a);
+            lossacc[k] += vf ? l : 0.f;
+            if (affs_b && live) affs_b[(int64_t)k * N + zoff] = vf ? a : 0.f;
+            // pair anchored at y + s whose partner is this voxel
+            if (GRAD) {
+                const bool vr = live && (y + s < H);
+                const float t2 = vr ? __ldg(tgt_b + (int64_t)k * N + zoff + (int64_t)s * W) : 0.f;
+                const float w2 = vr ? __ldg(wgt_b + (int64_t)k * N + zoff + (int64_t)s * W) : 0.f;
+                float a2;
+                inplane_pair<true>(nb_p, chs, e, G, t2, w2, P.gcoef[k], a2);
+            }
+        }
+        __syncthreads();  // every reader of sY / arms is done
+        if (threadIdx.x == 0 && z + 1 < D) issueY(z + 1);
+
+        // ---------------- x part
+        mbar_wait(&barX, par);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const int k = 3 * g + 2;
+            const float* nb_m = &S.sX[0][ty][tx + XPAD - s];
+            const float* nb_p = &S.sX[0][ty][tx + XPAD + s];
+            const bool vf = live && (x >= s);
+            float a;
+            const float l = inplane_pair<GRAD>(nb_m, CHS_X, e, G, t[k], vf ? w[k] : 0.f, P.gcoef[k], a);
+            lossacc[k] += vf ? l : 0.f;
+            if (affs_b && live) affs_b[(int64_t)k * N + zoff] = vf ? a : 0.f;
+            if (GRAD) {
+                const bool vr = live && (x + s < W);
+                const float t2 = vr ? __ldg(tgt_b + (int64_t)k * N + zoff + s) : 0.f;
+                const float w2 = vr ? __ldg(wgt_b + (int64_t)k * N + zoff + s) : 0.f;
+                float a2;
+                inplane_pair<true>(nb_p, CHS_X, e, G, t2, w2, P.gcoef[k], a2);
+            }
+        }
+        __syncthreads();  // every reader of sX is done
+        if (threadIdx.x == 0 && z + 1 < D) issueX(z + 1);
+
+        // ---------------- z part: pairs (z, z - j), j = 1..4, both ends in registers (each pair evaluated once)
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) {
+            const int k = 3 * (j - 1);
+            const bool v = live && (z >= j);
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; c += 2) {
+                d0 = fmaf(re[0][c], re[j][c], d0);
+                d1 = fmaf(re[0][c + 1], re[j][c + 1], d1);
+            }
+            const float a = d0 + d1;
+            const float diff = a - t[k];
+            const float wv = v ? w[k] : 0.f;
+            lossacc[k] += wv * diff * diff;
+            if (affs_b && live) affs_b[(int64_t)k * N + zoff] = v ? a : 0.f;
+            if (GRAD) {
+                const float gg = P.gcoef[k] * wv * diff;
+#pragma unroll
+                for (int c = 0; c < kC; ++c) {
+                    const float e0 = re[0][c], ej = re[j][c];
+                    rG[0][c] = fmaf(gg, ej, rG[0][c]);
+                    rG[j][c] = fmaf(gg, e0, rG[j][c]);
+                }
+            }
+        }
+        // slice z - 4 has now seen all of its pairs: retire it, then shift the rings
+        if (z >= 4) finalize(re[4], rG[4], rr[4], z - 4);
+#pragma unroll
+        for (int s = 4; s >= 1; --s) {
+            rr[s] = rr[s - 1];
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                re[s][c] = re[s - 1][c];
+                rG[s][c] = rG[s - 1][c];
+            }
+        }
+    }
+    // drain: after the last shift slot j holds slice D - j; slices D-4 .. D-1 (those >= 0) are still pending
+#pragma unroll
+    for (int j = 4; j >= 1; --j)
+        if (D - j >= 0) finalize(re[j], rG[j], rr[j], D - j);
+
+    // ---------------- loss partials: thread -> warp -> CTA row
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const float v = warp_sum(lossacc[k]);
+        if (tx == 0) s_red[k][ty] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < TY; ++i) v += s_red[threadIdx.x][i];
+        P.partials[(int64_t)blockIdx.x * 12 + threadIdx.x] = v;
+    }
+}
+
+}  // namespace t3
+
+// ---------------------------------------------------------------------------------------------------------------
+bool tiled3d_norm5_eligible(int C, int D, int H, int W, const OffsetTable& tab, int border, int mask_dtype, bool cross,
+                            const float* emb) {
+    static const int ref[12][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-2, 0, 0}, {0, -3, 0}, {0, 0, -3},
+                                   {-3, 0, 0}, {0, -9, 0}, {0, 0, -9}, {-4, 0, 0}, {0, -27, 0}, {0, 0, -27}};
+    if (C != 16 || tab.K != 12 || border != PEA_BORDER_ZERO || mask_dtype != PEA_MASK_NONE || cross) return false;
+    if (W % 4 != 0 || (reinterpret_cast<uintptr_t>(emb) & 15)) return false;
+    for (int k = 0; k < 12; ++k)
+        if (tab.dz[k] != ref[k][0] || tab.dy[k] != ref[k][1] || tab.dx[k] != ref[k][2]) return false;
+    (void)D; (void)H;
+    return true;
+}
+
+int tiled3d_norm5_blocks(int B, int H, int W) {
+    constexpr int TY = 8;
+    return B * ((H + TY - 1) / TY) * ((W + t3::TX - 1) / t3::TX);
+}
+
+int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
+                         const float* weight, float* affs, float* partials, float* grad, cudaStream_t st) {
+    constexpr int TY = 8;
+    CUtensorMap mY, mA, mX;
+    int rc;
+    if ((rc = encode_volume_map(&mY, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY + 2 * t3::HY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mA, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mX, emb, d.B, 16, d.D, d.H, d.W, t3::XW, TY, 1, 16))) return rc;
+    t3::Params P;
+    P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
+    for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
+    const int grid = tiled3d_norm5_blocks(d.B, d.H, d.W);
+    const size_t smem = sizeof(t3::Stage<TY>) + 1024;
+    cudaError_t e;
+    if (grad) {
+        auto kern = t3::fused3d_norm5<TY, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, P);
+    } else {
+        auto kern = t3::fused3d_norm5<TY, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, P);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pea

