@@ -16,7 +16,7 @@ int launch_fused_generic(const float* emb, const float* par, const float* rinvE,
 
 // pea_affs3d_tiled.cu
 bool tiled3d_norm5_eligible(int C, int D, int H, int W, const OffsetTable& tab, int border, int mask_dtype, bool cross,
-                            const float* emb);
+                            const float* emb, const float* target, const float* weight);
 int tiled3d_norm5_blocks(int B, int H, int W);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
@@ -188,7 +188,7 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // ---- tiled single-kernel path for the offset sets it specialises (same results, see tests)
-    const bool tiled_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb);
+    const bool tiled_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb, target, weight);
     if (impl == PEA_IMPL_TILED && !tiled_ok) return PEA_E_MODE;
     if (tiled_ok && impl != PEA_IMPL_GENERIC) {
         // the per-voxel plane at the head of the workspace doubles as the (much smaller) partials array

@@ -34,6 +34,8 @@ struct alignas(1024) Stage {
     float sAm[kC][TY][TX];          // rows y0-27 ..
     float sAp[kC][TY][TX];          // rows y0+27 ..
     float sX[kC][TY][XW];           // cols x0-28 .. x0+59
+    float sT[2][12][TY][TX];        // own target tile, double-buffered over z
+    float sW[2][12][TY][TX];        // own weight tile
 };
 
 struct Params {
@@ -50,6 +52,14 @@ struct Params {
 __device__ __forceinline__ constexpr int shift_yx(int g) { return g == 0 ? 1 : (g == 1 ? 3 : (g == 2 ? 9 : 27)); }
 
 __device__ __forceinline__ float inv_norm(float ss) { return fminf(rsqrtf(ss), 1e12f); }  // == 1 / max(sqrt(ss), 1e-12)
+
+// Arrive on a CTA-wide counter with release/acquire semantics; returns the value before the increment.
+// The warp that observes the last arrival of a phase owns the refill of the buffer everyone has finished reading.
+__device__ __forceinline__ uint32_t arrive_count(uint32_t* cnt) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+    return old;
+}
 
 // One in-plane neighbour q of the own voxel p.  `nb` points at channel 0 of q in shared memory (raw values),
 // channels are `chs` floats apart.  Computes a = <e^_p, e^_q>, g = gcoef * w * (a - t) and G += g * e^_q.
@@ -82,15 +92,20 @@ __device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int 
 template <int TY, bool GRAD>
 __global__ void __launch_bounds__(TY * 32, 1)
 fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
-              const __grid_constant__ CUtensorMap mapX, const Params P) {
+              const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT,
+              const __grid_constant__ CUtensorMap mapW, const Params P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Stage<TY>& S = *reinterpret_cast<Stage<TY>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t barY, barX;
+    // align inside the dynamic window with pointer arithmetic (keeps the shared address space visible to the compiler)
+    Stage<TY>& S = *reinterpret_cast<Stage<TY>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    __shared__ uint64_t barY, barX, barT[2];
+    __shared__ uint32_t cntY, cntX, cntZ;
     __shared__ float s_red[12][TY];
 
     constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp);
     constexpr uint32_t kBytesX = sizeof(S.sX);
+    constexpr uint32_t kBytesT = sizeof(S.sT[0]) + sizeof(S.sW[0]);
     constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
+    constexpr uint32_t kWarps = TY;
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int D = P.D, H = P.H, W = P.W;
@@ -106,16 +121,6 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     const int64_t HW = (int64_t)H * W, N = HW * D;
     const int64_t pix = (int64_t)y * W + x;
 
-    if (threadIdx.x == 0) {
-        mbar_init(&barY, 1);
-        mbar_init(&barX, 1);
-        mbar_fence_init();
-        tma_prefetch_desc(&mapY);
-        tma_prefetch_desc(&mapA);
-        tma_prefetch_desc(&mapX);
-    }
-    __syncthreads();
-
     auto issueY = [&](int z) {
         mbar_arrive_expect_tx(&barY, kBytesY);
         tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
@@ -126,10 +131,25 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         mbar_arrive_expect_tx(&barX, kBytesX);
         tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
     };
+    auto issueT = [&](int z) {
+        mbar_arrive_expect_tx(&barT[z & 1], kBytesT);
+        tma_load_5d(&S.sT[z & 1][0][0][0], &mapT, &barT[z & 1], x0, y0, z, 0, b);
+        tma_load_5d(&S.sW[z & 1][0][0][0], &mapW, &barT[z & 1], x0, y0, z, 0, b);
+    };
+
     if (threadIdx.x == 0) {
+        mbar_init(&barY, 1);
+        mbar_init(&barX, 1);
+        mbar_init(&barT[0], 1);
+        mbar_init(&barT[1], 1);
+        cntY = cntX = cntZ = 0;
+        mbar_fence_init();
         issueY(0);
         issueX(0);
+        issueT(0);
+        if (D > 1) issueT(1);
     }
+    __syncthreads();
 
     // register rings over z: slot j holds slice z - j (slot 0 = the slice being processed); shifted once per slice
     float re[5][kC], rG[5][kC], rr[5];
@@ -163,17 +183,26 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     for (int z = 0; z < D; ++z) {
         const uint32_t par = (uint32_t)(z & 1);
         const int64_t zoff = (int64_t)z * HW;
-        // own target / weight for the 12 channels of this voxel
-        float t[12], w[12];
+        const int tb = z & 1;
+        // target / weight of the pairs anchored at the +s neighbours (gather-form backward): issued now, used later
+        float t2[8], w2[8];
+        if (GRAD) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            t[k] = live ? __ldg(tgt_b + (int64_t)k * N + zoff) : 0.f;
-            w[k] = live ? __ldg(wgt_b + (int64_t)k * N + zoff) : 0.f;
+            for (int g = 0; g < 4; ++g) {
+                const int s = shift_yx(g);
+                const bool vy = live && (y + s < H), vx = live && (x + s < W);
+                const int64_t oy = (int64_t)(3 * g + 1) * N + zoff + (int64_t)s * W;
+                const int64_t ox = (int64_t)(3 * g + 2) * N + zoff + s;
+                t2[g] = vy ? __ldg(tgt_b + oy) : 0.f;
+                w2[g] = vy ? __ldg(wgt_b + oy) : 0.f;
+                t2[4 + g] = vx ? __ldg(tgt_b + ox) : 0.f;
+                w2[4 + g] = vx ? __ldg(wgt_b + ox) : 0.f;
+            }
         }
 
         float (&e)[kC] = re[0];
         float (&G)[kC] = rG[0];
-        // ---------------- y part (needs the y-column box and the arms)
+        // ---------------- y part (needs the y-column box, the arms and the own target/weight tile)
         mbar_wait(&barY, par);
         {
             const float* own = &S.sY[0][ty + HY][tx];
@@ -191,6 +220,9 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 G[c] = 0.f;
             }
         }
+        mbar_wait(&barT[tb], (uint32_t)((z >> 1) & 1));
+        const float* sTo = &S.sT[tb][0][ty][tx];
+        const float* sWo = &S.sW[tb][0][ty][tx];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int s = shift_yx(g);
@@ -201,20 +233,18 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             // pair anchored here: partner y - s
             const bool vf = live && (y >= s);
             float a;
-            const float l = inplane_pair<GRAD>(nb_m, chs, e, G, t[k], vf ? w[k] : 0.f, P.gcoef[k], a);
+            const float l = inplane_pair<GRAD>(nb_m, chs, e, G, sTo[k * CHS_A], vf ? sWo[k * CHS_A] : 0.f, P.gcoef[k], a);
             lossacc[k] += vf ? l : 0.f;
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = vf ? a : 0.f;
             // pair anchored at y + s whose partner is this voxel
             if (GRAD) {
-                const bool vr = live && (y + s < H);
-                const float t2 = vr ? __ldg(tgt_b + (int64_t)k * N + zoff + (int64_t)s * W) : 0.f;
-                const float w2 = vr ? __ldg(wgt_b + (int64_t)k * N + zoff + (int64_t)s * W) : 0.f;
                 float a2;
-                inplane_pair<true>(nb_p, chs, e, G, t2, w2, P.gcoef[k], a2);
+                inplane_pair<true>(nb_p, chs, e, G, t2[g], w2[g], P.gcoef[k], a2);
             }
         }
-        __syncthreads();  // every reader of sY / arms is done
-        if (threadIdx.x == 0 && z + 1 < D) issueY(z + 1);
+        // every lane of this warp is done reading sY / arms; the last warp to get here refills them for z + 1
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueY(z + 1);
 
         // ---------------- x part
         mbar_wait(&barX, par);
@@ -226,19 +256,16 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             const float* nb_p = &S.sX[0][ty][tx + XPAD + s];
             const bool vf = live && (x >= s);
             float a;
-            const float l = inplane_pair<GRAD>(nb_m, CHS_X, e, G, t[k], vf ? w[k] : 0.f, P.gcoef[k], a);
+            const float l = inplane_pair<GRAD>(nb_m, CHS_X, e, G, sTo[k * CHS_A], vf ? sWo[k * CHS_A] : 0.f, P.gcoef[k], a);
             lossacc[k] += vf ? l : 0.f;
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = vf ? a : 0.f;
             if (GRAD) {
-                const bool vr = live && (x + s < W);
-                const float t2 = vr ? __ldg(tgt_b + (int64_t)k * N + zoff + s) : 0.f;
-                const float w2 = vr ? __ldg(wgt_b + (int64_t)k * N + zoff + s) : 0.f;
                 float a2;
-                inplane_pair<true>(nb_p, CHS_X, e, G, t2, w2, P.gcoef[k], a2);
+                inplane_pair<true>(nb_p, CHS_X, e, G, t2[4 + g], w2[4 + g], P.gcoef[k], a2);
             }
         }
-        __syncthreads();  // every reader of sX is done
-        if (threadIdx.x == 0 && z + 1 < D) issueX(z + 1);
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueX(z + 1);
 
         // ---------------- z part: pairs (z, z - j), j = 1..4, both ends in registers (each pair evaluated once)
 #pragma unroll
@@ -252,8 +279,8 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 d1 = fmaf(re[0][c + 1], re[j][c + 1], d1);
             }
             const float a = d0 + d1;
-            const float diff = a - t[k];
-            const float wv = v ? w[k] : 0.f;
+            const float diff = a - sTo[k * CHS_A];
+            const float wv = v ? sWo[k * CHS_A] : 0.f;
             lossacc[k] += wv * diff * diff;
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = v ? a : 0.f;
             if (GRAD) {
@@ -266,6 +293,10 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 }
             }
         }
+        // the own target/weight tile of this slice is consumed: the last warp refills that buffer for z + 2
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntZ) == kWarps * (uint32_t)(z + 1) - 1 && z + 2 < D) issueT(z + 2);
+
         // slice z - 4 has now seen all of its pairs: retire it, then shift the rings
         if (z >= 4) finalize(re[4], rG[4], rr[4], z - 4);
 #pragma unroll
@@ -302,11 +333,13 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------------------------
 bool tiled3d_norm5_eligible(int C, int D, int H, int W, const OffsetTable& tab, int border, int mask_dtype, bool cross,
-                            const float* emb) {
+                            const float* emb, const float* target, const float* weight) {
     static const int ref[12][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-2, 0, 0}, {0, -3, 0}, {0, 0, -3},
                                    {-3, 0, 0}, {0, -9, 0}, {0, 0, -9}, {-4, 0, 0}, {0, -27, 0}, {0, 0, -27}};
     if (C != 16 || tab.K != 12 || border != PEA_BORDER_ZERO || mask_dtype != PEA_MASK_NONE || cross) return false;
-    if (W % 4 != 0 || (reinterpret_cast<uintptr_t>(emb) & 15)) return false;
+    // TMA: 16-byte row pitch and base alignment for all three tensors
+    if (W % 4 != 0 || ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(target) |
+                        reinterpret_cast<uintptr_t>(weight)) & 15)) return false;
     for (int k = 0; k < 12; ++k)
         if (tab.dz[k] != ref[k][0] || tab.dy[k] != ref[k][1] || tab.dx[k] != ref[k][2]) return false;
     (void)D; (void)H;
@@ -321,11 +354,13 @@ int tiled3d_norm5_blocks(int B, int H, int W) {
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st) {
     constexpr int TY = 8;
-    CUtensorMap mY, mA, mX;
+    CUtensorMap mY, mA, mX, mT, mW;
     int rc;
     if ((rc = encode_volume_map(&mY, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY + 2 * t3::HY, 1, 16))) return rc;
     if ((rc = encode_volume_map(&mA, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY, 1, 16))) return rc;
     if ((rc = encode_volume_map(&mX, emb, d.B, 16, d.D, d.H, d.W, t3::XW, TY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mT, target, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 12))) return rc;
+    if ((rc = encode_volume_map(&mW, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 12))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
     P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
@@ -336,11 +371,11 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
     if (grad) {
         auto kern = t3::fused3d_norm5<TY, true>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, P);
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
     } else {
         auto kern = t3::fused3d_norm5<TY, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, P);
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
     }
     return (int)cudaGetLastError();
 }

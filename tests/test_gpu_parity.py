@@ -460,7 +460,6 @@ def test_tiled3d_matches_generic_and_oracle(P, O, B, D, H, W, seed):
         close_s(l_ng, lo, what=f"{name} loss (no grad)")
         close_t(a_ng, ao, what=f"{name} affs (no grad)")
     # border semantics are exact zeros in both
-    assert torch.equal(out["tiled"][1] == 0, out["generic"][1] == 0) or True
     assert float((out["tiled"][1][:, 0, 0]).abs().max()) == 0.0      # z-channel 0 is zero on the first slice
     assert float((out["tiled"][1][:, 10, :, :27]).abs().max()) == 0.0  # y-27 channel zero on the first 27 rows
 
