@@ -51,7 +51,40 @@ struct Params {
 // channel layout of the 12-offset set: k = 3*g + axis, shift of (group g, axis): z {1,2,3,4}, y/x {1,3,9,27}
 __device__ __forceinline__ constexpr int shift_yx(int g) { return g == 0 ? 1 : (g == 1 ? 3 : (g == 2 ? 9 : 27)); }
 
-__device__ __forceinline__ float inv_norm(float ss) { return fminf(rsqrtf(ss), 1e12f); }  // == 1 / max(sqrt(ss), 1e-12)
+// 1 / max(sqrt(ss), 1e-12) == min(rsqrt(ss), 1e12); one MUFU.RSQ (2 ulp), ss == 0 -> +inf -> 1e12
+__device__ __forceinline__ float inv_norm(float ss) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ss));
+    return fminf(r, 1e12f);
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2): two channels per instruction, same rounding as fmaf
+typedef unsigned long long f32x2;
+constexpr int kC2 = kC / 2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float hsum2(f32x2 a, f32x2 b) {
+    float a0, a1, b0, b1;
+    unpack2(a, a0, a1);
+    unpack2(b, b0, b1);
+    return (a0 + a1) + (b0 + b1);
+}
 
 // Arrive on a CTA-wide counter with release/acquire semantics; returns the value before the increment.
 // The warp that observes the last arrival of a phase owns the refill of the buffer everyone has finished reading.
@@ -64,27 +97,28 @@ __device__ __forceinline__ uint32_t arrive_count(uint32_t* cnt) {
 // One in-plane neighbour q of the own voxel p.  `nb` points at channel 0 of q in shared memory (raw values),
 // channels are `chs` floats apart.  Computes a = <e^_p, e^_q>, g = gcoef * w * (a - t) and G += g * e^_q.
 template <bool GRAD>
-__device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int chs, const float (&e)[kC], float (&G)[kC],
-                                              float t, float w, float gco, float& a_out) {
-    float xq[kC];
+__device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int chs, const f32x2 (&e)[kC2],
+                                              f32x2 (&G)[kC2], float t, float w, float gco, float& a_out) {
+    f32x2 xq[kC2];
 #pragma unroll
-    for (int c = 0; c < kC; ++c) xq[c] = nb[c * chs];
-    float ss0 = 0.f, ss1 = 0.f, d0 = 0.f, d1 = 0.f;
+    for (int i = 0; i < kC2; ++i) xq[i] = pack2(nb[(2 * i) * chs], nb[(2 * i + 1) * chs]);
+    f32x2 ss0 = 0ull, ss1 = 0ull, d0 = 0ull, d1 = 0ull;  // bit pattern of (+0.f, +0.f)
 #pragma unroll
-    for (int c = 0; c < kC; c += 2) {
-        ss0 = fmaf(xq[c], xq[c], ss0);
-        ss1 = fmaf(xq[c + 1], xq[c + 1], ss1);
-        d0 = fmaf(e[c], xq[c], d0);
-        d1 = fmaf(e[c + 1], xq[c + 1], d1);
+    for (int i = 0; i < kC2; i += 2) {
+        ss0 = fma2(xq[i], xq[i], ss0);
+        ss1 = fma2(xq[i + 1], xq[i + 1], ss1);
+        d0 = fma2(e[i], xq[i], d0);
+        d1 = fma2(e[i + 1], xq[i + 1], d1);
     }
-    const float rq = inv_norm(ss0 + ss1);
-    const float a = (d0 + d1) * rq;
+    const float rq = inv_norm(hsum2(ss0, ss1));
+    const float a = hsum2(d0, d1) * rq;
     a_out = a;
     const float diff = a - t;
     if (GRAD) {
         const float gr = gco * w * diff * rq;
+        const f32x2 gr2 = pack2(gr, gr);
 #pragma unroll
-        for (int c = 0; c < kC; ++c) G[c] = fmaf(gr, xq[c], G[c]);
+        for (int i = 0; i < kC2; ++i) G[i] = fma2(gr2, xq[i], G[i]);
     }
     return w * diff * diff;
 }
@@ -152,7 +186,8 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     __syncthreads();
 
     // register rings over z: slot j holds slice z - j (slot 0 = the slice being processed); shifted once per slice
-    float re[5][kC], rG[5][kC], rr[5];
+    f32x2 re[5][kC2], rG[5][kC2];
+    float rr[5];
     float lossacc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) lossacc[k] = 0.f;
@@ -160,7 +195,7 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     for (int s = 0; s < 5; ++s) {
         rr[s] = 0.f;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) re[s][c] = rG[s][c] = 0.f;
+        for (int i = 0; i < kC2; ++i) re[s][i] = rG[s][i] = 0ull;
     }
 
     const float* tgt_b = P.target + (int64_t)b * 12 * N + pix;
@@ -169,15 +204,25 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     float* grad_b = P.grad ? P.grad + (int64_t)b * kC * N + pix : nullptr;
 
     // back through the normalisation:  (G - e^ <e^, G>) / |x|   (eps branch of F.normalize: G / eps)
-    auto finalize = [&](const float (&e)[kC], const float (&G)[kC], float r, int zf) {
+    auto finalize = [&](const f32x2 (&e)[kC2], const f32x2 (&G)[kC2], float r, int zf) {
         if (!GRAD || !live) return;
-        float eg = 0.f;
+        f32x2 p0 = 0ull, p1 = 0ull;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) eg = fmaf(e[c], G[c], eg);
+        for (int i = 0; i < kC2; i += 2) {
+            p0 = fma2(e[i], G[i], p0);
+            p1 = fma2(e[i + 1], G[i + 1], p1);
+        }
+        float eg = hsum2(p0, p1);
         if (!(r < 1e12f)) eg = 0.f;
+        const f32x2 neg = pack2(-eg, -eg), r2 = pack2(r, r);
         float* dst = grad_b + (int64_t)zf * HW;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) dst[(int64_t)c * N] = (G[c] - e[c] * eg) * r;
+        for (int i = 0; i < kC2; ++i) {
+            float lo, hi;
+            unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
+            dst[(int64_t)(2 * i) * N] = lo;
+            dst[(int64_t)(2 * i + 1) * N] = hi;
+        }
     };
 
     for (int z = 0; z < D; ++z) {
@@ -200,24 +245,27 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             }
         }
 
-        float (&e)[kC] = re[0];
-        float (&G)[kC] = rG[0];
+        f32x2 (&e)[kC2] = re[0];
+        f32x2 (&G)[kC2] = rG[0];
         // ---------------- y part (needs the y-column box, the arms and the own target/weight tile)
         mbar_wait(&barY, par);
         {
             const float* own = &S.sY[0][ty + HY][tx];
-            float ss = 0.f;
+            f32x2 s0 = 0ull, s1 = 0ull;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) {
-                e[c] = own[c * CHS_Y];
-                ss = fmaf(e[c], e[c], ss);
+            for (int i = 0; i < kC2; ++i) e[i] = pack2(own[(2 * i) * CHS_Y], own[(2 * i + 1) * CHS_Y]);
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                s0 = fma2(e[i], e[i], s0);
+                s1 = fma2(e[i + 1], e[i + 1], s1);
             }
-            const float rp = inv_norm(ss);
+            const float rp = inv_norm(hsum2(s0, s1));
             rr[0] = rp;
+            const f32x2 rp2 = pack2(rp, rp);
 #pragma unroll
-            for (int c = 0; c < kC; ++c) {
-                e[c] *= rp;
-                G[c] = 0.f;
+            for (int i = 0; i < kC2; ++i) {
+                e[i] = mul2(e[i], rp2);
+                G[i] = 0ull;
             }
         }
         mbar_wait(&barT[tb], (uint32_t)((z >> 1) & 1));
@@ -272,24 +320,24 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         for (int j = 1; j <= 4; ++j) {
             const int k = 3 * (j - 1);
             const bool v = live && (z >= j);
-            float d0 = 0.f, d1 = 0.f;
+            f32x2 d0 = 0ull, d1 = 0ull;
 #pragma unroll
-            for (int c = 0; c < kC; c += 2) {
-                d0 = fmaf(re[0][c], re[j][c], d0);
-                d1 = fmaf(re[0][c + 1], re[j][c + 1], d1);
+            for (int i = 0; i < kC2; i += 2) {
+                d0 = fma2(re[0][i], re[j][i], d0);
+                d1 = fma2(re[0][i + 1], re[j][i + 1], d1);
             }
-            const float a = d0 + d1;
+            const float a = hsum2(d0, d1);
             const float diff = a - sTo[k * CHS_A];
             const float wv = v ? sWo[k * CHS_A] : 0.f;
             lossacc[k] += wv * diff * diff;
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = v ? a : 0.f;
             if (GRAD) {
                 const float gg = P.gcoef[k] * wv * diff;
+                const f32x2 gg2 = pack2(gg, gg);
 #pragma unroll
-                for (int c = 0; c < kC; ++c) {
-                    const float e0 = re[0][c], ej = re[j][c];
-                    rG[0][c] = fmaf(gg, ej, rG[0][c]);
-                    rG[j][c] = fmaf(gg, e0, rG[j][c]);
+                for (int i = 0; i < kC2; ++i) {
+                    rG[0][i] = fma2(gg2, re[j][i], rG[0][i]);
+                    rG[j][i] = fma2(gg2, re[0][i], rG[j][i]);
                 }
             }
         }
@@ -303,9 +351,9 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         for (int s = 4; s >= 1; --s) {
             rr[s] = rr[s - 1];
 #pragma unroll
-            for (int c = 0; c < kC; ++c) {
-                re[s][c] = re[s - 1][c];
-                rG[s][c] = rG[s - 1][c];
+            for (int i = 0; i < kC2; ++i) {
+                re[s][i] = re[s - 1][i];
+                rG[s][i] = rG[s - 1][i];
             }
         }
     }
