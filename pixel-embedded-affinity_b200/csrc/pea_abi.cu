@@ -21,6 +21,13 @@ int tiled3d_norm5_blocks(int B, int H, int W);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
 
+// pea_affs2d_tiled.cu
+bool tiled2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, bool need_grad_partner);
+int tiled2d_blocks(int B, int H, int W, const OffsetTable& tab);
+int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap,
+                   const float* target, const float* weight, const void* mask, int mask_dtype, float* affs,
+                   float* partials, float* grad, cudaStream_t st);
+
 struct LossScale {
     float norm[PEA_MAX_OFFSETS];
     float coef[PEA_MAX_OFFSETS];
@@ -139,8 +146,8 @@ extern "C" size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, 
 extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
                             const int32_t* offsets, int K, int border, int impl, float* affs, void* workspace,
                             size_t ws_bytes, void* stream) {
-    (void)impl;
     if (!emb || !offsets || !affs || !workspace) return PEA_E_NULL;
+    if (impl != PEA_IMPL_AUTO && impl != PEA_IMPL_GENERIC && impl != PEA_IMPL_TILED) return PEA_E_MODE;
     Dims d;
     int rc = check_volume(B, C, D, H, W, K, d);
     if (rc) return rc;
@@ -153,6 +160,11 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     OffsetTable tab;
     fill_offsets(offsets, K, tab);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, false);
+    if (impl == PEA_IMPL_TILED && !tiled2_ok) return PEA_E_MODE;
+    if (tiled2_ok && impl != PEA_IMPL_GENERIC)
+        return launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, nullptr, nullptr, nullptr, PEA_MASK_NONE,
+                              affs, nullptr, nullptr, st);
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
     return launch_fwd_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP, affs,
@@ -188,8 +200,18 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // ---- tiled single-kernel path for the offset sets it specialises (same results, see tests)
-    const bool tiled_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb, target, weight);
-    if (impl == PEA_IMPL_TILED && !tiled_ok) return PEA_E_MODE;
+    const bool tiled3_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb, target, weight);
+    const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, grad_partner != nullptr);
+    if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
+    if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC) {
+        float* parts = ws.rinvE;
+        if ((rc = launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs,
+                                 parts, grad_emb, st)))
+            return rc;
+        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, tiled2d_blocks(B, H, W, tab), K, sc, loss_out);
+        return (int)cudaGetLastError();
+    }
+    const bool tiled_ok = tiled3_ok;
     if (tiled_ok && impl != PEA_IMPL_GENERIC) {
         // the per-voxel plane at the head of the workspace doubles as the (much smaller) partials array
         float* parts = ws.rinvE;

@@ -477,3 +477,51 @@ def test_tiled3d_forced_on_ineligible_input_is_refused(P, O):
     lo, ao = O.embedding_loss_norm5(torch.tensor(emb), torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE())
     close_s(l, lo)
     close_t(a, ao)
+
+
+@pytest.mark.parametrize("B,H,W,shifts,nb,seed", [
+    (2, 37, 53, [1, 3, 5, 9, 27], 4, 81),     # plus-shaped halo 27, partial tiles
+    (1, 40, 48, [1, 3, 5, 9, 11], 8, 82),     # diagonals -> rectangular halo
+    (3, 24, 20, [1, 30], 4, 83),              # shift larger than the image: halo wraps more than once
+    (1, 130, 70, [1, 3, 5, 9, 11], 4, 84),    # several tiles in y and x
+])
+def test_tiled2d_matches_generic_and_oracle(P, O, B, H, W, shifts, nb, seed):
+    from pea_b200 import _ops as ops
+    offsets = O.multi_offset(shifts, neighbor=nb)
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, B, 16, H, W, offsets, seed, float_mask=(seed % 2 == 0))
+    res = {}
+    for name, impl in (("generic", ops.IMPL_GENERIC), ("tiled", ops.IMPL_TILED)):
+        ops.set_default_impl(impl)
+        try:
+            e = dev(emb, True)
+            l, a, al = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+            l.backward()
+            e2 = dev(emb, True)
+            l2, a2 = P.ema_embedding_loss(e2, dev(ema), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets,
+                                          affs0_weight=0.25)
+            l2.backward()
+            fwd = ops.affs_fwd(dev(emb), None, ops.offsets3(offsets, 2), ops.BORDER_WRAP, impl)
+            fwd0 = ops.affs_fwd(dev(emb), None, ops.offsets3(offsets, 2), ops.BORDER_ZERO, impl)
+            res[name] = (float(l.detach()), a.detach().cpu(), e.grad.cpu(), np.asarray(list(al)), float(l2.detach()),
+                         a2.detach().cpu(), e2.grad.cpu(), fwd.cpu(), fwd0.cpu())
+        finally:
+            ops.set_default_impl(ops.IMPL_AUTO)
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao, allo = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), O.WeightedMSE(), offsets)
+    lo.backward()
+    eo2 = torch.tensor(emb, requires_grad=True)
+    lo2, ao2 = O.ema_embedding_loss(eo2, torch.tensor(ema), torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk),
+                                    O.WeightedMSE(), offsets, affs0_weight=0.25)
+    lo2.backward()
+    for name in ("generic", "tiled"):
+        l, a, g, al, l2, a2, g2, fwd, fwd0 = res[name]
+        close_s(l, lo, what=f"{name} loss")
+        close_t(a, ao, what=f"{name} affs")
+        close_t(g, eo.grad, what=f"{name} grad")
+        close_t(al, np.asarray(allo), what=f"{name} all_loss")
+        close_s(l2, lo2, what=f"{name} ema loss")
+        close_t(a2, ao2, what=f"{name} ema affs")
+        close_t(g2, eo2.grad, what=f"{name} ema grad")
+        close_t(fwd, ao, what=f"{name} embedding2affs")
+    # zero-border forward (D = 1 volumes through the C ABI): tiled and table-driven kernels agree
+    close_t(res["tiled"][8], res["generic"][8], what="zero-border forward")
