@@ -22,8 +22,8 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
 
 // pea_affs2d_tiled.cu
-bool tiled2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, bool need_grad_partner);
-int tiled2d_blocks(int B, int H, int W, const OffsetTable& tab);
+bool tiled2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wrap, bool need_grad_partner);
+int tiled2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap);
 int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap,
                    const float* target, const float* weight, const void* mask, int mask_dtype, float* affs,
                    float* partials, float* grad, cudaStream_t st);
@@ -160,7 +160,7 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     OffsetTable tab;
     fill_offsets(offsets, K, tab);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, false);
+    const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, false);
     if (impl == PEA_IMPL_TILED && !tiled2_ok) return PEA_E_MODE;
     if (tiled2_ok && impl != PEA_IMPL_GENERIC)
         return launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, nullptr, nullptr, nullptr, PEA_MASK_NONE,
@@ -201,14 +201,14 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // ---- tiled single-kernel path for the offset sets it specialises (same results, see tests)
     const bool tiled3_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb, target, weight);
-    const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, grad_partner != nullptr);
+    const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr);
     if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC) {
         float* parts = ws.rinvE;
         if ((rc = launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs,
                                  parts, grad_emb, st)))
             return rc;
-        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, tiled2d_blocks(B, H, W, tab), K, sc, loss_out);
+        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, tiled2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
         return (int)cudaGetLastError();
     }
     const bool tiled_ok = tiled3_ok;

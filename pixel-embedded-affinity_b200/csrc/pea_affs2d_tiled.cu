@@ -9,8 +9,11 @@
 //     rectangle when the table holds diagonal offsets.  The fill maps halo coordinates through the border rule
 //     (modulo for wrap, zeros outside for the zero border), so wrap-around needs no special tiles, and every staged
 //     pixel is normalised exactly once;
+//   * shared memory is PIXEL-MAJOR (16 channels = 64 B per staged pixel, 16-byte chunks XOR-swizzled by the pixel
+//     index): a neighbour vector is four conflict-free LDS.128 with immediate offsets whatever the halo size, and
+//     lands in registers as aligned pairs ready for packed FFMA2;
 //   * the offset loop is a compact runtime loop: per offset one forward neighbour (pair anchored here) and, for the
-//     self variant with gradient, one reverse neighbour (pair anchored at p - o), 16 LDS + 16 packed FMAs each;
+//     self variant with gradient, one reverse neighbour (pair anchored at p - o), 4 LDS.128 + 16 packed FMAs each;
 //   * per-offset loss terms go to shared memory and are reduced in a fixed order -> one row of partials per CTA.
 #include "pea_common.cuh"
 
@@ -53,6 +56,26 @@ __device__ __forceinline__ float inv_norm(float ss) {
     return fminf(r, 1e12f);  // == 1 / max(sqrt(ss), 1e-12)
 }
 
+// v mod n for -n <= v < 4n (offsets are pre-reduced on the host and the plan requires H >= TY/2, W >= 16).
+// Written as straight-line selects: a loop here is recognised as a remainder and compiled to an integer division.
+__device__ __forceinline__ int wrapn(int v, int n) {
+    v += (v < 0) ? n : 0;
+    v -= (v >= n) ? n : 0;
+    v -= (v >= n) ? n : 0;
+    v -= (v >= n) ? n : 0;
+    return v;
+}
+
+// mask element as raw bits (no conversion at the load, so the load can stay in flight) and its later decoding
+__device__ __forceinline__ uint32_t load_mask_raw(const void* mask, int mask_dtype, int64_t i) {
+    if (mask_dtype == PEA_MASK_U8) return (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(mask) + i);
+    if (mask_dtype == PEA_MASK_F32) return __float_as_uint(__ldg(reinterpret_cast<const float*>(mask) + i));
+    return mask_dtype == PEA_MASK_NONE ? 0x3f800000u : 0u;
+}
+__device__ __forceinline__ float decode_mask(uint32_t raw, int mask_dtype) {
+    return mask_dtype == PEA_MASK_U8 ? (float)raw : __uint_as_float(raw);
+}
+
 struct Params {
     int B, H, W, K, P;        // P = halo = max |offset component|
     int wrap, rect, mask_dtype;
@@ -68,8 +91,23 @@ struct Params {
     float gcoef[kMaxK];
 };
 
-// Normalised embedding of one staged pixel -> channel-planar shared memory (stride `chs` floats between channels).
-__device__ __forceinline__ void stage_pixel(const float* __restrict__ src, int64_t N, bool inside, float* dst, int chs,
+// Pixel-major staging: pixel q occupies floats [16 q, 16 q + 16); its 16-byte chunk j sits at slot j ^ ((q >> 1) & 3),
+// which makes a warp's LDS.128 / STS.128 over consecutive pixels bank-conflict free.
+__device__ __forceinline__ int swz(int q) { return (q >> 1) & 3; }
+
+__device__ __forceinline__ void load_px(const float* __restrict__ tile, int q, f32x2 (&v)[kC2]) {
+    const float4* base = reinterpret_cast<const float4*>(tile) + (size_t)q * 4;
+    const int sw = swz(q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 c = base[j ^ sw];
+        v[2 * j] = pack2(c.x, c.y);
+        v[2 * j + 1] = pack2(c.z, c.w);
+    }
+}
+
+// Normalised embedding of one staged pixel (fetched channel-planar from global) -> shared memory.
+__device__ __forceinline__ void stage_pixel(const float* __restrict__ src, int64_t N, bool inside, float* tile, int q,
                                             float* rinv_out) {
     float v[kC];
     float ss = 0.f;
@@ -79,13 +117,16 @@ __device__ __forceinline__ void stage_pixel(const float* __restrict__ src, int64
         ss = fmaf(v[c], v[c], ss);
     }
     const float r = inv_norm(ss);
+    float4* base = reinterpret_cast<float4*>(tile) + (size_t)q * 4;
+    const int sw = swz(q);
 #pragma unroll
-    for (int c = 0; c < kC; ++c) dst[c * chs] = v[c] * r;
+    for (int j = 0; j < 4; ++j)
+        base[j ^ sw] = make_float4(v[4 * j] * r, v[4 * j + 1] * r, v[4 * j + 2] * r, v[4 * j + 3] * r);
     if (rinv_out) *rinv_out = r;
 }
 
 template <int TY, bool CROSS>
-__global__ void __launch_bounds__(TY * 32)
+__global__ void __launch_bounds__(TY * 32, (TY <= 12) ? 2 : 1)
 fused2d_tiled(const Params P) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_rinv[TY][TX];
@@ -107,43 +148,35 @@ fused2d_tiled(const Params P) {
     // ---- shared-memory geometry
     const int YR = TY + 2 * HP;          // rows of the y-column / rectangle
     const int XW = TX + 2 * HP;          // cols of the x-row / rectangle
-    float* sY;                           // [c][YR][TX]      (plus mode)   or [c][YR][XW] (rect mode)
-    float* sX;                           // [c][TY][XW]      (plus mode only)
-    int chsY, pitchY, chsX;
-    if (P.rect) {
-        pitchY = XW; chsY = YR * XW; sY = smem; sX = smem; chsX = chsY;
-    } else {
-        pitchY = TX; chsY = YR * TX; sY = smem; chsX = TY * XW; sX = smem + kC * chsY;
-    }
+    // staged pixel index: y-column (or rectangle) first -- q = row * pitchY + col -- then the x-row at qX0 + row * XW + col
+    const int pitchY = P.rect ? XW : TX;
+    const int qX0 = P.rect ? 0 : YR * TX;
     const float* stage_src = (CROSS ? P.par : P.emb) + (int64_t)b * kC * N;
 
     // ---- fill: every staged pixel is fetched through the border rule and normalised once
     {
         const int colsY = P.rect ? XW : TX;
-        const int chunksY = (colsY + 31) / 32;
-        for (int r = ty; r < YR * chunksY; r += TY) {
-            const int row = r / chunksY, col = (r - row * chunksY) * 32 + tx;
-            if (col < colsY) {
+        for (int row = ty; row < YR; row += TY) {
+            for (int col = tx; col < colsY; col += 32) {
                 int gy = y0 - HP + row, gx = (P.rect ? x0 - HP : x0) + col;
                 bool inside = true;
-                if (wrap) { gy = pmod(gy, H); gx = pmod(gx, W); }
+                if (wrap) { gy = wrapn(gy, H); gx = wrapn(gx, W); }
                 else inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
                 // the own 1/|x| of the tile centre is kept for the final projection (self variant)
                 const int cy = row - HP, cx = P.rect ? col - HP : col;
                 float* rv = (!CROSS && (unsigned)cy < (unsigned)TY && (unsigned)cx < (unsigned)TX) ? &s_rinv[cy][cx] : nullptr;
-                stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, sY + row * pitchY + col, chsY, rv);
+                stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, row * pitchY + col, rv);
             }
         }
         if (!P.rect) {
-            const int chunksX = (XW + 31) / 32;
-            for (int r = ty; r < TY * chunksX; r += TY) {
-                const int row = r / chunksX, col = (r - row * chunksX) * 32 + tx;
-                if (col < XW) {
+            {
+                const int row = ty;
+                for (int col = tx; col < XW; col += 32) {
                     int gy = y0 + row, gx = x0 - HP + col;
                     bool inside = true;
-                    if (wrap) { gy = pmod(gy, H); gx = pmod(gx, W); }
+                    if (wrap) { gy = wrapn(gy, H); gx = wrapn(gx, W); }
                     else inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-                    stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, sX + row * XW + col, chsX, nullptr);
+                    stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, qX0 + row * XW + col, nullptr);
                 }
             }
         }
@@ -165,9 +198,7 @@ fused2d_tiled(const Params P) {
 #pragma unroll
         for (int i = 0; i < kC2; ++i) e[i] = pack2(v[2 * i] * rp, v[2 * i + 1] * rp);
     } else {
-        const float* own = P.rect ? sY + (ty + HP) * pitchY + (tx + HP) : sY + (ty + HP) * pitchY + tx;
-#pragma unroll
-        for (int i = 0; i < kC2; ++i) e[i] = pack2(own[(2 * i) * chsY], own[(2 * i + 1) * chsY]);
+        load_px(smem, (ty + HP) * pitchY + (P.rect ? tx + HP : tx), e);
         rp = s_rinv[ty][tx];
     }
 #pragma unroll
@@ -175,23 +206,45 @@ fused2d_tiled(const Params P) {
 
     const bool want_loss = P.target != nullptr;
     const bool want_grad = P.grad != nullptr;
+    const bool want_rev = !CROSS && want_grad;
     const int64_t pix = (int64_t)(live ? y : 0) * W + (live ? x : 0);
     const int64_t kbase = (int64_t)b * K * N;
-    // per-offset loss terms of this thread; the scratch lives behind the tile when it fits, else it aliases the
-    // tile after the offset loop (see below) -- here we keep them in a small local array indexed dynamically
-    float lterm[kMaxK];
+    float lterm[kMaxK];  // per-offset loss terms of this pixel (reduced over the CTA after the loop)
 
+    // target / weight / mask of the pair anchored here and of the pair anchored at p - o_k, fetched ONE OFFSET AHEAD
+    struct KV { float t, w, t2, w2; uint32_t m, m2; };
+    auto fetch = [&](int k) -> KV {
+        KV v = {0.f, 0.f, 0.f, 0.f, 0u, 0u};
+        if (!want_loss || k >= K) return v;
+        const int dy = P.dy[k], dx = P.dx[k];
+        bool valid = live;
+        if (!wrap) valid = valid && (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W;
+        const int64_t idx = kbase + (int64_t)k * N + pix;
+        if (valid) { v.t = __ldg(P.target + idx); v.w = __ldg(P.weight + idx); v.m = load_mask_raw(P.mask, P.mask_dtype, idx); }
+        if (want_rev) {
+            int qy = y - dy, qx = x - dx;
+            bool v2 = live;
+            if (wrap) { qy = wrapn(qy, H); qx = wrapn(qx, W); }
+            else v2 = v2 && (unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W;
+            if (v2) {
+                const int64_t idx2 = kbase + (int64_t)k * N + (int64_t)qy * W + qx;
+                v.t2 = __ldg(P.target + idx2); v.w2 = __ldg(P.weight + idx2); v.m2 = load_mask_raw(P.mask, P.mask_dtype, idx2);
+            }
+        }
+        return v;
+    };
+
+    KV cur = fetch(0);
     for (int k = 0; k < K; ++k) {
+        const KV nxt = fetch(k + 1);
         const int dy = P.dy[k], dx = P.dx[k];
         // ---------------- pair anchored here: partner p + o_k
-        const float* nb;
-        int chs;
-        if (P.rect) { nb = sY + (ty + HP + dy) * pitchY + (tx + HP + dx); chs = chsY; }
-        else if (dx == 0) { nb = sY + (ty + HP + dy) * pitchY + tx; chs = chsY; }
-        else { nb = sX + ty * XW + (tx + HP + dx); chs = chsX; }
+        int q;
+        if (P.rect) q = (ty + HP + dy) * pitchY + (tx + HP + dx);
+        else if (dx == 0) q = (ty + HP + dy) * pitchY + tx;
+        else q = qX0 + ty * XW + (tx + HP + dx);
         f32x2 xq[kC2];
-#pragma unroll
-        for (int i = 0; i < kC2; ++i) xq[i] = pack2(nb[(2 * i) * chs], nb[(2 * i + 1) * chs]);
+        load_px(smem, q, xq);
         f32x2 d0 = 0ull, d1 = 0ull;
 #pragma unroll
         for (int i = 0; i < kC2; i += 2) {
@@ -202,30 +255,26 @@ fused2d_tiled(const Params P) {
         bool valid = live;
         if (!wrap) valid = valid && (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W;
         if (!valid) a = 0.f;
-        const int64_t idx = kbase + (int64_t)k * N + pix;
-        if (P.affs && live) P.affs[idx] = a;
+        if (P.affs && live) P.affs[kbase + (int64_t)k * N + pix] = a;
         float lt = 0.f;
         if (want_loss) {
-            float g = 0.f;
-            if (valid) {
-                const float t = __ldg(P.target + idx), w = __ldg(P.weight + idx), m = load_mask(P.mask, P.mask_dtype, idx);
-                const float dd = a * m - t * m;
-                lt = w * dd * dd;
-                g = P.gcoef[k] * w * m * m * (a - t);
-            }
+            // invalid pairs were fetched as t = w = m = 0: they contribute nothing
+            const float m = decode_mask(cur.m, P.mask_dtype);
+            const float dd = a * m - cur.t * m;
+            lt = cur.w * dd * dd;
             if (want_grad) {
+                const float g = P.gcoef[k] * cur.w * m * m * (a - cur.t);
 #pragma unroll
                 for (int i = 0; i < kC2; ++i) G[i] = fma2(pack2(g, g), xq[i], G[i]);
             }
             // ---------------- pair anchored at p - o_k, whose partner is this pixel (self variant only)
-            if (!CROSS && want_grad) {
-                const float* nb2;
-                if (P.rect) nb2 = sY + (ty + HP - dy) * pitchY + (tx + HP - dx);
-                else if (dx == 0) nb2 = sY + (ty + HP - dy) * pitchY + tx;
-                else nb2 = sX + ty * XW + (tx + HP - dx);
+            if (want_rev) {
+                int q2;
+                if (P.rect) q2 = (ty + HP - dy) * pitchY + (tx + HP - dx);
+                else if (dx == 0) q2 = (ty + HP - dy) * pitchY + tx;
+                else q2 = qX0 + ty * XW + (tx + HP - dx);
                 f32x2 xr[kC2];
-#pragma unroll
-                for (int i = 0; i < kC2; ++i) xr[i] = pack2(nb2[(2 * i) * chs], nb2[(2 * i + 1) * chs]);
+                load_px(smem, q2, xr);
                 f32x2 r0 = 0ull, r1 = 0ull;
 #pragma unroll
                 for (int i = 0; i < kC2; i += 2) {
@@ -233,22 +282,14 @@ fused2d_tiled(const Params P) {
                     r1 = fma2(e[i + 1], xr[i + 1], r1);
                 }
                 const float a2 = hsum2(r0, r1);
-                int qy = y - dy, qx = x - dx;
-                bool v2 = live;
-                if (wrap) { qy = pmod(qy, H); qx = pmod(qx, W); }
-                else v2 = v2 && (unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W;
-                float g2 = 0.f;
-                if (v2) {
-                    const int64_t idx2 = kbase + (int64_t)k * N + (int64_t)qy * W + qx;
-                    const float t2 = __ldg(P.target + idx2), w2 = __ldg(P.weight + idx2),
-                                m2 = load_mask(P.mask, P.mask_dtype, idx2);
-                    g2 = P.gcoef[k] * w2 * m2 * m2 * (a2 - t2);
-                }
+                const float m2 = decode_mask(cur.m2, P.mask_dtype);
+                const float g2 = P.gcoef[k] * cur.w2 * m2 * m2 * (a2 - cur.t2);
 #pragma unroll
                 for (int i = 0; i < kC2; ++i) G[i] = fma2(pack2(g2, g2), xr[i], G[i]);
             }
         }
         lterm[k] = lt;
+        cur = nxt;
     }
 
     // ---- gradient back through the normalisation
@@ -298,18 +339,22 @@ struct Plan2D {
     size_t smem;
 };
 
-static bool plan2d(const OffsetTable& tab, int H, int W, Plan2D& plan) {
+// Under the circular border an offset acts modulo the image extent: reduce it once on the host so the kernel's halo
+// and its index arithmetic stay within one period (C remainder: |r| < n, sign of the dividend).
+static inline int eff_off(int o, int n, int wrap) { return wrap ? o % n : o; }
+
+static bool plan2d(const OffsetTable& tab, int H, int W, int wrap, Plan2D& plan) {
     if (tab.K > t2::kMaxK) return false;
     int P = 0, rect = 0;
     for (int k = 0; k < tab.K; ++k) {
         if (tab.dz[k] != 0) return false;
-        const int ay = tab.dy[k] < 0 ? -tab.dy[k] : tab.dy[k], ax = tab.dx[k] < 0 ? -tab.dx[k] : tab.dx[k];
+        const int oy = eff_off(tab.dy[k], H, wrap), ox = eff_off(tab.dx[k], W, wrap);
+        const int ay = oy < 0 ? -oy : oy, ax = ox < 0 ? -ox : ox;
         if (ay > P) P = ay;
         if (ax > P) P = ax;
         if (ay != 0 && ax != 0) rect = 1;
     }
     if (P > 64) return false;
-    (void)H; (void)W;
     const int cands[3] = {16, 12, 8};
     for (int i = 0; i < 3; ++i) {
         const int TY = cands[i];
@@ -326,15 +371,16 @@ static bool plan2d(const OffsetTable& tab, int H, int W, Plan2D& plan) {
     return false;
 }
 
-bool tiled2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, bool need_grad_partner) {
+bool tiled2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wrap, bool need_grad_partner) {
     if (C != 16 || D != 1 || need_grad_partner) return false;
+    if (H < 8 || W < 16) return false;  // wrapn() covers at most three periods beyond the image
     Plan2D plan;
-    return plan2d(tab, H, W, plan);
+    return plan2d(tab, H, W, wrap, plan);
 }
 
-int tiled2d_blocks(int B, int H, int W, const OffsetTable& tab) {
+int tiled2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap) {
     Plan2D plan;
-    if (!plan2d(tab, H, W, plan)) return 0;
+    if (!plan2d(tab, H, W, wrap, plan)) return 0;
     return B * ((H + plan.TY - 1) / plan.TY) * ((W + t2::TX - 1) / t2::TX);
 }
 
@@ -358,14 +404,18 @@ int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const 
                    const float* target, const float* weight, const void* mask, int mask_dtype, float* affs,
                    float* partials, float* grad, cudaStream_t st) {
     Plan2D plan;
-    if (!plan2d(tab, d.H, d.W, plan)) return PEA_E_MODE;
+    if (!plan2d(tab, d.H, d.W, wrap, plan)) return PEA_E_MODE;
     t2::Params P;
     P.B = d.B; P.H = d.H; P.W = d.W; P.K = tab.K; P.P = plan.P;
     P.wrap = wrap; P.rect = plan.rect; P.mask_dtype = mask_dtype;
     P.emb = emb; P.par = partner ? partner : emb;
     P.target = target; P.weight = weight; P.mask = mask;
     P.affs = affs; P.grad = grad; P.partials = partials;
-    for (int k = 0; k < tab.K; ++k) { P.dy[k] = tab.dy[k]; P.dx[k] = tab.dx[k]; P.gcoef[k] = tab.gcoef[k]; }
+    for (int k = 0; k < tab.K; ++k) {
+        P.dy[k] = eff_off(tab.dy[k], d.H, wrap);
+        P.dx[k] = eff_off(tab.dx[k], d.W, wrap);
+        P.gcoef[k] = tab.gcoef[k];
+    }
     const int grid = d.B * ((d.H + plan.TY - 1) / plan.TY) * ((d.W + t2::TX - 1) / t2::TX);
     switch (plan.TY) {
         case 16: return launch2d_ty<16>(P, partner != nullptr, grid, plan.smem, st);
