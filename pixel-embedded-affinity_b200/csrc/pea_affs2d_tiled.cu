@@ -56,29 +56,9 @@ __device__ __forceinline__ float inv_norm(float ss) {
     return fminf(r, 1e12f);  // == 1 / max(sqrt(ss), 1e-12)
 }
 
-// v mod n for -n <= v < 4n (offsets are pre-reduced on the host and the plan requires H >= TY/2, W >= 16).
-// Written as straight-line selects: a loop here is recognised as a remainder and compiled to an integer division.
-__device__ __forceinline__ int wrapn(int v, int n) {
-    v += (v < 0) ? n : 0;
-    v -= (v >= n) ? n : 0;
-    v -= (v >= n) ? n : 0;
-    v -= (v >= n) ? n : 0;
-    return v;
-}
-
-// mask element as raw bits (no conversion at the load, so the load can stay in flight) and its later decoding
-__device__ __forceinline__ uint32_t load_mask_raw(const void* mask, int mask_dtype, int64_t i) {
-    if (mask_dtype == PEA_MASK_U8) return (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(mask) + i);
-    if (mask_dtype == PEA_MASK_F32) return __float_as_uint(__ldg(reinterpret_cast<const float*>(mask) + i));
-    return mask_dtype == PEA_MASK_NONE ? 0x3f800000u : 0u;
-}
-__device__ __forceinline__ float decode_mask(uint32_t raw, int mask_dtype) {
-    return mask_dtype == PEA_MASK_U8 ? (float)raw : __uint_as_float(raw);
-}
-
 struct Params {
-    int B, H, W, K, P;        // P = halo = max |offset component|
-    int wrap, rect, mask_dtype;
+    int B, H, W, K, P;        // P = halo = max |offset component| (after reduction modulo the image under wrap)
+    int wrap, rect;
     const float* emb;         // anchor view
     const float* par;         // partner view (== emb for the self variant)
     const float* target;      // null => forward only
@@ -90,6 +70,20 @@ struct Params {
     int dy[kMaxK], dx[kMaxK];
     float gcoef[kMaxK];
 };
+
+// v mod n for -n <= v < 2n: straight-line selects (a loop here is recognised as a remainder -> integer division)
+__device__ __forceinline__ int wrap1(int v, int n) {
+    v += (v < 0) ? n : 0;
+    v -= (v >= n) ? n : 0;
+    return v;
+}
+// -n <= v < 4n: fill coordinates of tiles hanging over the image edge
+__device__ __forceinline__ int wrap3(int v, int n) {
+    v = wrap1(v, n);
+    v -= (v >= n) ? n : 0;
+    v -= (v >= n) ? n : 0;
+    return v;
+}
 
 // Pixel-major staging: pixel q occupies floats [16 q, 16 q + 16); its 16-byte chunk j sits at slot j ^ ((q >> 1) & 3),
 // which makes a warp's LDS.128 / STS.128 over consecutive pixels bank-conflict free.
@@ -106,30 +100,58 @@ __device__ __forceinline__ void load_px(const float* __restrict__ tile, int q, f
     }
 }
 
-// Normalised embedding of one staged pixel (fetched channel-planar from global) -> shared memory.
-__device__ __forceinline__ void stage_pixel(const float* __restrict__ src, int64_t N, bool inside, float* tile, int q,
-                                            float* rinv_out) {
+// Normalised embedding of one staged pixel (fetched channel-planar from global) -> shared memory; returns 1/|x|.
+__device__ __forceinline__ float stage_pixel(const float* __restrict__ src, int64_t N, bool inside, float* tile, int q) {
     float v[kC];
-    float ss = 0.f;
+    if (inside) {
+        const float* p = src;
 #pragma unroll
-    for (int c = 0; c < kC; ++c) {
-        v[c] = inside ? __ldg(src + (int64_t)c * N) : 0.f;
-        ss = fmaf(v[c], v[c], ss);
+        for (int c = 0; c < kC; ++c) {
+            v[c] = __ldg(p);
+            p += N;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < kC; ++c) v[c] = 0.f;
     }
-    const float r = inv_norm(ss);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kC; c += 2) {
+        s0 = fmaf(v[c], v[c], s0);
+        s1 = fmaf(v[c + 1], v[c + 1], s1);
+    }
+    const float r = inv_norm(s0 + s1);
     float4* base = reinterpret_cast<float4*>(tile) + (size_t)q * 4;
     const int sw = swz(q);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         base[j ^ sw] = make_float4(v[4 * j] * r, v[4 * j + 1] * r, v[4 * j + 2] * r, v[4 * j + 3] * r);
-    if (rinv_out) *rinv_out = r;
+    return r;
 }
 
-template <int TY, bool CROSS>
+template <int MASK>
+__device__ __forceinline__ uint32_t mask_raw(const void* mask, uint32_t i) {
+    if (MASK == PEA_MASK_U8) return (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(mask) + i);
+    if (MASK == PEA_MASK_F32) return __float_as_uint(__ldg(reinterpret_cast<const float*>(mask) + i));
+    return 0x3f800000u;
+}
+template <int MASK>
+__device__ __forceinline__ float mask_val(uint32_t raw) {
+    return MASK == PEA_MASK_U8 ? (float)raw : __uint_as_float(raw);
+}
+
+// per-offset table, decoded once per CTA: which staged region holds the neighbour and its pixel-index delta
+struct KTab {
+    int sel[kMaxK];    // 0: y-column / rectangle, 1: x-row
+    int delta[kMaxK];  // staged-pixel index of (p + o) minus that of p within the region
+};
+
+template <int TY, bool CROSS, int MASK>
 __global__ void __launch_bounds__(TY * 32, (TY <= 12) ? 2 : 1)
 fused2d_tiled(const Params P) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_rinv[TY][TX];
+    __shared__ KTab s_k;
     constexpr int NT = TY * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int H = P.H, W = P.W, K = P.K, HP = P.P;
@@ -145,60 +167,72 @@ fused2d_tiled(const Params P) {
     const int64_t N = (int64_t)H * W;
     const bool wrap = P.wrap != 0;
 
-    // ---- shared-memory geometry
-    const int YR = TY + 2 * HP;          // rows of the y-column / rectangle
-    const int XW = TX + 2 * HP;          // cols of the x-row / rectangle
-    // staged pixel index: y-column (or rectangle) first -- q = row * pitchY + col -- then the x-row at qX0 + row * XW + col
+    // ---- shared-memory geometry (staged pixel index q): y-column (or rectangle) first, q = row * pitchY + col,
+    //      then the x-row at qX0 + row * XW + col
+    const int YR = TY + 2 * HP;
+    const int XW = TX + 2 * HP;
     const int pitchY = P.rect ? XW : TX;
     const int qX0 = P.rect ? 0 : YR * TX;
+    if (threadIdx.x < K) {
+        const int k = threadIdx.x, dy = P.dy[k], dx = P.dx[k];
+        const bool inX = !P.rect && dx != 0;
+        s_k.sel[k] = inX ? 1 : 0;
+        s_k.delta[k] = inX ? dx : dy * pitchY + dx;
+    }
     const float* stage_src = (CROSS ? P.par : P.emb) + (int64_t)b * kC * N;
 
     // ---- fill: every staged pixel is fetched through the border rule and normalised once
     {
         const int colsY = P.rect ? XW : TX;
+        const int gx_base = P.rect ? x0 - HP : x0;
         for (int row = ty; row < YR; row += TY) {
+            int gy = y0 - HP + row;
+            const bool rin = wrap || (unsigned)gy < (unsigned)H;
+            if (wrap) gy = wrap3(gy, H);
+            const int cy = row - HP;
             for (int col = tx; col < colsY; col += 32) {
-                int gy = y0 - HP + row, gx = (P.rect ? x0 - HP : x0) + col;
-                bool inside = true;
-                if (wrap) { gy = wrapn(gy, H); gx = wrapn(gx, W); }
-                else inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+                int gx = gx_base + col;
+                const bool inside = rin && (wrap || (unsigned)gx < (unsigned)W);
+                if (wrap) gx = wrap3(gx, W);
+                const float r = stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, row * pitchY + col);
                 // the own 1/|x| of the tile centre is kept for the final projection (self variant)
-                const int cy = row - HP, cx = P.rect ? col - HP : col;
-                float* rv = (!CROSS && (unsigned)cy < (unsigned)TY && (unsigned)cx < (unsigned)TX) ? &s_rinv[cy][cx] : nullptr;
-                stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, row * pitchY + col, rv);
+                const int cx = P.rect ? col - HP : col;
+                if (!CROSS && (unsigned)cy < (unsigned)TY && (unsigned)cx < (unsigned)TX) s_rinv[cy][cx] = r;
             }
         }
         if (!P.rect) {
-            {
-                const int row = ty;
-                for (int col = tx; col < XW; col += 32) {
-                    int gy = y0 + row, gx = x0 - HP + col;
-                    bool inside = true;
-                    if (wrap) { gy = wrapn(gy, H); gx = wrapn(gx, W); }
-                    else inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-                    stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, qX0 + row * XW + col, nullptr);
-                }
+            int gy = y0 + ty;
+            const bool rin = wrap || gy < H;
+            if (wrap) gy = wrap3(gy, H);
+            for (int col = tx; col < XW; col += 32) {
+                int gx = x0 - HP + col;
+                const bool inside = rin && (wrap || (unsigned)gx < (unsigned)W);
+                if (wrap) gx = wrap3(gx, W);
+                stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, qX0 + ty * XW + col);
             }
         }
     }
     __syncthreads();
 
     // ---- own unit vector
+    const int qY = (ty + HP) * pitchY + (P.rect ? tx + HP : tx);  // own pixel in the y-column / rectangle
+    const int qXo = qX0 + ty * XW + tx + HP;                        // own pixel in the x-row
     f32x2 e[kC2], G[kC2];
     float rp;
     if (CROSS) {
-        const float* src = P.emb + (int64_t)b * kC * N + (int64_t)(live ? y : 0) * W + (live ? x : 0);
+        const float* p = P.emb + (int64_t)b * kC * N + (int64_t)(live ? y : 0) * W + (live ? x : 0);
         float v[kC], ss = 0.f;
 #pragma unroll
         for (int c = 0; c < kC; ++c) {
-            v[c] = live ? __ldg(src + (int64_t)c * N) : 0.f;
+            v[c] = live ? __ldg(p) : 0.f;
+            p += N;
             ss = fmaf(v[c], v[c], ss);
         }
         rp = inv_norm(ss);
 #pragma unroll
         for (int i = 0; i < kC2; ++i) e[i] = pack2(v[2 * i] * rp, v[2 * i + 1] * rp);
     } else {
-        load_px(smem, (ty + HP) * pitchY + (P.rect ? tx + HP : tx), e);
+        load_px(smem, qY, e);
         rp = s_rinv[ty][tx];
     }
 #pragma unroll
@@ -207,28 +241,42 @@ fused2d_tiled(const Params P) {
     const bool want_loss = P.target != nullptr;
     const bool want_grad = P.grad != nullptr;
     const bool want_rev = !CROSS && want_grad;
-    const int64_t pix = (int64_t)(live ? y : 0) * W + (live ? x : 0);
-    const int64_t kbase = (int64_t)b * K * N;
+    // per-sample bases (64-bit) + 32-bit element offsets inside the sample (K * N < 2^31 is a plan requirement)
+    const uint32_t Nu = (uint32_t)N;
+    const uint32_t pix = (uint32_t)((live ? y : 0) * W + (live ? x : 0));
+    const float* tgt_b = want_loss ? P.target + (int64_t)b * K * N : nullptr;
+    const float* wgt_b = want_loss ? P.weight + (int64_t)b * K * N : nullptr;
+    const void* msk_b = nullptr;
+    if (MASK == PEA_MASK_U8) msk_b = reinterpret_cast<const uint8_t*>(P.mask) + (int64_t)b * K * N;
+    if (MASK == PEA_MASK_F32) msk_b = reinterpret_cast<const float*>(P.mask) + (int64_t)b * K * N;
+    float* affs_b = P.affs ? P.affs + (int64_t)b * K * N : nullptr;
     float lterm[kMaxK];  // per-offset loss terms of this pixel (reduced over the CTA after the loop)
 
     // target / weight / mask of the pair anchored here and of the pair anchored at p - o_k, fetched ONE OFFSET AHEAD
+    // (raw mask bits: converting at the load would stall the warp on it)
     struct KV { float t, w, t2, w2; uint32_t m, m2; };
     auto fetch = [&](int k) -> KV {
         KV v = {0.f, 0.f, 0.f, 0.f, 0u, 0u};
         if (!want_loss || k >= K) return v;
         const int dy = P.dy[k], dx = P.dx[k];
+        const uint32_t koff = (uint32_t)k * Nu;
         bool valid = live;
         if (!wrap) valid = valid && (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W;
-        const int64_t idx = kbase + (int64_t)k * N + pix;
-        if (valid) { v.t = __ldg(P.target + idx); v.w = __ldg(P.weight + idx); v.m = load_mask_raw(P.mask, P.mask_dtype, idx); }
+        if (valid) {
+            v.t = __ldg(tgt_b + koff + pix);
+            v.w = __ldg(wgt_b + koff + pix);
+            v.m = mask_raw<MASK>(msk_b, koff + pix);
+        }
         if (want_rev) {
             int qy = y - dy, qx = x - dx;
             bool v2 = live;
-            if (wrap) { qy = wrapn(qy, H); qx = wrapn(qx, W); }
+            if (wrap) { qy = wrap1(qy, H); qx = wrap1(qx, W); }
             else v2 = v2 && (unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W;
             if (v2) {
-                const int64_t idx2 = kbase + (int64_t)k * N + (int64_t)qy * W + qx;
-                v.t2 = __ldg(P.target + idx2); v.w2 = __ldg(P.weight + idx2); v.m2 = load_mask_raw(P.mask, P.mask_dtype, idx2);
+                const uint32_t i2 = koff + (uint32_t)(qy * W + qx);
+                v.t2 = __ldg(tgt_b + i2);
+                v.w2 = __ldg(wgt_b + i2);
+                v.m2 = mask_raw<MASK>(msk_b, i2);
             }
         }
         return v;
@@ -237,14 +285,11 @@ fused2d_tiled(const Params P) {
     KV cur = fetch(0);
     for (int k = 0; k < K; ++k) {
         const KV nxt = fetch(k + 1);
-        const int dy = P.dy[k], dx = P.dx[k];
+        const int sel = s_k.sel[k], delta = s_k.delta[k];
+        const int qo = sel ? qXo : qY;
         // ---------------- pair anchored here: partner p + o_k
-        int q;
-        if (P.rect) q = (ty + HP + dy) * pitchY + (tx + HP + dx);
-        else if (dx == 0) q = (ty + HP + dy) * pitchY + tx;
-        else q = qX0 + ty * XW + (tx + HP + dx);
         f32x2 xq[kC2];
-        load_px(smem, q, xq);
+        load_px(smem, qo + delta, xq);
         f32x2 d0 = 0ull, d1 = 0ull;
 #pragma unroll
         for (int i = 0; i < kC2; i += 2) {
@@ -252,14 +297,15 @@ fused2d_tiled(const Params P) {
             d1 = fma2(e[i + 1], xq[i + 1], d1);
         }
         float a = hsum2(d0, d1);
-        bool valid = live;
-        if (!wrap) valid = valid && (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W;
-        if (!valid) a = 0.f;
-        if (P.affs && live) P.affs[kbase + (int64_t)k * N + pix] = a;
+        if (!wrap) {
+            const bool valid = (unsigned)(y + P.dy[k]) < (unsigned)H && (unsigned)(x + P.dx[k]) < (unsigned)W;
+            if (!valid) a = 0.f;
+        }
+        if (affs_b && live) affs_b[(uint32_t)k * Nu + pix] = a;
         float lt = 0.f;
         if (want_loss) {
             // invalid pairs were fetched as t = w = m = 0: they contribute nothing
-            const float m = decode_mask(cur.m, P.mask_dtype);
+            const float m = mask_val<MASK>(cur.m);
             const float dd = a * m - cur.t * m;
             lt = cur.w * dd * dd;
             if (want_grad) {
@@ -269,12 +315,8 @@ fused2d_tiled(const Params P) {
             }
             // ---------------- pair anchored at p - o_k, whose partner is this pixel (self variant only)
             if (want_rev) {
-                int q2;
-                if (P.rect) q2 = (ty + HP - dy) * pitchY + (tx + HP - dx);
-                else if (dx == 0) q2 = (ty + HP - dy) * pitchY + tx;
-                else q2 = qX0 + ty * XW + (tx + HP - dx);
                 f32x2 xr[kC2];
-                load_px(smem, q2, xr);
+                load_px(smem, qo - delta, xr);
                 f32x2 r0 = 0ull, r1 = 0ull;
 #pragma unroll
                 for (int i = 0; i < kC2; i += 2) {
@@ -282,7 +324,7 @@ fused2d_tiled(const Params P) {
                     r1 = fma2(e[i + 1], xr[i + 1], r1);
                 }
                 const float a2 = hsum2(r0, r1);
-                const float m2 = decode_mask(cur.m2, P.mask_dtype);
+                const float m2 = mask_val<MASK>(cur.m2);
                 const float g2 = P.gcoef[k] * cur.w2 * m2 * m2 * (a2 - cur.t2);
 #pragma unroll
                 for (int i = 0; i < kC2; ++i) G[i] = fma2(pack2(g2, g2), xr[i], G[i]);
@@ -308,8 +350,9 @@ fused2d_tiled(const Params P) {
         for (int i = 0; i < kC2; ++i) {
             float lo, hi;
             unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
-            dst[(int64_t)(2 * i) * N] = lo;
-            dst[(int64_t)(2 * i + 1) * N] = hi;
+            dst[0] = lo;
+            dst[N] = hi;
+            dst += 2 * N;
         }
     }
 
@@ -354,7 +397,7 @@ static bool plan2d(const OffsetTable& tab, int H, int W, int wrap, Plan2D& plan)
         if (ax > P) P = ax;
         if (ay != 0 && ax != 0) rect = 1;
     }
-    if (P > 64) return false;
+    if (P > 64 || (int64_t)tab.K * H * W >= ((int64_t)1 << 31)) return false;
     const int cands[3] = {16, 12, 8};
     for (int i = 0; i < 3; ++i) {
         const int TY = cands[i];
@@ -373,7 +416,7 @@ static bool plan2d(const OffsetTable& tab, int H, int W, int wrap, Plan2D& plan)
 
 bool tiled2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wrap, bool need_grad_partner) {
     if (C != 16 || D != 1 || need_grad_partner) return false;
-    if (H < 8 || W < 16) return false;  // wrapn() covers at most three periods beyond the image
+    if (H < 8 || W < 16) return false;  // wrap3() covers at most three periods beyond the image
     Plan2D plan;
     return plan2d(tab, H, W, wrap, plan);
 }
@@ -384,19 +427,25 @@ int tiled2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap) {
     return B * ((H + plan.TY - 1) / plan.TY) * ((W + t2::TX - 1) / t2::TX);
 }
 
-template <int TY>
-static int launch2d_ty(const t2::Params& P, bool cross, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e;
-    if (cross) {
-        auto kern = t2::fused2d_tiled<TY, true>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(P);
-    } else {
-        auto kern = t2::fused2d_tiled<TY, false>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(P);
-    }
+template <int TY, bool CROSS, int MASK>
+static int launch2d_one(const t2::Params& P, int grid, size_t smem, cudaStream_t st) {
+    auto kern = t2::fused2d_tiled<TY, CROSS, MASK>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, TY * 32, smem, st>>>(P);
     return (int)cudaGetLastError();
+}
+
+template <int TY>
+static int launch2d_ty(const t2::Params& P, bool cross, int mask_dtype, int grid, size_t smem, cudaStream_t st) {
+    if (cross) {
+        if (mask_dtype == PEA_MASK_U8) return launch2d_one<TY, true, PEA_MASK_U8>(P, grid, smem, st);
+        if (mask_dtype == PEA_MASK_F32) return launch2d_one<TY, true, PEA_MASK_F32>(P, grid, smem, st);
+        return launch2d_one<TY, true, PEA_MASK_NONE>(P, grid, smem, st);
+    }
+    if (mask_dtype == PEA_MASK_U8) return launch2d_one<TY, false, PEA_MASK_U8>(P, grid, smem, st);
+    if (mask_dtype == PEA_MASK_F32) return launch2d_one<TY, false, PEA_MASK_F32>(P, grid, smem, st);
+    return launch2d_one<TY, false, PEA_MASK_NONE>(P, grid, smem, st);
 }
 
 // target == nullptr: forward only (affs must be given).  partner == nullptr: self variant.
@@ -407,7 +456,7 @@ int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const 
     if (!plan2d(tab, d.H, d.W, wrap, plan)) return PEA_E_MODE;
     t2::Params P;
     P.B = d.B; P.H = d.H; P.W = d.W; P.K = tab.K; P.P = plan.P;
-    P.wrap = wrap; P.rect = plan.rect; P.mask_dtype = mask_dtype;
+    P.wrap = wrap; P.rect = plan.rect;
     P.emb = emb; P.par = partner ? partner : emb;
     P.target = target; P.weight = weight; P.mask = mask;
     P.affs = affs; P.grad = grad; P.partials = partials;
@@ -418,9 +467,9 @@ int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const 
     }
     const int grid = d.B * ((d.H + plan.TY - 1) / plan.TY) * ((d.W + t2::TX - 1) / t2::TX);
     switch (plan.TY) {
-        case 16: return launch2d_ty<16>(P, partner != nullptr, grid, plan.smem, st);
-        case 12: return launch2d_ty<12>(P, partner != nullptr, grid, plan.smem, st);
-        default: return launch2d_ty<8>(P, partner != nullptr, grid, plan.smem, st);
+        case 16: return launch2d_ty<16>(P, partner != nullptr, mask_dtype, grid, plan.smem, st);
+        case 12: return launch2d_ty<12>(P, partner != nullptr, mask_dtype, grid, plan.smem, st);
+        default: return launch2d_ty<8>(P, partner != nullptr, mask_dtype, grid, plan.smem, st);
     }
 }
 
