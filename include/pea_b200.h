@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PEA_ABI_VERSION 1
+#define PEA_ABI_VERSION 2
 #define PEA_MAX_OFFSETS 64
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -76,9 +76,14 @@ size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, int cross);
  *   replaces  embedding2affs                 scripts_cvppp/loss/loss_embedding_mse.py:58-66   (border = WRAP)
  *             inf_embedding_loss_norm1/5     scripts_ac3ac4/loss/loss_embedding_mse.py:54-67,212-234 (border = ZERO)
  * affs[b,k,p] = <e^[b,:,p], u^[b,:,p+o_k]>,  e^ = emb / max(|emb|_2, 1e-12), u^ likewise from `partner`
- * (or e^ itself when partner == NULL).  offsets: host int32[K*3] as (dz, dy, dx). */
+ * (or e^ itself when partner == NULL).  offsets: host int32[K*3] as (dz, dy, dx).
+ * z-sharded volumes: the first `z_skip` slices of emb are halo received from the previous shard --
+ * they are read as neighbours but produce no output, so affs has D - z_skip slices.  `emb_plane` / `affs_plane`
+ * are the element strides between consecutive channel planes (0 = contiguous: D*H*W and (D - z_skip)*H*W), which
+ * lets emb / affs be z-range views of deeper buffers without a copy. */
 int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
                  const int32_t* offsets, int K, int border, int impl,
+                 int z_skip, int64_t emb_plane, int64_t affs_plane,
                  float* affs, void* workspace, size_t ws_bytes, void* stream);
 
 /* Fused embedding -> affinities -> weighted-MSE loss -> d loss / d embedding, one pass.

@@ -51,7 +51,7 @@ def _f32(values):
     return arr, arr.ctypes.data_as(c_float_p)
 
 
-def check_embedding(name, t, ndim=None):
+def check_embedding(name, t, ndim=None, make_contiguous=True):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
     if not t.is_cuda:
@@ -60,7 +60,7 @@ def check_embedding(name, t, ndim=None):
         raise TypeError(f"{name} must be float32, got {t.dtype}")
     if ndim is not None and t.dim() != ndim:
         raise ValueError(f"{name} must have {ndim} dimensions, got shape {tuple(t.shape)}")
-    return t.contiguous()
+    return t.contiguous() if make_contiguous else t
 
 
 def check_like(name, t, shape, dtypes=(torch.float32,)):
@@ -102,17 +102,48 @@ def _workspace(B, C, D, H, W, K, cross, device):
     return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
-def affs_fwd(emb, partner, offs3, border, impl=IMPL_AUTO):
-    """(B,C,[D,]H,W) -> (B,K,[D,]H,W) affinities.  emb/partner already validated + contiguous."""
+def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None):
+    """(B,C,[D,]H,W) -> (B,K,[D - z_skip,]H,W) affinities.  emb/partner already validated.
+
+    ``emb`` may be a z-range view ``buf[:, :, z0:z1]`` of a contiguous (B,C,Dtot,H,W) buffer and ``out`` a z-range
+    view of a contiguous (B,K,Dout,H,W) buffer (z-sharded inference): only the channel-plane stride differs from
+    the contiguous case and it is passed through to the kernel."""
+    impl = DEFAULT_IMPL if impl is None else impl
     B, C, D, H, W = _dims5(emb)
     K = offs3.shape[0]
-    spatial = emb.shape[2:]
-    affs = torch.empty((B, K) + tuple(spatial), dtype=torch.float32, device=emb.device)
+    spatial = tuple(emb.shape[2:])
+    emb_plane = 0
+    if emb.dim() == 5 and not emb.is_contiguous():
+        st = emb.stride()
+        if st[4] != 1 or st[3] != W or st[2] != H * W or st[0] != C * st[1]:
+            emb = emb.contiguous()
+        else:
+            emb_plane = st[1]
+    elif not emb.is_contiguous():
+        emb = emb.contiguous()
+    if partner is not None:
+        partner = partner.contiguous()
+    out_spatial = ((D - z_skip,) + spatial[1:]) if emb.dim() == 5 else spatial
+    affs_plane = 0
+    if out is None:
+        affs = torch.empty((B, K) + out_spatial, dtype=torch.float32, device=emb.device)
+    else:
+        affs = out
+        if tuple(affs.shape) != (B, K) + out_spatial or affs.dtype != torch.float32:
+            raise ValueError(f"out must be float32 of shape {(B, K) + out_spatial}")
+        if not affs.is_contiguous():
+            st = affs.stride()
+            if affs.dim() != 5 or st[4] != 1 or st[3] != W or st[2] != H * W or st[0] != K * st[1]:
+                raise ValueError("out must be contiguous or a z-range view of a contiguous buffer")
+            affs_plane = st[1]
     ws, n = _workspace(B, C, D, H, W, K, partner is not None, emb.device)
     keep, optr = _i32(offs3)
     with torch.cuda.device(emb.device):
-        rc = lib.pea_affs_fwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, _ptr(affs), _ptr(ws), n,
-                              _stream())
+        rc = lib.pea_affs_fwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, int(z_skip), emb_plane,
+                              affs_plane, _ptr(affs), _ptr(ws), n, _stream())
+    if rc == -8 and emb_plane and impl != IMPL_TILED:
+        # z-range view that the tiled kernel cannot take (shape / offsets): fall back to a contiguous copy
+        return affs_fwd(emb.contiguous(), partner, offs3, border, impl, z_skip, out)
     check("pea_affs_fwd", rc)
     return affs
 

@@ -8,7 +8,7 @@ namespace pea {
 int generic_partial_blocks(int64_t total);
 int launch_rinv(const float* emb, int C, const Dims& d, float* rinv, cudaStream_t st);
 int launch_fwd_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C, const Dims& d,
-                       const OffsetTable& tab, int wrap, float* affs, cudaStream_t st);
+                       const OffsetTable& tab, int wrap, int z_skip, int64_t affs_plane, float* affs, cudaStream_t st);
 int launch_fused_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C,
                          const Dims& d, const OffsetTable& tab, int wrap, int cross, const float* target,
                          const float* weight, const void* mask, int mask_dtype, const float* upstream, float* affs,
@@ -18,6 +18,10 @@ int launch_fused_generic(const float* emb, const float* par, const float* rinvE,
 bool tiled3d_norm5_eligible(int C, int D, int H, int W, const OffsetTable& tab, int border, int mask_dtype, bool cross,
                             const float* emb, const float* target, const float* weight);
 int tiled3d_norm5_blocks(int B, int H, int W);
+bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
+                          int64_t emb_plane);
+int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
+                       cudaStream_t st);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
 
@@ -144,15 +148,20 @@ extern "C" size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, 
 }
 
 extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
-                            const int32_t* offsets, int K, int border, int impl, float* affs, void* workspace,
-                            size_t ws_bytes, void* stream) {
+                            const int32_t* offsets, int K, int border, int impl, int z_skip, int64_t emb_plane,
+                            int64_t affs_plane, float* affs, void* workspace, size_t ws_bytes, void* stream) {
     if (!emb || !offsets || !affs || !workspace) return PEA_E_NULL;
     if (impl != PEA_IMPL_AUTO && impl != PEA_IMPL_GENERIC && impl != PEA_IMPL_TILED) return PEA_E_MODE;
     Dims d;
     int rc = check_volume(B, C, D, H, W, K, d);
     if (rc) return rc;
     if (border != PEA_BORDER_WRAP && border != PEA_BORDER_ZERO) return PEA_E_MODE;
+    if (z_skip < 0 || z_skip >= D) return PEA_E_SHAPE;
     if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
+    const int64_t HW = (int64_t)H * W;
+    if (emb_plane == 0) emb_plane = d.N;
+    if (affs_plane == 0) affs_plane = (int64_t)(D - z_skip) * HW;
+    if (emb_plane < d.N || affs_plane < (int64_t)(D - z_skip) * HW) return PEA_E_SHAPE;
     const int cross = partner != nullptr;
     Workspace ws;
     carve(workspace, B, d.N, K, cross, ws);
@@ -160,15 +169,22 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     OffsetTable tab;
     fill_offsets(offsets, K, tab);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, false);
-    if (impl == PEA_IMPL_TILED && !tiled2_ok) return PEA_E_MODE;
-    if (tiled2_ok && impl != PEA_IMPL_GENERIC)
-        return launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, nullptr, nullptr, nullptr, PEA_MASK_NONE,
-                              affs, nullptr, nullptr, st);
+    const bool contiguous = emb_plane == d.N;
+    const bool plain = contiguous && z_skip == 0 && affs_plane == d.N;
+    const bool tiled2_ok = plain && tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, false);
+    const bool tiled3_ok = tiled3d_fwd_eligible(C, W, tab, border, cross != 0, emb, emb_plane);
+    if (impl == PEA_IMPL_TILED && !tiled2_ok && !tiled3_ok) return PEA_E_MODE;
+    if (impl != PEA_IMPL_GENERIC) {
+        if (tiled3_ok) return launch_fwd3d_norm5(emb, d, z_skip, emb_plane, affs_plane, affs, st);
+        if (tiled2_ok)
+            return launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, nullptr, nullptr, nullptr,
+                                  PEA_MASK_NONE, affs, nullptr, nullptr, st);
+    }
+    if (!contiguous) return PEA_E_MODE;  // the table-driven kernel reads contiguous volumes only
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
-    return launch_fwd_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP, affs,
-                              st);
+    return launch_fwd_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP,
+                              z_skip, affs_plane, affs, st);
 }
 
 extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,

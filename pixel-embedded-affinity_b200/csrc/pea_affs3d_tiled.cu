@@ -377,6 +377,164 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     }
 }
 
+
+// ================================================================================================================
+// Forward only: inf_embedding_loss_norm5 (scripts_ac3ac4/loss/loss_embedding_mse.py:212-234) and the z-sharded
+// full-volume inference.  Same z-march, but only the "-shift" side of every offset is needed: a 4-slice register
+// ring of unit vectors, a y-column box with 9 rows of upper halo, the y-27 arm and an x-row box with 28 columns of
+// left halo.  `z_skip` leading slices are halo from the previous z-shard: they only warm the ring up (read straight
+// from global, no tiles), nothing is written for them.
+template <int TY>
+struct alignas(1024) StageF {
+    float sY[kC][TY + HY][TX];    // rows y0-9 .. y0+TY-1
+    float sAm[kC][TY][TX];        // rows y0-27 ..
+    float sX[kC][TY][TX + XPAD];  // cols x0-28 .. x0+31
+};
+
+struct ParamsF {
+    int B, D, H, W, z_skip;
+    int64_t emb_plane, affs_plane;  // elements between channel planes of emb / affs
+    const float* emb;
+    float* affs;
+};
+
+template <int TY>
+__global__ void __launch_bounds__(TY * 32, 2)
+fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
+            const __grid_constant__ CUtensorMap mapX, const ParamsF P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    StageF<TY>& S = *reinterpret_cast<StageF<TY>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    __shared__ uint64_t barY, barX;
+    __shared__ uint32_t cntY, cntX;
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm);
+    constexpr uint32_t kBytesX = sizeof(S.sX);
+    constexpr int CHS_Y = (TY + HY) * TX, CHS_A = TY * TX, XWF = TX + XPAD, CHS_X = TY * XWF;
+    constexpr uint32_t kWarps = TY;
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int D = P.D, H = P.H, W = P.W, zs = P.z_skip;
+    const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+    int bid = blockIdx.x;
+    const int tix = bid % tiles_x;
+    bid /= tiles_x;
+    const int tiy = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int x0 = tix * TX, y0 = tiy * TY;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool live = (x < W) && (y < H);
+    const int64_t HW = (int64_t)H * W;
+    const int64_t pix = (int64_t)(live ? y : 0) * W + (live ? x : 0);
+
+    auto issueY = [&](int z) {
+        mbar_arrive_expect_tx(&barY, kBytesY);
+        tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
+        tma_load_5d(&S.sAm[0][0][0], &mapA, &barY, x0, y0 - FAR, z, 0, b);
+    };
+    auto issueX = [&](int z) {
+        mbar_arrive_expect_tx(&barX, kBytesX);
+        tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&barY, 1);
+        mbar_init(&barX, 1);
+        cntY = cntX = 0;
+        mbar_fence_init();
+        if (zs < D) {
+            issueY(zs);
+            issueX(zs);
+        }
+    }
+    __syncthreads();
+
+    f32x2 re[5][kC2];  // slot j: unit vector of slice z - j
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int i = 0; i < kC2; ++i) re[s][i] = 0ull;
+
+    // ---- ring warm-up on the halo slices (previous shard's last slices): own column straight from global
+    const float* emb_b = P.emb + (int64_t)b * kC * P.emb_plane + pix;
+    for (int z = (zs > 4 ? zs - 4 : 0); z < zs; ++z) {
+        float v[kC], ss = 0.f;
+        const float* p = emb_b + (int64_t)z * HW;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+            v[c] = live ? __ldg(p) : 0.f;
+            p += P.emb_plane;
+            ss = fmaf(v[c], v[c], ss);
+        }
+        const float r = inv_norm(ss);
+#pragma unroll
+        for (int s = 4; s >= 2; --s)
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) re[s][i] = re[s - 1][i];
+#pragma unroll
+        for (int i = 0; i < kC2; ++i) re[1][i] = pack2(v[2 * i] * r, v[2 * i + 1] * r);
+    }
+
+    float* affs_b = P.affs + (int64_t)b * 12 * P.affs_plane + pix;
+    int it = 0;
+    for (int z = zs; z < D; ++z, ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        float* out = affs_b + (int64_t)(z - zs) * HW;
+        f32x2 (&e)[kC2] = re[0];
+        // ---------------- y part
+        mbar_wait(&barY, par);
+        {
+            const float* own = &S.sY[0][ty + HY][tx];
+            f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) e[i] = pack2(own[(2 * i) * CHS_Y], own[(2 * i + 1) * CHS_Y]);
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                s0 = fma2(e[i], e[i], s0);
+                s1 = fma2(e[i + 1], e[i + 1], s1);
+            }
+            const float rp = inv_norm(hsum2(s0, s1));
+            const f32x2 rp2 = pack2(rp, rp);
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) e[i] = mul2(e[i], rp2);
+        }
+        f32x2 dummyG[kC2];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const float* nb = (g < 3) ? &S.sY[0][ty + HY - s][tx] : &S.sAm[0][ty][tx];
+            float a;
+            inplane_pair<false>(nb, (g < 3) ? CHS_Y : CHS_A, e, dummyG, 0.f, 0.f, 0.f, a);
+            if (live) out[(int64_t)(3 * g + 1) * P.affs_plane] = (y >= s) ? a : 0.f;
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(it + 1) - 1 && z + 1 < D) issueY(z + 1);
+        // ---------------- x part
+        mbar_wait(&barX, par);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            float a;
+            inplane_pair<false>(&S.sX[0][ty][tx + XPAD - s], CHS_X, e, dummyG, 0.f, 0.f, 0.f, a);
+            if (live) out[(int64_t)(3 * g + 2) * P.affs_plane] = (x >= s) ? a : 0.f;
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(it + 1) - 1 && z + 1 < D) issueX(z + 1);
+        // ---------------- z part: ring
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) {
+            f32x2 d0 = 0ull, d1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                d0 = fma2(re[0][i], re[j][i], d0);
+                d1 = fma2(re[0][i + 1], re[j][i + 1], d1);
+            }
+            if (live) out[(int64_t)(3 * (j - 1)) * P.affs_plane] = (z >= j) ? hsum2(d0, d1) : 0.f;
+        }
+#pragma unroll
+        for (int s = 4; s >= 1; --s)
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) re[s][i] = re[s - 1][i];
+    }
+}
+
 }  // namespace t3
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -425,6 +583,37 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
         kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
     }
+    return (int)cudaGetLastError();
+}
+
+bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
+                          int64_t emb_plane) {
+    static const int ref[12][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-2, 0, 0}, {0, -3, 0}, {0, 0, -3},
+                                   {-3, 0, 0}, {0, -9, 0}, {0, 0, -9}, {-4, 0, 0}, {0, -27, 0}, {0, 0, -27}};
+    if (C != 16 || tab.K != 12 || border != PEA_BORDER_ZERO || cross) return false;
+    if (W % 4 != 0 || (reinterpret_cast<uintptr_t>(emb) & 15) || (emb_plane % 4) != 0) return false;
+    for (int k = 0; k < 12; ++k)
+        if (tab.dz[k] != ref[k][0] || tab.dy[k] != ref[k][1] || tab.dx[k] != ref[k][2]) return false;
+    return true;
+}
+
+int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
+                       cudaStream_t st) {
+    constexpr int TY = 8;
+    CUtensorMap mY, mA, mX;
+    int rc;
+    if ((rc = encode_volume_map(&mY, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY + t3::HY, 1, 16, emb_plane))) return rc;
+    if ((rc = encode_volume_map(&mA, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY, 1, 16, emb_plane))) return rc;
+    if ((rc = encode_volume_map(&mX, emb, d.B, 16, d.D, d.H, d.W, t3::TX + t3::XPAD, TY, 1, 16, emb_plane))) return rc;
+    t3::ParamsF P;
+    P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W; P.z_skip = z_skip;
+    P.emb_plane = emb_plane; P.affs_plane = affs_plane; P.emb = emb; P.affs = affs;
+    const int grid = d.B * ((d.H + TY - 1) / TY) * ((d.W + t3::TX - 1) / t3::TX);
+    const size_t smem = sizeof(t3::StageF<TY>) + 1024;
+    auto kern = t3::fwd3d_norm5<TY>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, P);
     return (int)cudaGetLastError();
 }
 

@@ -58,15 +58,18 @@ __device__ __forceinline__ float dot(const float (&a)[C], const float (&b)[C]) {
 template <int C>
 __global__ void __launch_bounds__(kThreads)
 fwd_generic(const float* __restrict__ emb, const float* __restrict__ par, const float* __restrict__ rinvE,
-            const float* __restrict__ rinvU, Dims d, OffsetTable tab, int wrap, float* __restrict__ affs) {
+            const float* __restrict__ rinvU, Dims d, OffsetTable tab, int wrap, int z_skip, int64_t affs_plane,
+            float* __restrict__ affs) {
     const int64_t total = (int64_t)d.B * d.N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = i / d.N, p = i - b * d.N;
         const int x = (int)(p % d.W);
         const int y = (int)((p / d.W) % d.H);
         const int z = (int)(p / ((int64_t)d.W * d.H));
+        if (z < z_skip) continue;  // halo slices of the previous z-shard: neighbours only
         float e[C];
         load_unit<C>(emb, rinvE, b, p, d.N, e);
+        const int64_t pout = p - (int64_t)z_skip * d.W * d.H;
         for (int k = 0; k < tab.K; ++k) {
             int64_t q;
             float a = 0.f;
@@ -75,7 +78,7 @@ fwd_generic(const float* __restrict__ emb, const float* __restrict__ par, const 
                 load_unit<C>(par, rinvU, b, q, d.N, un);
                 a = dot<C>(e, un);
             }
-            affs[(b * tab.K + k) * d.N + p] = a;
+            affs[(b * tab.K + k) * affs_plane + pout] = a;
         }
     }
 }
@@ -224,9 +227,10 @@ int launch_rinv(const float* emb, int C, const Dims& d, float* rinv, cudaStream_
 }
 
 int launch_fwd_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C, const Dims& d,
-                       const OffsetTable& tab, int wrap, float* affs, cudaStream_t st) {
+                       const OffsetTable& tab, int wrap, int z_skip, int64_t affs_plane, float* affs, cudaStream_t st) {
     const int grid = grid_for((int64_t)d.B * d.N);
-    PEA_DISPATCH_C(C, fwd_generic<CC><<<grid, kThreads, 0, st>>>(emb, par, rinvE, rinvU, d, tab, wrap, affs));
+    PEA_DISPATCH_C(C, fwd_generic<CC><<<grid, kThreads, 0, st>>>(emb, par, rinvE, rinvU, d, tab, wrap, z_skip, affs_plane,
+                                                                 affs));
     return (int)cudaGetLastError();
 }
 

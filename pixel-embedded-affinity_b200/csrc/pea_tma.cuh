@@ -65,13 +65,15 @@ inline EncodeTiledFn get_encode_tiled() {
 }
 
 // returns 0 on success, a CUresult (> 0) otherwise
+// `plane` = elements between consecutive channel planes (>= D*H*W: the volume may be a z-range view of a deeper buffer)
 inline int encode_volume_map(CUtensorMap* map, const float* base, int B, int C, int D, int H, int W, int bx, int by,
-                             int bz, int bc) {
+                             int bz, int bc, int64_t plane = 0) {
     EncodeTiledFn fn = get_encode_tiled();
     if (!fn) return (int)cudaErrorNotSupported;
     const cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * D * 4,
-                                   (cuuint64_t)W * H * D * C * 4};
+    if (plane <= 0) plane = (int64_t)W * H * D;
+    const cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)plane * 4,
+                                   (cuuint64_t)plane * C * 4};
     const cuuint32_t box[5] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)bc, 1u};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
