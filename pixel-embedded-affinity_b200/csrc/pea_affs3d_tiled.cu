@@ -455,21 +455,30 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
     // ---- ring warm-up on the halo slices (previous shard's last slices): own column straight from global
     const float* emb_b = P.emb + (int64_t)b * kC * P.emb_plane + pix;
     for (int z = (zs > 4 ? zs - 4 : 0); z < zs; ++z) {
-        float v[kC], ss = 0.f;
+        // same arithmetic order as the tile path below, so slabs reproduce the whole-volume result bit for bit
+        f32x2 v[kC2];
         const float* p = emb_b + (int64_t)z * HW;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) {
-            v[c] = live ? __ldg(p) : 0.f;
-            p += P.emb_plane;
-            ss = fmaf(v[c], v[c], ss);
+        for (int i = 0; i < kC2; ++i) {
+            const float lo = live ? __ldg(p) : 0.f;
+            const float hi = live ? __ldg(p + P.emb_plane) : 0.f;
+            p += 2 * P.emb_plane;
+            v[i] = pack2(lo, hi);
         }
-        const float r = inv_norm(ss);
+        f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+        for (int i = 0; i < kC2; i += 2) {
+            s0 = fma2(v[i], v[i], s0);
+            s1 = fma2(v[i + 1], v[i + 1], s1);
+        }
+        const float r = inv_norm(hsum2(s0, s1));
+        const f32x2 r2 = pack2(r, r);
 #pragma unroll
         for (int s = 4; s >= 2; --s)
 #pragma unroll
             for (int i = 0; i < kC2; ++i) re[s][i] = re[s - 1][i];
 #pragma unroll
-        for (int i = 0; i < kC2; ++i) re[1][i] = pack2(v[2 * i] * r, v[2 * i + 1] * r);
+        for (int i = 0; i < kC2; ++i) re[1][i] = mul2(v[i], r2);
     }
 
     float* affs_b = P.affs + (int64_t)b * 12 * P.affs_plane + pix;
