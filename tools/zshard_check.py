@@ -1,0 +1,33 @@
+"""Run under torchrun (one rank per GPU): z-sharded affinities with the real NCCL halo exchange must equal, bit for
+bit, the same slab cut out of the whole-volume result computed locally.  Prints one OK line per rank."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pea_b200 as P  # noqa: E402
+from pea_b200.zshard import ZShard, sharded_affinities  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+D, H, W = 37, 96, 128
+g = torch.Generator(device="cpu").manual_seed(7)
+vol = torch.randn((1, 16, D, H, W), generator=g).to(dev)   # identical on every rank
+whole = P.inf_embedding_loss_norm5(vol)
+sh = ZShard(1, 16, D, H, W, rank, world, dev)
+sh.own.copy_(vol[:, :, sh.z0:sh.z1])
+if sh.halo:
+    sh.buf[:, :, :sh.halo].fill_(float("nan"))
+for it in range(3):
+    out = sharded_affinities(sh)
+    ok = torch.equal(out, whole[:, :, sh.z0:sh.z1])
+    assert ok, f"rank {rank} iteration {it}: slab differs from the whole-volume result"
+torch.cuda.synchronize()
+dist.barrier()
+print(f"zshard_check OK rank {rank}/{world} slab [{sh.z0},{sh.z1}) halo {sh.halo_bytes()} B", flush=True)
+dist.destroy_process_group()
