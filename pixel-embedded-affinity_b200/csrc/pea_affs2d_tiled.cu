@@ -16,6 +16,7 @@
 //     self variant with gradient, one reverse neighbour (pair anchored at p - o), 4 LDS.128 + 16 packed FMAs each;
 //   * per-offset loss terms go to shared memory and are reduced in a fixed order -> one row of partials per CTA.
 #include "pea_common.cuh"
+#include <cstdlib>
 
 namespace pea {
 namespace t2 {
@@ -101,15 +102,13 @@ __device__ __forceinline__ void load_px(const float* __restrict__ tile, int q, f
 }
 
 // Normalised embedding of one staged pixel (fetched channel-planar from global) -> shared memory; returns 1/|x|.
-__device__ __forceinline__ float stage_pixel(const float* __restrict__ src, int64_t N, bool inside, float* tile, int q) {
+// `base` is the sample's channel-0 plane; `off` the 32-bit element offset of the pixel (16 H W < 2^31 by the plan).
+__device__ __forceinline__ float stage_pixel(const float* __restrict__ base, uint32_t off, uint32_t Nu, bool inside,
+                                             float* tile, int q) {
     float v[kC];
     if (inside) {
-        const float* p = src;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) {
-            v[c] = __ldg(p);
-            p += N;
-        }
+        for (int c = 0; c < kC; ++c) v[c] = __ldg(base + (off + (uint32_t)c * Nu));
     } else {
 #pragma unroll
         for (int c = 0; c < kC; ++c) v[c] = 0.f;
@@ -121,11 +120,11 @@ __device__ __forceinline__ float stage_pixel(const float* __restrict__ src, int6
         s1 = fmaf(v[c + 1], v[c + 1], s1);
     }
     const float r = inv_norm(s0 + s1);
-    float4* base = reinterpret_cast<float4*>(tile) + (size_t)q * 4;
+    float4* dst = reinterpret_cast<float4*>(tile) + (size_t)q * 4;
     const int sw = swz(q);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        base[j ^ sw] = make_float4(v[4 * j] * r, v[4 * j + 1] * r, v[4 * j + 2] * r, v[4 * j + 3] * r);
+        dst[j ^ sw] = make_float4(v[4 * j] * r, v[4 * j + 1] * r, v[4 * j + 2] * r, v[4 * j + 3] * r);
     return r;
 }
 
@@ -146,7 +145,9 @@ struct KTab {
     int delta[kMaxK];  // staged-pixel index of (p + o) minus that of p within the region
 };
 
-template <int TY, bool CROSS, int MASK>
+// KU > 0: the offset loop is fully unrolled over KU slots (K <= KU), every per-offset quantity is statically indexed
+// (registers, constant-bank immediates); KU == 0: runtime loop for longer tables.
+template <int TY, bool CROSS, int MASK, int KU>
 __global__ void __launch_bounds__(TY * 32, (TY <= 12) ? 2 : 1)
 fused2d_tiled(const Params P) {
     extern __shared__ __align__(16) float smem[];
@@ -194,7 +195,7 @@ fused2d_tiled(const Params P) {
                 int gx = gx_base + col;
                 const bool inside = rin && (wrap || (unsigned)gx < (unsigned)W);
                 if (wrap) gx = wrap3(gx, W);
-                const float r = stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, row * pitchY + col);
+                const float r = stage_pixel(stage_src, (uint32_t)(gy * W + gx), (uint32_t)N, inside, smem, row * pitchY + col);
                 // the own 1/|x| of the tile centre is kept for the final projection (self variant)
                 const int cx = P.rect ? col - HP : col;
                 if (!CROSS && (unsigned)cy < (unsigned)TY && (unsigned)cx < (unsigned)TX) s_rinv[cy][cx] = r;
@@ -208,7 +209,7 @@ fused2d_tiled(const Params P) {
                 int gx = x0 - HP + col;
                 const bool inside = rin && (wrap || (unsigned)gx < (unsigned)W);
                 if (wrap) gx = wrap3(gx, W);
-                stage_pixel(stage_src + (int64_t)gy * W + gx, N, inside, smem, qX0 + ty * XW + col);
+                stage_pixel(stage_src, (uint32_t)(gy * W + gx), (uint32_t)N, inside, smem, qX0 + ty * XW + col);
             }
         }
     }
@@ -220,12 +221,12 @@ fused2d_tiled(const Params P) {
     f32x2 e[kC2], G[kC2];
     float rp;
     if (CROSS) {
-        const float* p = P.emb + (int64_t)b * kC * N + (int64_t)(live ? y : 0) * W + (live ? x : 0);
+        const float* eb = P.emb + (int64_t)b * kC * N;
+        const uint32_t po = (uint32_t)((live ? y : 0) * W + (live ? x : 0));
         float v[kC], ss = 0.f;
 #pragma unroll
         for (int c = 0; c < kC; ++c) {
-            v[c] = live ? __ldg(p) : 0.f;
-            p += N;
+            v[c] = live ? __ldg(eb + (po + (uint32_t)c * (uint32_t)N)) : 0.f;
             ss = fmaf(v[c], v[c], ss);
         }
         rp = inv_norm(ss);
@@ -250,7 +251,7 @@ fused2d_tiled(const Params P) {
     if (MASK == PEA_MASK_U8) msk_b = reinterpret_cast<const uint8_t*>(P.mask) + (int64_t)b * K * N;
     if (MASK == PEA_MASK_F32) msk_b = reinterpret_cast<const float*>(P.mask) + (int64_t)b * K * N;
     float* affs_b = P.affs ? P.affs + (int64_t)b * K * N : nullptr;
-    float lterm[kMaxK];  // per-offset loss terms of this pixel (reduced over the CTA after the loop)
+    float lterm[KU > 0 ? KU : kMaxK];  // per-offset loss terms of this pixel (reduced over the CTA after the loop)
 
     // target / weight / mask of the pair anchored here and of the pair anchored at p - o_k, fetched ONE OFFSET AHEAD
     // (raw mask bits: converting at the load would stall the warp on it)
@@ -283,7 +284,9 @@ fused2d_tiled(const Params P) {
     };
 
     KV cur = fetch(0);
-    for (int k = 0; k < K; ++k) {
+#pragma unroll(KU > 0 ? KU : 1)
+    for (int k = 0; k < (KU > 0 ? KU : K); ++k) {
+        if (KU > 0 && k >= K) break;
         const KV nxt = fetch(k + 1);
         const int sel = s_k.sel[k], delta = s_k.delta[k];
         const int qo = sel ? qXo : qY;
@@ -345,14 +348,13 @@ fused2d_tiled(const Params P) {
         float eg = hsum2(p0, p1);
         if (!(rp < 1e12f)) eg = 0.f;
         const f32x2 neg = pack2(-eg, -eg), r2 = pack2(rp, rp);
-        float* dst = P.grad + (int64_t)b * kC * N + pix;
+        float* gb = P.grad + (int64_t)b * kC * N;
 #pragma unroll
         for (int i = 0; i < kC2; ++i) {
             float lo, hi;
             unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
-            dst[0] = lo;
-            dst[N] = hi;
-            dst += 2 * N;
+            gb[pix + (uint32_t)(2 * i) * Nu] = lo;
+            gb[pix + (uint32_t)(2 * i + 1) * Nu] = hi;
         }
     }
 
@@ -360,7 +362,9 @@ fused2d_tiled(const Params P) {
     if (want_loss && P.partials) {
         __syncthreads();  // everyone is done with the tile
         float* scratch = smem;  // [K][NT]
-        for (int k = 0; k < K; ++k) scratch[k * NT + threadIdx.x] = lterm[k];
+#pragma unroll(KU > 0 ? KU : 1)
+        for (int k = 0; k < (KU > 0 ? KU : K); ++k)
+            if (k < K) scratch[k * NT + threadIdx.x] = lterm[k];
         __syncthreads();
         for (int k = ty; k < K; k += TY) {
             float v = 0.f;
@@ -397,16 +401,19 @@ static bool plan2d(const OffsetTable& tab, int H, int W, int wrap, Plan2D& plan)
         if (ax > P) P = ax;
         if (ay != 0 && ax != 0) rect = 1;
     }
-    if (P > 64 || (int64_t)tab.K * H * W >= ((int64_t)1 << 31)) return false;
+    if (P > 64 || (int64_t)(tab.K > 16 ? tab.K : 16) * H * W >= ((int64_t)1 << 31)) return false;
     const int cands[3] = {16, 12, 8};
+    const char* force = getenv("PEA_TUNE_TY2D");  // tuning aid only: pin the tile height
     for (int i = 0; i < 3; ++i) {
         const int TY = cands[i];
+        if (force && atoi(force) != TY) continue;
         const size_t tile = rect ? (size_t)16 * (TY + 2 * P) * (t2::TX + 2 * P) * 4
                                  : (size_t)16 * ((size_t)(TY + 2 * P) * t2::TX + (size_t)TY * (t2::TX + 2 * P)) * 4;
         const size_t scratch = (size_t)tab.K * TY * 32 * 4;
         const size_t smem = tile > scratch ? tile : scratch;
         // prefer two resident CTAs per SM (113 KB each); accept one CTA (up to ~220 KB) for the largest halos
-        if (smem <= 110 * 1024 || (i == 2 && smem <= 220 * 1024) || (smem <= 220 * 1024 && TY == 12 && P > 16)) {
+        if (smem <= 110 * 1024 || (i == 2 && smem <= 220 * 1024) || (smem <= 220 * 1024 && TY == 12 && P > 16) ||
+            (force && smem <= 220 * 1024)) {
             plan.TY = TY; plan.P = P; plan.rect = rect; plan.smem = smem;
             return true;
         }
@@ -427,13 +434,21 @@ int tiled2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap) {
     return B * ((H + plan.TY - 1) / plan.TY) * ((W + t2::TX - 1) / t2::TX);
 }
 
-template <int TY, bool CROSS, int MASK>
-static int launch2d_one(const t2::Params& P, int grid, size_t smem, cudaStream_t st) {
-    auto kern = t2::fused2d_tiled<TY, CROSS, MASK>;
+constexpr int kStaticK = 10;  // multi_offset(5 shifts, neighbor 4): every shipped 2-D config and its deep-supervision prefixes
+
+template <int TY, bool CROSS, int MASK, int KU>
+static int launch2d_k(const t2::Params& P, int grid, size_t smem, cudaStream_t st) {
+    auto kern = t2::fused2d_tiled<TY, CROSS, MASK, KU>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, TY * 32, smem, st>>>(P);
     return (int)cudaGetLastError();
+}
+
+template <int TY, bool CROSS, int MASK>
+static int launch2d_one(const t2::Params& P, int grid, size_t smem, cudaStream_t st) {
+    if (P.K <= kStaticK) return launch2d_k<TY, CROSS, MASK, kStaticK>(P, grid, smem, st);
+    return launch2d_k<TY, CROSS, MASK, 0>(P, grid, smem, st);
 }
 
 template <int TY>
