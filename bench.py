@@ -48,13 +48,17 @@ WORKLOADS = {
                  descr="BBBC039V1-shaped 2D batch: B=8, 16ch 520x696, multi_offset([1,3,5,9,11],4), K=10"),
     "cfg3": dict(nd=3, B=4, spatial=(18, 160, 160), shifts=None,
                  descr="AC3/AC4-shaped 3D patch: B=4, 16ch 18x160x160, 12 anisotropic offsets (norm5), K=12"),
+    "cfg3x": dict(nd=3, B=4, spatial=(18, 160, 160), shifts=None, cross=True,
+                  descr="cfg3 shape, two-view loss (ema_embedding_loss_norm5, second view detached), K=12"),
+    "cfg2x": dict(nd=2, B=8, spatial=(520, 696), shifts=[1, 3, 5, 9, 11], cross=True,
+                  descr="cfg2 shape, two-view loss (ema_embedding_loss, second view detached), K=10"),
 }
 
 
 def algorithmic_bytes_per_step(w):
     """read E 4C + target 4K + weight 4K (+ mask K, 2D) + write grad 4C + affs 4K, per spatial voxel."""
     K = 12 if w["nd"] == 3 else 2 * len(w["shifts"])
-    per_voxel = 4 * C + 4 * K + 4 * K + (K if w["nd"] == 2 else 0) + 4 * C + 4 * K
+    per_voxel = 4 * C + 4 * K + 4 * K + (K if w["nd"] == 2 else 0) + 4 * C + 4 * K + (4 * C if w.get("cross") else 0)
     return per_voxel * w["B"] * int(np.prod(w["spatial"])), K
 
 
@@ -194,8 +198,13 @@ def device_inputs(P, w, seed, device):
     return lab, emb, tgt, wgt, msk, offsets
 
 
-def our_step(P, w, e, tgt, wgt, msk, offsets, crit):
-    if w["nd"] == 2:
+def our_step(P, w, e, tgt, wgt, msk, offsets, crit, partner=None):
+    if w.get("cross"):
+        if w["nd"] == 2:
+            loss, _ = P.ema_embedding_loss(e, partner, tgt, wgt, msk, crit, offsets)
+        else:
+            loss, _ = P.ema_embedding_loss_norm5(e, partner, tgt, wgt, crit)
+    elif w["nd"] == 2:
         loss, _, _ = P.embedding_loss(e, tgt, wgt, msk, crit, offsets)
     else:
         loss, _ = P.embedding_loss_norm5(e, tgt, wgt, crit)
@@ -211,16 +220,17 @@ def time_workload(P, w, steps, warmup, device, flush, dist_on):
     lab, emb, tgt, wgt, msk, offsets = device_inputs(P, w, 0, device)
     crit = P.WeightedMSE()
     e = emb.clone().requires_grad_(True)
+    partner = torch.randn_like(emb) if w.get("cross") else None
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for _ in range(2):
-            our_step(P, w, e, tgt, wgt, msk, offsets, crit)
+            our_step(P, w, e, tgt, wgt, msk, offsets, crit, partner)
             e.grad = None
     torch.cuda.current_stream().wait_stream(side)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        loss = our_step(P, w, e, tgt, wgt, msk, offsets, crit)
+        loss = our_step(P, w, e, tgt, wgt, msk, offsets, crit, partner)
     for _ in range(max(warmup, 3)):
         flush.zero_()
         graph.replay()
@@ -416,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
         achieved = alg_bytes / (statistics.mean(res["per_ms"]) * 1e-3) / 1e9
         also = {}
         if world == 1 and not args.quick:
-            for name in ("cfg1", "cfg2", "cfg3"):
+            for name in ("cfg1", "cfg2", "cfg3", "cfg2x", "cfg3x"):
                 if name == args.workload:
                     continue
                 ww = WORKLOADS[name]
@@ -475,7 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="skip the other workloads (the `also` block)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from an ncu capture (for the roofline object)")

@@ -32,6 +32,10 @@ int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const 
                    const float* target, const float* weight, const void* mask, int mask_dtype, float* affs,
                    float* partials, float* grad, cudaStream_t st);
 
+int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab,
+                         const float* target, const float* weight, float* affs, float* partials, float* grad,
+                         cudaStream_t st);
+
 struct LossScale {
     float norm[PEA_MAX_OFFSETS];
     float coef[PEA_MAX_OFFSETS];
@@ -216,7 +220,8 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // ---- tiled single-kernel path for the offset sets it specialises (same results, see tests)
-    const bool tiled3_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb, target, weight);
+    const bool tiled3_ok = tiled3d_norm5_eligible(C, D, H, W, tab, border, mask_dtype, cross != 0, emb, target, weight) &&
+                           grad_partner == nullptr;
     const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr);
     if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC) {
@@ -231,7 +236,9 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     if (tiled_ok && impl != PEA_IMPL_GENERIC) {
         // the per-voxel plane at the head of the workspace doubles as the (much smaller) partials array
         float* parts = ws.rinvE;
-        if ((rc = launch_fused3d_norm5(emb, d, tab, target, weight, affs, parts, grad_emb, st))) return rc;
+        rc = cross ? launch_cross3d_norm5(emb, partner, d, tab, target, weight, affs, parts, grad_emb, st)
+                   : launch_fused3d_norm5(emb, d, tab, target, weight, affs, parts, grad_emb, st);
+        if (rc) return rc;
         finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, tiled3d_norm5_blocks(B, H, W), K, sc, loss_out);
         return (int)cudaGetLastError();
     }

@@ -446,12 +446,26 @@ def test_tiled3d_matches_generic_and_oracle(P, O, B, D, H, W, seed):
             l.backward()
             with torch.no_grad():   # forward-only evaluation (validation loop): no gradient buffers
                 l_ng, a_ng = P.embedding_loss_norm5(dev(emb), dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=1.5)
+            # two-view variant, second view detached (the shipped training loop): gradient w.r.t. the first view
+            e2 = dev(emb, True)
+            lx, ax = P.ema_embedding_loss_norm5(e2, dev(ema), dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=1.5)
+            lx.backward()
             out[name] = (float(l.detach()), a.cpu(), e.grad.cpu(), float(l_ng), a_ng.cpu())
+            out[name + "_x"] = (float(lx.detach()), ax.cpu(), e2.grad.cpu())
         finally:
             ops.set_default_impl(ops.IMPL_AUTO)
     eo = torch.tensor(emb, requires_grad=True)
     lo, ao = O.embedding_loss_norm5(eo, torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(), affs0_weight=1.5)
     lo.backward()
+    ex = torch.tensor(emb, requires_grad=True)
+    lxo, axo = O.ema_embedding_loss_norm5(ex, torch.tensor(ema), torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(),
+                                          affs0_weight=1.5)
+    lxo.backward()
+    for name in ("generic", "tiled"):
+        lx, ax, gx = out[name + "_x"]
+        close_s(lx, lxo, what=f"{name} cross loss")
+        close_t(ax, axo, what=f"{name} cross affs")
+        close_t(gx, ex.grad, what=f"{name} cross grad")
     for name in ("generic", "tiled"):
         l, a, g, l_ng, a_ng = out[name]
         close_s(l, lo, what=f"{name} loss")
