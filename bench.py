@@ -356,6 +356,35 @@ def HALO_BYTES(shape):
     return C * 4 * shape[1] * shape[2] * 4
 
 
+def time_gt(P, w, device, iters=20):
+    """Device-side ground truth for one batch of the workload: labels -> target (+mask) + weights (K6-K8)."""
+    lab = make_labels(w, 0)
+    K = 12 if w["nd"] == 3 else 2 * len(w["shifts"])
+    if w["nd"] == 2:
+        t = torch.tensor(lab).to(device)
+        offsets = P.multi_offset(w["shifts"], 4)
+        fn = lambda: P.make_targets_2d(t, offsets)
+        per_voxel = 2 * t.element_size() + 4 * K + K + 4 * K
+    else:
+        t = torch.tensor(lab.astype(np.int32)).to(device)
+        fn = lambda: P.make_targets_3d(t)
+        per_voxel = 2 * t.element_size() + 4 * K + 4 * K
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    vox = w["B"] * int(np.prod(w["spatial"]))
+    return {"workload": "GT generation (labels -> target/mask/weight) for " + w["descr"], "ms_per_step": ms,
+            "value": K * vox / (ms * 1e-3), "unit": "aff-voxels/s", "hbm_gbs": per_voxel * vox / (ms * 1e-3) / 1e9,
+            "algorithmic_bytes": per_voxel * vox, "timing": "back-to-back calls, working set may sit in L2"}
+
+
 def cpu_baseline(w, seconds=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -437,6 +466,9 @@ def run_ours(args, rank, world, local_rank):
                               "value": ww["B"] * kk * int(np.prod(ww["spatial"])) / (ms * 1e-3), "unit": UNIT,
                               "hbm_gbs": ab / (ms * 1e-3) / 1e9, "roofline_frac": ab / (ms * 1e-3) / 1e9 / peak}
                 del r
+            for name in ("cfg2", "cfg3"):
+                also["gt_" + name] = time_gt(P, WORKLOADS[name], device)
+                also["gt_" + name]["roofline_frac"] = also["gt_" + name]["hbm_gbs"] / peak
             torch.cuda.empty_cache()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

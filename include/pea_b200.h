@@ -141,6 +141,16 @@ size_t pea_wbr_stats_bytes(int n_channels);
 int pea_weight_binary_ratio(const float* label, int n_channels, int64_t n_per_channel, double alpha,
                             float* weight, void* stats, size_t stats_bytes, void* stream);
 
+/* Whole-batch ground truth in two passes over the labels (the training-loop form of the three functions above,
+ * scripts_cvppp/data/data_provider.py:204-225, scripts_ac3ac4/data/data_provider_labeled_deep.py:246-285 with
+ * separate_weight): labels (B,D,H,W) -> target (B,K,D,H,W), [mask u8, semantics 0 only], weight (B,K,D,H,W), one
+ * weight problem per (sample, channel).  semantics 0 = gen_affs_ours (ignore / padding apply), 1 = seg_to_aff
+ * without replicate pad.  offsets: host int32[K*3] (dz,dy,dx).  counts: device scratch of pea_gt_counts_bytes(B,K). */
+size_t pea_gt_counts_bytes(int B, int K);
+int pea_gt_targets(const void* labels, int label_dtype, int B, int D, int H, int W,
+                   const int32_t* offsets, int K, int semantics, int ignore, int padding, double alpha,
+                   float* target, uint8_t* mask, float* weight, void* counts, size_t counts_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

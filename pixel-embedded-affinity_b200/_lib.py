@@ -27,6 +27,9 @@ SIGNATURES = {
     "pea_scale_inplace": (ci, [vp, ctypes.c_int64, vp, vp]),
     "pea_gt_affs2d": (ci, [vp, ci, ci, ci, ci, c_int32_p, ci, ci, ci, vp, vp, vp]),
     "pea_gt_affs3d": (ci, [vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, vp, vp]),
+    "pea_gt_counts_bytes": (ctypes.c_size_t, [ci, ci]),
+    "pea_gt_targets": (ci, [vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, ci, ctypes.c_double, vp, vp, vp, vp,
+                            ctypes.c_size_t, vp]),
     "pea_wbr_stats_bytes": (ctypes.c_size_t, [ci]),
     "pea_weight_binary_ratio": (ci, [vp, ci, ctypes.c_int64, ctypes.c_double, vp, vp, ctypes.c_size_t, vp]),
 }

@@ -254,3 +254,25 @@ def weight_binary_ratio(label, n_channels, alpha=1.0):
                                          _stream())
     check("pea_weight_binary_ratio", rc)
     return weight
+
+
+def gt_targets(labels4, offsets3_, semantics, ignore=False, padding=True, alpha=1.0, want_mask=True):
+    """labels (B,D,H,W) CUDA tensor -> (target (B,K,D,H,W) f32, mask u8 or None, weight f32): fused two-pass kernels."""
+    B, D, H, W = labels4.shape
+    offs = np.asarray(offsets3_, dtype=np.int32).reshape(-1, 3)
+    K = offs.shape[0]
+    if not 1 <= K <= MAX_OFFSETS:
+        raise ValueError(f"between 1 and {MAX_OFFSETS} offsets are supported, got {K}")
+    dev = labels4.device
+    target = torch.empty((B, K, D, H, W), dtype=torch.float32, device=dev)
+    weight = torch.empty_like(target)
+    mask = torch.empty((B, K, D, H, W), dtype=torch.uint8, device=dev) if (want_mask and semantics == 0) else None
+    nbytes = lib.pea_gt_counts_bytes(B, K)
+    counts = torch.empty(nbytes // 8, dtype=torch.int64, device=dev)
+    keep, optr = _i32(offs)
+    with torch.cuda.device(dev):
+        rc = lib.pea_gt_targets(_ptr(labels4), label_code(labels4), B, D, H, W, optr, K, int(semantics), int(bool(ignore)),
+                                int(bool(padding)), float(alpha), _ptr(target), _ptr(mask), _ptr(weight), _ptr(counts),
+                                nbytes, _stream())
+    check("pea_gt_targets", rc)
+    return target, mask, weight

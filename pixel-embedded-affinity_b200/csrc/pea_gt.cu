@@ -147,6 +147,119 @@ wbr_write_kernel(const float* __restrict__ label, int64_t n, int chunks, const u
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = (__ldg(src + i) != 0.f) ? w_pos : w_neg;
 }
 
+// ---- fused batch GT: labels -> target (+ mask) with the per-(sample, channel) non-zero counts accumulated in the
+//      same pass, then weights recomputed from the labels (the target is never re-read): 2 label reads + 4K (+K)
+//      + 4K bytes per voxel, the algorithmic minimum of SURVEY.md 8(d).
+// MODE 0: gen_affs_ours semantics (2-D, validity mask, padding/ignore);  MODE 1: seg_to_aff semantics (background-aware).
+template <typename L, int MODE>
+__device__ __forceinline__ float gt_value(const L* __restrict__ s, L here, int z, int y, int x, int dz, int dy, int dx,
+                                          int D, int H, int W, int ignore, int padding, bool& inb) {
+    const int qz = z + dz, qy = y + dy, qx = x + dx;
+    inb = (unsigned)qz < (unsigned)D && (unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W;
+    if (!inb) return (MODE == 0 && padding) ? 1.f : 0.f;
+    const L there = __ldg(s + ((int64_t)qz * H + qy) * W + qx);
+    if (MODE == 0) {
+        bool same = (here == there);
+        if (ignore) same = same && (here != (L)0) && (there != (L)0);
+        return same ? 1.f : 0.f;
+    }
+    return (here > (L)0 && there > (L)0 && here == there) ? 1.f : 0.f;
+}
+
+// pass 1: target (+ mask) and counts.  grid = (chunks, B); every block handles a contiguous voxel range of one sample.
+template <typename L, int MODE>
+__global__ void __launch_bounds__(256)
+gt_fused_pass1(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int ignore, int padding,
+               float* __restrict__ target, uint8_t* __restrict__ mask, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_cnt[PEA_MAX_OFFSETS];
+    const int b = blockIdx.y, K = tab.K;
+    const int64_t N = (int64_t)D * H * W;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const L* s = labels + (int64_t)b * N;
+    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = (lo + per < N) ? lo + per : N;
+    for (int64_t base = lo; base < hi; base += blockDim.x) {
+        const int64_t p = base + threadIdx.x;
+        const bool live = p < hi;
+        int x = 0, y = 0, z = 0;
+        L here = (L)0;
+        if (live) {
+            x = (int)(p % W); y = (int)((p / W) % H); z = (int)(p / ((int64_t)W * H));
+            here = s[p];
+        }
+        for (int k = 0; k < K; ++k) {
+            bool inb = false;
+            float a = 0.f;
+            if (live) {
+                a = gt_value<L, MODE>(s, here, z, y, x, tab.dz[k], tab.dy[k], tab.dx[k], D, H, W, ignore, padding, inb);
+                const int64_t o = ((int64_t)b * K + k) * N + p;
+                target[o] = a;
+                if (MODE == 0 && mask != nullptr) mask[o] = inb ? 1 : 0;
+            }
+            const unsigned int votes = __popc(__ballot_sync(0xffffffffu, live && a != 0.f));
+            if ((threadIdx.x & 31) == 0 && votes) atomicAdd(&s_cnt[k], votes);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (s_cnt[k]) atomicAdd(counts + (int64_t)b * K + k, (unsigned long long)s_cnt[k]);
+}
+
+// pass 2: weights from the labels again + the exact counts (values are 0/1, so "all equal" <=> count in {0, N})
+template <typename L, int MODE>
+__global__ void __launch_bounds__(256)
+gt_fused_pass2(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int ignore, int padding, double alpha,
+               const unsigned long long* __restrict__ counts, float* __restrict__ weight) {
+    __shared__ float s_pos[PEA_MAX_OFFSETS], s_neg[PEA_MAX_OFFSETS];
+    const int b = blockIdx.y, K = tab.K;
+    const int64_t N = (int64_t)D * H * W;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const unsigned long long cnt = counts[(int64_t)b * K + k];
+        float w_pos = 1.f, w_neg = 1.f;
+        if (cnt != 0ull && cnt != (unsigned long long)N) {
+            double wf = (double)cnt / (double)N;
+            wf = fmin(fmax(wf, 5e-2), 0.99);
+            if (wf > 0.5) w_neg = (float)(alpha * wf / (1.0 - wf));
+            else w_pos = (float)(alpha * (1.0 - wf) / wf);
+        }
+        s_pos[k] = w_pos;
+        s_neg[k] = w_neg;
+    }
+    __syncthreads();
+    const L* s = labels + (int64_t)b * N;
+    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = (lo + per < N) ? lo + per : N;
+    for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+        const int x = (int)(p % W), y = (int)((p / W) % H), z = (int)(p / ((int64_t)W * H));
+        const L here = s[p];
+        for (int k = 0; k < K; ++k) {
+            bool inb;
+            const float a = gt_value<L, MODE>(s, here, z, y, x, tab.dz[k], tab.dy[k], tab.dx[k], D, H, W, ignore, padding, inb);
+            weight[((int64_t)b * K + k) * N + p] = (a != 0.f) ? s_pos[k] : s_neg[k];
+        }
+    }
+}
+
+template <typename L, int MODE>
+static int run_gt_fused(const void* labels, int B, int D, int H, int W, const GtTable& tab, int ignore, int padding,
+                        double alpha, float* target, uint8_t* mask, float* weight, unsigned long long* counts,
+                        cudaStream_t st) {
+    const int64_t N = (int64_t)D * H * W;
+    int64_t chunks = (148 * 8 + B - 1) / B;
+    const int64_t max_chunks = (N + 2047) / 2048;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)B * tab.K * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    gt_fused_pass1<L, MODE><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, target, mask,
+                                                 counts);
+    gt_fused_pass2<L, MODE><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, alpha, counts,
+                                                 weight);
+    return (int)cudaGetLastError();
+}
+
 // ---- launchers -----------------------------------------------------------------------------------
 static int grid1d(int64_t total) {
     int64_t g = (total + 255) / 256;
@@ -243,4 +356,43 @@ extern "C" int pea_weight_binary_ratio(const float* label, int n_channels, int64
     wbr_write_kernel<<<(unsigned)(n_channels * chunks), 256, 0, st>>>(label, n_per_channel, (int)chunks, s, alpha,
                                                                       weight);
     return (int)cudaGetLastError();
+}
+
+extern "C" size_t pea_gt_counts_bytes(int B, int K) {
+    return (B > 0 && K > 0) ? (size_t)B * K * sizeof(unsigned long long) : 0;
+}
+
+extern "C" int pea_gt_targets(const void* labels, int label_dtype, int B, int D, int H, int W, const int32_t* offsets,
+                              int K, int semantics, int ignore, int padding, double alpha, float* target, uint8_t* mask,
+                              float* weight, void* counts, size_t counts_bytes, void* stream) {
+    if (!labels || !offsets || !target || !weight || !counts) return PEA_E_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535) return PEA_E_SHAPE;
+    if (K < 1 || K > PEA_MAX_OFFSETS) return PEA_E_OFFSETS;
+    if (semantics != 0 && semantics != 1) return PEA_E_MODE;
+    if (counts_bytes < pea_gt_counts_bytes(B, K)) return PEA_E_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(counts) % 8) return PEA_E_ALIGN;
+    GtTable tab;
+    tab.K = K;
+    for (int k = 0; k < K; ++k) { tab.dz[k] = offsets[3 * k]; tab.dy[k] = offsets[3 * k + 1]; tab.dx[k] = offsets[3 * k + 2]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* c = static_cast<unsigned long long*>(counts);
+#define PEA_GT_CASE(CODE, TYPE)                                                                                        \
+    case CODE:                                                                                                         \
+        return semantics == 0 ? run_gt_fused<TYPE, 0>(labels, B, D, H, W, tab, ignore, padding, alpha, target, mask,  \
+                                                      weight, c, st)                                                   \
+                              : run_gt_fused<TYPE, 1>(labels, B, D, H, W, tab, ignore, padding, alpha, target, mask,  \
+                                                      weight, c, st);
+    switch (label_dtype) {
+        PEA_GT_CASE(PEA_LABEL_U8, uint8_t)
+        PEA_GT_CASE(PEA_LABEL_U16, uint16_t)
+        PEA_GT_CASE(PEA_LABEL_U32, uint32_t)
+        PEA_GT_CASE(PEA_LABEL_U64, uint64_t)
+        PEA_GT_CASE(PEA_LABEL_S8, int8_t)
+        PEA_GT_CASE(PEA_LABEL_S16, int16_t)
+        PEA_GT_CASE(PEA_LABEL_S32, int32_t)
+        PEA_GT_CASE(PEA_LABEL_S64, int64_t)
+        PEA_GT_CASE(PEA_LABEL_F32, float)
+        default: return PEA_E_DTYPE;
+    }
+#undef PEA_GT_CASE
 }

@@ -16,10 +16,9 @@ def make_targets_2d(labels, offsets, ignore=False, padding=True):
     """labels (B,H,W) CUDA integer tensor -> target (B,K,H,W) f32, mask (B,K,H,W) u8, weightmap (B,K,H,W) f32."""
     if labels.dim() != 3 or not labels.is_cuda:
         raise ValueError("labels must be a (B,H,W) CUDA tensor")
-    target, mask = ops.gt_affs2d(labels.contiguous(), offsets, ignore, padding)
-    B, K = target.shape[:2]
-    weight = ops.weight_binary_ratio(target, B * K)
-    return target, mask, weight
+    offs3 = ops.offsets3(offsets, 2)
+    target, mask, weight = ops.gt_targets(labels.contiguous()[:, None], offs3, 0, ignore, padding)
+    return target[:, :, 0], mask[:, :, 0], weight[:, :, 0]
 
 
 def make_targets_3d(seg, nhood=NHOOD_NORM5, replicate=False):
@@ -27,7 +26,9 @@ def make_targets_3d(seg, nhood=NHOOD_NORM5, replicate=False):
     if seg.dim() != 4 or not seg.is_cuda:
         raise ValueError("seg must be a (B,D,H,W) CUDA tensor")
     nhood = np.asarray(nhood)
-    target = ops.gt_affs3d(seg.contiguous(), nhood, 3 if (replicate and nhood.shape[0] == 3) else 0)
-    B, K = target.shape[:2]
-    weight = ops.weight_binary_ratio(target, B * K)
+    if replicate and nhood.shape[0] == 3:   # replicate-padded 3-edge targets (deep-supervision scales): unfused path
+        target = ops.gt_affs3d(seg.contiguous(), nhood, 3)
+        B, K = target.shape[:2]
+        return target, ops.weight_binary_ratio(target, B * K)
+    target, _, weight = ops.gt_targets(seg.contiguous(), nhood, 1)
     return target, weight
