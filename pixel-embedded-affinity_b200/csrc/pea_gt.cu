@@ -166,77 +166,98 @@ __device__ __forceinline__ float gt_value(const L* __restrict__ s, L here, int z
     return (here > (L)0 && there > (L)0 && here == there) ? 1.f : 0.f;
 }
 
-// pass 1: target (+ mask) and counts.  grid = (chunks, B); every block handles a contiguous voxel range of one sample.
-template <typename L, int MODE>
+// Both passes, four consecutive x per thread (W % 4 == 0): one coordinate decode and one 128-bit store per channel per
+// four voxels, 32-bit index arithmetic inside a sample.  PASS 1 writes target (+ mask) and accumulates the exact
+// per-(sample, channel) non-zero counts (warp redux -> per-warp shared counters -> one global atomic per block and
+// channel; integer, so the order does not matter).  PASS 2 recomputes the 0/1 values from the labels and writes the
+// two-valued weights (values are 0/1, so the reference's "all equal -> ones" test is count in {0, N}).
+// grid = (chunks, B); a block handles a contiguous range of voxel quads of one sample.
+template <typename L, int MODE, int PASS>
 __global__ void __launch_bounds__(256)
-gt_fused_pass1(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int ignore, int padding,
-               float* __restrict__ target, uint8_t* __restrict__ mask, unsigned long long* __restrict__ counts) {
-    __shared__ unsigned int s_cnt[PEA_MAX_OFFSETS];
-    const int b = blockIdx.y, K = tab.K;
-    const int64_t N = (int64_t)D * H * W;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
-    __syncthreads();
-    const L* s = labels + (int64_t)b * N;
-    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = (lo + per < N) ? lo + per : N;
-    for (int64_t base = lo; base < hi; base += blockDim.x) {
-        const int64_t p = base + threadIdx.x;
-        const bool live = p < hi;
-        int x = 0, y = 0, z = 0;
-        L here = (L)0;
-        if (live) {
-            x = (int)(p % W); y = (int)((p / W) % H); z = (int)(p / ((int64_t)W * H));
-            here = s[p];
-        }
-        for (int k = 0; k < K; ++k) {
-            bool inb = false;
-            float a = 0.f;
-            if (live) {
-                a = gt_value<L, MODE>(s, here, z, y, x, tab.dz[k], tab.dy[k], tab.dx[k], D, H, W, ignore, padding, inb);
-                const int64_t o = ((int64_t)b * K + k) * N + p;
-                target[o] = a;
-                if (MODE == 0 && mask != nullptr) mask[o] = inb ? 1 : 0;
-            }
-            const unsigned int votes = __popc(__ballot_sync(0xffffffffu, live && a != 0.f));
-            if ((threadIdx.x & 31) == 0 && votes) atomicAdd(&s_cnt[k], votes);
-        }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x)
-        if (s_cnt[k]) atomicAdd(counts + (int64_t)b * K + k, (unsigned long long)s_cnt[k]);
-}
-
-// pass 2: weights from the labels again + the exact counts (values are 0/1, so "all equal" <=> count in {0, N})
-template <typename L, int MODE>
-__global__ void __launch_bounds__(256)
-gt_fused_pass2(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int ignore, int padding, double alpha,
-               const unsigned long long* __restrict__ counts, float* __restrict__ weight) {
+gt_fused_x4(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int ignore, int padding, double alpha,
+            float* __restrict__ target, uint8_t* __restrict__ mask, unsigned long long* __restrict__ counts,
+            float* __restrict__ weight) {
+    __shared__ unsigned int s_cnt[8][PEA_MAX_OFFSETS];
     __shared__ float s_pos[PEA_MAX_OFFSETS], s_neg[PEA_MAX_OFFSETS];
     const int b = blockIdx.y, K = tab.K;
-    const int64_t N = (int64_t)D * H * W;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        const unsigned long long cnt = counts[(int64_t)b * K + k];
-        float w_pos = 1.f, w_neg = 1.f;
-        if (cnt != 0ull && cnt != (unsigned long long)N) {
-            double wf = (double)cnt / (double)N;
-            wf = fmin(fmax(wf, 5e-2), 0.99);
-            if (wf > 0.5) w_neg = (float)(alpha * wf / (1.0 - wf));
-            else w_pos = (float)(alpha * (1.0 - wf) / wf);
+    const uint32_t HW = (uint32_t)H * W, N = HW * (uint32_t)D, NQ = N / 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (PASS == 1) {
+        for (int i = threadIdx.x; i < 8 * PEA_MAX_OFFSETS; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
+    } else {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const unsigned long long cnt = counts[(int64_t)b * K + k];
+            float w_pos = 1.f, w_neg = 1.f;
+            if (cnt != 0ull && cnt != (unsigned long long)N) {
+                double wf = (double)cnt / (double)N;  // Python float64 arithmetic of the reference, left to right
+                wf = fmin(fmax(wf, 5e-2), 0.99);
+                if (wf > 0.5) w_neg = (float)(alpha * wf / (1.0 - wf));
+                else w_pos = (float)(alpha * (1.0 - wf) / wf);
+            }
+            s_pos[k] = w_pos;
+            s_neg[k] = w_neg;
         }
-        s_pos[k] = w_pos;
-        s_neg[k] = w_neg;
     }
     __syncthreads();
     const L* s = labels + (int64_t)b * N;
-    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = (lo + per < N) ? lo + per : N;
-    for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
-        const int x = (int)(p % W), y = (int)((p / W) % H), z = (int)(p / ((int64_t)W * H));
-        const L here = s[p];
+    float* out = (PASS == 1 ? target : weight) + (int64_t)b * K * N;
+    uint8_t* mout = (PASS == 1 && MODE == 0 && mask) ? mask + (int64_t)b * K * N : nullptr;
+    const uint32_t per = (NQ + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per, hi = (lo + per < NQ) ? lo + per : NQ;
+    for (uint32_t base = lo; base < hi; base += blockDim.x) {
+        const uint32_t qd = base + threadIdx.x;
+        const bool live = qd < hi;
+        const uint32_t p = (live ? qd : lo) * 4;
+        const int z = (int)(p / HW);
+        const uint32_t r = p - (uint32_t)z * HW;
+        const int y = (int)(r / (uint32_t)W), x = (int)(r - (uint32_t)y * W);
+        L here[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) here[j] = s[p + j];
         for (int k = 0; k < K; ++k) {
-            bool inb;
-            const float a = gt_value<L, MODE>(s, here, z, y, x, tab.dz[k], tab.dy[k], tab.dx[k], D, H, W, ignore, padding, inb);
-            weight[((int64_t)b * K + k) * N + p] = (a != 0.f) ? s_pos[k] : s_neg[k];
+            const int dz = tab.dz[k], dy = tab.dy[k], dx = tab.dx[k];
+            const int qz = z + dz, qy = y + dy;
+            const bool row_in = (unsigned)qz < (unsigned)D && (unsigned)qy < (unsigned)H;
+            const int32_t nb = (int32_t)p + (dz * (int32_t)HW + dy * W + dx);
+            float a[4];
+            unsigned int inb = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool in = row_in && (unsigned)(x + j + dx) < (unsigned)W;
+                inb |= in ? (1u << j) : 0u;
+                if (!in) {
+                    a[j] = (MODE == 0 && padding) ? 1.f : 0.f;
+                } else {
+                    const L there = __ldg(s + (nb + j));
+                    bool same = (here[j] == there);
+                    if (MODE == 0) { if (ignore) same = same && (here[j] != (L)0) && (there != (L)0); }
+                    else same = same && (here[j] > (L)0) && (there > (L)0);
+                    a[j] = same ? 1.f : 0.f;
+                }
+            }
+            const uint32_t o = (uint32_t)k * N + p;
+            if (PASS == 1) {
+                if (live) {
+                    *reinterpret_cast<float4*>(out + o) = make_float4(a[0], a[1], a[2], a[3]);
+                    if (mout) *reinterpret_cast<uint32_t*>(mout + o) = (inb & 1u) | ((inb & 2u) << 7) | ((inb & 4u) << 14) | ((inb & 8u) << 21);
+                }
+                const unsigned int c = live ? (unsigned)((a[0] != 0.f) + (a[1] != 0.f) + (a[2] != 0.f) + (a[3] != 0.f)) : 0u;
+                const unsigned int tot = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0) s_cnt[warp][k] += tot;
+            } else if (live) {
+                const float wp = s_pos[k], wn = s_neg[k];
+                *reinterpret_cast<float4*>(out + o) = make_float4(a[0] != 0.f ? wp : wn, a[1] != 0.f ? wp : wn,
+                                                                  a[2] != 0.f ? wp : wn, a[3] != 0.f ? wp : wn);
+            }
+        }
+    }
+    if (PASS == 1) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            unsigned int c = 0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) c += s_cnt[w8][k];
+            if (c) atomicAdd(counts + (int64_t)b * K + k, (unsigned long long)c);
         }
     }
 }
@@ -247,16 +268,16 @@ static int run_gt_fused(const void* labels, int B, int D, int H, int W, const Gt
                         cudaStream_t st) {
     const int64_t N = (int64_t)D * H * W;
     int64_t chunks = (148 * 8 + B - 1) / B;
-    const int64_t max_chunks = (N + 2047) / 2048;
+    const int64_t max_chunks = (N / 4 + 1023) / 1024;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)B * tab.K * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)chunks, (unsigned)B);
-    gt_fused_pass1<L, MODE><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, target, mask,
-                                                 counts);
-    gt_fused_pass2<L, MODE><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, alpha, counts,
-                                                 weight);
+    gt_fused_x4<L, MODE, 1><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, alpha, target,
+                                                 mask, counts, weight);
+    gt_fused_x4<L, MODE, 2><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, alpha, target,
+                                                 mask, counts, weight);
     return (int)cudaGetLastError();
 }
 
@@ -371,6 +392,10 @@ extern "C" int pea_gt_targets(const void* labels, int label_dtype, int B, int D,
     if (semantics != 0 && semantics != 1) return PEA_E_MODE;
     if (counts_bytes < pea_gt_counts_bytes(B, K)) return PEA_E_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(counts) % 8) return PEA_E_ALIGN;
+    // four voxels per thread with 128-bit stores and 32-bit in-sample indices
+    if (W % 4 != 0 || (int64_t)K * D * H * W >= ((int64_t)1 << 31)) return PEA_E_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(weight)) & 15) return PEA_E_ALIGN;
+    if (mask && (reinterpret_cast<uintptr_t>(mask) & 3)) return PEA_E_ALIGN;
     GtTable tab;
     tab.K = K;
     for (int k = 0; k < K; ++k) { tab.dz[k] = offsets[3 * k]; tab.dy[k] = offsets[3 * k + 1]; tab.dx[k] = offsets[3 * k + 2]; }

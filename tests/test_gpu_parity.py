@@ -577,3 +577,23 @@ def test_zshard_emulated_on_one_gpu_is_bit_identical(P, O, world, D):
         sh.world = 1   # no process group in this test: the exchange was emulated by the copy above
         parts.append(sharded_affinities(sh))
     assert torch.equal(torch.cat(parts, dim=2), whole)
+
+
+def test_fused_batch_gt_matches_oracle(P, O):
+    """make_targets_2d / _3d (two fused passes, 4 voxels per thread) vs the oracle, per (sample, channel) weights."""
+    offsets = O.multi_offset([1, 3, 5, 9, 27], neighbor=4) + [[2, 3], [0, 40]]
+    labs = np.stack([O.voronoi_labels((52, 64), 9, 300 + b) for b in range(3)])
+    labs[2] = 0                                     # an all-background sample: uniform channels -> weight 1
+    tgt, msk, wgt = P.make_targets_2d(torch.tensor(labs).cuda(), offsets)
+    for b in range(3):
+        to, mo = O.gen_affs_ours(labs[b], offsets, ignore=False, padding=True)
+        same(tgt[b], to, "2D target")
+        same(msk[b], mo, "2D mask")
+        same(wgt[b], np.stack([O.weight_binary_ratio(c) for c in to]), "2D weight")
+    segs = np.stack([O.voronoi_labels((9, 40, 48), 14, 400 + b, z_scale=3.0, dtype=np.uint16) for b in range(2)])
+    for dt in (np.int32, np.int64, np.uint8):
+        tgt, wgt = P.make_targets_3d(torch.tensor((segs % 200).astype(dt)).cuda())
+        for b in range(2):
+            to = O.seg_to_aff_norm5((segs[b] % 200).astype(dt))
+            same(tgt[b], to, f"3D target {dt.__name__}")
+            same(wgt[b], np.stack([O.weight_binary_ratio(c) for c in to]), "3D weight")
