@@ -17,6 +17,10 @@
 #include "pea_common.cuh"
 #include "pea_tma.cuh"
 
+#ifndef PEA_TILE_Y3D
+#define PEA_TILE_Y3D 8
+#endif
+
 namespace pea {
 
 namespace t3 {
@@ -124,7 +128,7 @@ __device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int 
 }
 
 template <int TY, bool GRAD>
-__global__ void __launch_bounds__(TY * 32, 1)
+__global__ void __launch_bounds__(TY * 32, (TY <= 4) ? 2 : 1)
 fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
               const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT,
               const __grid_constant__ CUtensorMap mapW, const Params P) {
@@ -563,7 +567,7 @@ struct alignas(1024) StageX {
 };
 
 template <int TY, bool GRAD>
-__global__ void __launch_bounds__(TY * 32, 1)
+__global__ void __launch_bounds__(TY * 32, (TY <= 4) ? 2 : 1)
 cross3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
               const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapO,
               const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapW, const Params P) {
@@ -803,14 +807,16 @@ bool tiled3d_norm5_eligible(int C, int D, int H, int W, const OffsetTable& tab, 
     return true;
 }
 
+constexpr int kTileY = PEA_TILE_Y3D;  // rows per CTA of the fused 3-D kernels (tuned on B200)
+
 int tiled3d_norm5_blocks(int B, int H, int W) {
-    constexpr int TY = 8;
+    constexpr int TY = kTileY;
     return B * ((H + TY - 1) / TY) * ((W + t3::TX - 1) / t3::TX);
 }
 
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st) {
-    constexpr int TY = 8;
+    constexpr int TY = kTileY;
     CUtensorMap mY, mA, mX, mT, mW;
     int rc;
     if ((rc = encode_volume_map(&mY, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY + 2 * t3::HY, 1, 16))) return rc;
@@ -871,7 +877,7 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
 int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab,
                          const float* target, const float* weight, float* affs, float* partials, float* grad,
                          cudaStream_t st) {
-    constexpr int TY = 8;
+    constexpr int TY = kTileY;
     if (reinterpret_cast<uintptr_t>(partner) & 15) return PEA_E_ALIGN;
     CUtensorMap mY, mA, mX, mO, mT, mW;
     int rc;
