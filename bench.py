@@ -316,17 +316,39 @@ def time_e2e_labels_only(P, w, steps, device, inputs):
 
 
 def time_zshard(P, device, rank, world, steps, shape=(100, 1024, 1024)):
-    """cfg4: forward-only 12-channel affinities of a full AC3/AC4 volume, z-sharded over `world` GPUs with the 4-slice
-    halo exchanged in place over NCCL (112 B/voxel algorithmic).  Strong scaling: the volume is fixed."""
-    from pea_b200.zshard import ZShard, sharded_affinities
+    """cfg4: forward-only 12-channel affinities of a full AC3/AC4 volume, z-sharded over `world` GPUs (112 B/voxel
+    algorithmic).  Strong scaling: the volume is fixed.  Halo transport, best available first: "peer" = slabs in
+    symmetric memory, the kernel reads the previous rank's last 4 slices in place over NVLink (one launch, no exchange
+    step; a device-side barrier orders producer writes before the reads); "nccl" = send/recv in place, overlapped."""
+    from pea_b200.zshard import ZShard, PeerZShard, sharded_affinities, fused_halo_affinities
     D, H, W = shape
-    sh = ZShard(1, C, D, H, W, rank, world, device)
+    dist_on = world > 1
+    transport, sh = "none", None
+    if dist_on:
+        ok = torch.zeros(1, device=device)
+        try:
+            sh = PeerZShard(1, C, D, H, W, rank, world, device)
+            transport, ok[0] = "peer", 1.0
+        except Exception as ex:  # noqa: BLE001  (symmetric memory not available on this box)
+            sys.stderr.write(f"rank {rank}: peer halo unavailable ({type(ex).__name__}: {ex}); using NCCL\n")
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if float(ok) < 1.0:
+            transport, sh = "nccl", None
+    if sh is None:
+        sh = ZShard(1, C, D, H, W, rank, world, device)
     g = torch.Generator(device=device).manual_seed(1234 + rank)
     sh.own.normal_(generator=g)
     out = torch.empty((1, 12, sh.depth, H, W), device=device)
-    dist_on = world > 1
+
+    def step():
+        if transport == "peer":
+            sh.publish()                       # producer's slab visible to the next rank
+            fused_halo_affinities(sh.own, sh.prev_tail, out=out)
+        else:
+            sharded_affinities(sh, out=out)
+
     for _ in range(2):
-        sharded_affinities(sh, out=out)
+        step()
     torch.cuda.synchronize()
     if dist_on:
         torch.distributed.barrier()
@@ -334,7 +356,7 @@ def time_zshard(P, device, rank, world, steps, shape=(100, 1024, 1024)):
     s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(steps):
-        sharded_affinities(sh, out=out)
+        step()
     t.record()
     torch.cuda.synchronize()
     ms = torch.tensor([s.elapsed_time(t) / steps], device=device, dtype=torch.float64)
@@ -345,7 +367,8 @@ def time_zshard(P, device, rank, world, steps, shape=(100, 1024, 1024)):
     res = {"workload": f"cfg4 AC3/AC4 full volume 100x1024x1024 forward-only, z-sharded over {world} GPU(s)",
            "ms_per_step": ms, "value": 12 * vox / (ms * 1e-3), "unit": "aff-voxels/s (forward only)",
            "scaling": "strong", "hbm_gbs_aggregate": 112 * vox / (ms * 1e-3) / 1e9,
-           "halo_bytes_per_boundary": sh.halo_bytes() if rank > 0 else (HALO_BYTES(shape) if world > 1 else 0),
+           "halo_transport": transport,
+           "halo_bytes_per_boundary": HALO_BYTES(shape) if world > 1 else 0,
            "slab_depths": [b - a for a, b in __import__("pea_b200").zshard.shard_ranges(D, world)]}
     del sh, out
     torch.cuda.empty_cache()

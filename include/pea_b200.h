@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PEA_ABI_VERSION 2
+#define PEA_ABI_VERSION 3
 #define PEA_MAX_OFFSETS 64
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -80,10 +80,15 @@ size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, int cross);
  * z-sharded volumes: the first `z_skip` slices of emb are halo received from the previous shard --
  * they are read as neighbours but produce no output, so affs has D - z_skip slices.  `emb_plane` / `affs_plane`
  * are the element strides between consecutive channel planes (0 = contiguous: D*H*W and (D - z_skip)*H*W), which
- * lets emb / affs be z-range views of deeper buffers without a copy. */
+ * lets emb / affs be z-range views of deeper buffers without a copy.
+ * Alternatively (z_skip == 0) `halo` points at the previous shard's last `halo_slices` (<= 4) slices wherever they
+ * live -- typically the PEER GPU's memory mapped over NVLink (symmetric memory) -- laid out (B, C, halo_slices, H, W)
+ * with channel-plane stride `halo_plane`: the kernel reads them in place, so no exchange step or staging copy
+ * exists at all.  halo == NULL: no external halo.  Only the tiled 3-D forward kernel takes an external halo. */
 int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
                  const int32_t* offsets, int K, int border, int impl,
                  int z_skip, int64_t emb_plane, int64_t affs_plane,
+                 const float* halo, int halo_slices, int64_t halo_plane,
                  float* affs, void* workspace, size_t ws_bytes, void* stream);
 
 /* Fused embedding -> affinities -> weighted-MSE loss -> d loss / d embedding, one pass.

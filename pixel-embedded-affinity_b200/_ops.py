@@ -102,12 +102,13 @@ def _workspace(B, C, D, H, W, K, cross, device):
     return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
-def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None):
+def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None, halo=None):
     """(B,C,[D,]H,W) -> (B,K,[D - z_skip,]H,W) affinities.  emb/partner already validated.
 
     ``emb`` may be a z-range view ``buf[:, :, z0:z1]`` of a contiguous (B,C,Dtot,H,W) buffer and ``out`` a z-range
     view of a contiguous (B,K,Dout,H,W) buffer (z-sharded inference): only the channel-plane stride differs from
-    the contiguous case and it is passed through to the kernel."""
+    the contiguous case and it is passed through to the kernel.  ``halo`` (B,C,n<=4,H,W): the previous shard's last
+    slices as a z-range view of any buffer -- including a PEER GPU's symmetric-memory buffer -- read in place."""
     impl = DEFAULT_IMPL if impl is None else impl
     B, C, D, H, W = _dims5(emb)
     K = offs3.shape[0]
@@ -136,12 +137,19 @@ def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None):
             if affs.dim() != 5 or st[4] != 1 or st[3] != W or st[2] != H * W or st[0] != K * st[1]:
                 raise ValueError("out must be contiguous or a z-range view of a contiguous buffer")
             affs_plane = st[1]
+    halo_n, halo_plane = 0, 0
+    if halo is not None:
+        hs = halo.stride()
+        if (halo.dim() != 5 or tuple(halo.shape[:2]) != (B, C) or tuple(halo.shape[3:]) != (H, W) or not 1 <= halo.shape[2] <= 4
+                or hs[4] != 1 or hs[3] != W or hs[2] != H * W or hs[0] != C * hs[1] or halo.dtype != torch.float32):
+            raise ValueError("halo must be a float32 (B,C,n<=4,H,W) z-range view of a contiguous buffer")
+        halo_n, halo_plane = int(halo.shape[2]), int(hs[1])
     ws, n = _workspace(B, C, D, H, W, K, partner is not None, emb.device)
     keep, optr = _i32(offs3)
     with torch.cuda.device(emb.device):
         rc = lib.pea_affs_fwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, int(z_skip), emb_plane,
-                              affs_plane, _ptr(affs), _ptr(ws), n, _stream())
-    if rc == -8 and emb_plane and impl != IMPL_TILED:
+                              affs_plane, _ptr(halo), halo_n, halo_plane, _ptr(affs), _ptr(ws), n, _stream())
+    if rc == -8 and emb_plane and impl != IMPL_TILED and halo is None:
         # z-range view that the tiled kernel cannot take (shape / offsets): fall back to a contiguous copy
         return affs_fwd(emb.contiguous(), partner, offs3, border, impl, z_skip, out)
     check("pea_affs_fwd", rc)

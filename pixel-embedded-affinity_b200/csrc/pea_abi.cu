@@ -21,7 +21,7 @@ int tiled3d_norm5_blocks(int B, int H, int W);
 bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
                           int64_t emb_plane);
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
-                       cudaStream_t st);
+                       const float* halo, int halo_n, int64_t halo_plane, cudaStream_t st);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
 
@@ -153,7 +153,8 @@ extern "C" size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, 
 
 extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
                             const int32_t* offsets, int K, int border, int impl, int z_skip, int64_t emb_plane,
-                            int64_t affs_plane, float* affs, void* workspace, size_t ws_bytes, void* stream) {
+                            int64_t affs_plane, const float* halo, int halo_slices, int64_t halo_plane, float* affs,
+                            void* workspace, size_t ws_bytes, void* stream) {
     if (!emb || !offsets || !affs || !workspace) return PEA_E_NULL;
     if (impl != PEA_IMPL_AUTO && impl != PEA_IMPL_GENERIC && impl != PEA_IMPL_TILED) return PEA_E_MODE;
     Dims d;
@@ -161,6 +162,8 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     if (rc) return rc;
     if (border != PEA_BORDER_WRAP && border != PEA_BORDER_ZERO) return PEA_E_MODE;
     if (z_skip < 0 || z_skip >= D) return PEA_E_SHAPE;
+    if (halo && (z_skip != 0 || halo_slices < 1 || halo_slices > 4 || halo_plane < (int64_t)halo_slices * H * W))
+        return PEA_E_SHAPE;
     if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
     const int64_t HW = (int64_t)H * W;
     if (emb_plane == 0) emb_plane = d.N;
@@ -178,8 +181,10 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     const bool tiled2_ok = plain && tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, false);
     const bool tiled3_ok = tiled3d_fwd_eligible(C, W, tab, border, cross != 0, emb, emb_plane);
     if (impl == PEA_IMPL_TILED && !tiled2_ok && !tiled3_ok) return PEA_E_MODE;
+    if (halo && (!tiled3_ok || impl == PEA_IMPL_GENERIC)) return PEA_E_MODE;  // only the tiled kernel reads an external halo
     if (impl != PEA_IMPL_GENERIC) {
-        if (tiled3_ok) return launch_fwd3d_norm5(emb, d, z_skip, emb_plane, affs_plane, affs, st);
+        if (tiled3_ok)
+            return launch_fwd3d_norm5(emb, d, z_skip, emb_plane, affs_plane, affs, halo, halo ? halo_slices : 0, halo_plane, st);
         if (tiled2_ok)
             return launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, nullptr, nullptr, nullptr,
                                   PEA_MASK_NONE, affs, nullptr, nullptr, st);

@@ -400,6 +400,11 @@ struct ParamsF {
     int64_t emb_plane, affs_plane;  // elements between channel planes of emb / affs
     const float* emb;
     float* affs;
+    // optional external halo: the previous z-shard's last `halo_n` (<= 4) slices, typically PEER memory mapped over
+    // NVLink (symmetric memory): read in place by the ring warm-up, so the halo "exchange" is fused into this kernel
+    const float* halo;
+    int halo_n;
+    int64_t halo_plane;
 };
 
 template <int TY>
@@ -456,17 +461,21 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < kC2; ++i) re[s][i] = 0ull;
 
-    // ---- ring warm-up on the halo slices (previous shard's last slices): own column straight from global
-    const float* emb_b = P.emb + (int64_t)b * kC * P.emb_plane + pix;
-    for (int z = (zs > 4 ? zs - 4 : 0); z < zs; ++z) {
+    // ---- ring warm-up on the halo slices (previous shard's last slices): own column straight from global -- either
+    //      the leading z_skip slices of emb, or the external (peer) halo buffer
+    const bool ext = P.halo != nullptr;
+    const int nwarm = ext ? P.halo_n : (zs > 4 ? 4 : zs);
+    const int64_t wplane = ext ? P.halo_plane : P.emb_plane;
+    const float* warm_b = (ext ? P.halo : P.emb + (int64_t)(zs - nwarm) * HW) + (int64_t)b * kC * wplane + pix;
+    for (int zw = 0; zw < nwarm; ++zw) {
         // same arithmetic order as the tile path below, so slabs reproduce the whole-volume result bit for bit
         f32x2 v[kC2];
-        const float* p = emb_b + (int64_t)z * HW;
+        const float* p = warm_b + (int64_t)zw * HW;
 #pragma unroll
         for (int i = 0; i < kC2; ++i) {
             const float lo = live ? __ldg(p) : 0.f;
-            const float hi = live ? __ldg(p + P.emb_plane) : 0.f;
-            p += 2 * P.emb_plane;
+            const float hi = live ? __ldg(p + wplane) : 0.f;
+            p += 2 * wplane;
             v[i] = pack2(lo, hi);
         }
         f32x2 s0 = 0ull, s1 = 0ull;
@@ -485,6 +494,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
         for (int i = 0; i < kC2; ++i) re[1][i] = mul2(v[i], r2);
     }
 
+    const int zprev = ext ? P.halo_n : 0;  // slices that precede emb's slice 0 (zero border applies when none do)
     float* affs_b = P.affs + (int64_t)b * 12 * P.affs_plane + pix;
     int it = 0;
     for (int z = zs; z < D; ++z, ++it) {
@@ -539,7 +549,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
                 d0 = fma2(re[0][i], re[j][i], d0);
                 d1 = fma2(re[0][i + 1], re[j][i + 1], d1);
             }
-            if (live) out[(int64_t)(3 * (j - 1)) * P.affs_plane] = (z >= j) ? hsum2(d0, d1) : 0.f;
+            if (live) out[(int64_t)(3 * (j - 1)) * P.affs_plane] = (z + zprev >= j) ? hsum2(d0, d1) : 0.f;
         }
 #pragma unroll
         for (int s = 4; s >= 1; --s)
@@ -855,7 +865,7 @@ bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool
 }
 
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
-                       cudaStream_t st) {
+                       const float* halo, int halo_n, int64_t halo_plane, cudaStream_t st) {
     constexpr int TY = 8;
     CUtensorMap mY, mA, mX;
     int rc;
@@ -865,6 +875,7 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
     t3::ParamsF P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W; P.z_skip = z_skip;
     P.emb_plane = emb_plane; P.affs_plane = affs_plane; P.emb = emb; P.affs = affs;
+    P.halo = halo; P.halo_n = halo_n; P.halo_plane = halo_plane;
     const int grid = d.B * ((d.H + TY - 1) / TY) * ((d.W + t3::TX - 1) / t3::TX);
     const size_t smem = sizeof(t3::StageF<TY>) + 1024;
     auto kern = t3::fwd3d_norm5<TY>;

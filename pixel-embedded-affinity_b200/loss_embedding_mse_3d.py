@@ -94,10 +94,11 @@ def ema_embedding_loss_norm1(embedding, ema_embedding, target, weightmap, criter
     return _loss3d(embedding, ema_embedding, target, weightmap, criterion, [shift] * 3, affs0_weight, 1)
 
 
-def _inf3d(embedding, shifts, z_skip=0, out=None):
+def _inf3d(embedding, shifts, z_skip=0, out=None, halo=None):
     embedding = ops.check_embedding("embedding", embedding, 5, make_contiguous=False)
     with torch.no_grad():
-        return ops.affs_fwd(embedding.detach(), None, offsets_from_shifts(shifts), ops.BORDER_ZERO, z_skip=z_skip, out=out)
+        return ops.affs_fwd(embedding.detach(), None, offsets_from_shifts(shifts), ops.BORDER_ZERO, z_skip=z_skip, out=out,
+                            halo=halo)
 
 
 def inf_embedding_loss_norm5(embedding):

@@ -63,9 +63,9 @@ def start_halo_exchange(shard, group=None):
     return dist.batch_isend_irecv(ops) if ops else []
 
 
-def _cuda_compute(emb_view, z_skip, out_view):
+def _cuda_compute(emb_view, z_skip, out_view, halo=None):
     from .loss_embedding_mse_3d import _inf3d, SHIFTS_NORM5
-    _inf3d(emb_view, SHIFTS_NORM5, z_skip=z_skip, out=out_view)
+    _inf3d(emb_view, SHIFTS_NORM5, z_skip=z_skip, out=out_view, halo=halo)
 
 
 def sharded_affinities(shard, out=None, group=None, compute=None):
@@ -84,4 +84,55 @@ def sharded_affinities(shard, out=None, group=None, compute=None):
         r.wait()
     # first slices of the slab: need the halo (rank > 0) or the zero border (rank 0)
     compute(shard.buf[:, :, :shard.halo + head], shard.halo, out[:, :, :head])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fused halo: no exchange step at all.  The slabs live in symmetric memory (every rank's buffer is mapped into every
+# other rank's address space over NVLink / NVSwitch); rank r's kernel reads the last four slices of rank r-1 IN PLACE
+# through the `halo` pointer of pea_affs_fwd (include/pea_b200.h) while it warms its z ring up.  268 MB per boundary
+# cross NVLink exactly once, inside the compute kernel, overlapped with its own HBM traffic; nothing is staged.
+class PeerZShard:
+    """One rank's slab in symmetric memory.  ``own`` is what the producer writes; ``prev_tail`` is the (B,C,4,H,W) view
+    of the previous rank's last four slices in PEER memory (None on rank 0)."""
+
+    def __init__(self, B, C, D_total, H, W, rank, world, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = rank, world
+        ranges = shard_ranges(D_total, world)
+        self.z0, self.z1 = ranges[rank]
+        self.depth = self.z1 - self.z0
+        if world > 1 and min(b - a for a, b in ranges) < HALO:
+            raise ValueError(f"a slab is thinner than the {HALO}-slice halo: use fewer ranks")
+        cap = max(b - a for a, b in ranges)            # symmetric allocations have the same size on every rank
+        self.shape = (B, C, cap, H, W)
+        self.buf = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group=(group or dist.group.WORLD))
+        self.own = self.buf[:, :, :self.depth]
+        self.halo = HALO if rank > 0 else 0
+        self.prev_tail = None
+        if rank > 0:
+            pd = ranges[rank - 1][1] - ranges[rank - 1][0]
+            peer = self.handle.get_buffer(rank - 1, self.shape, torch.float32)
+            self.prev_tail = peer[:, :, pd - HALO:pd]
+
+    def halo_bytes(self):
+        B, C, _, H, W = self.shape
+        return B * C * self.halo * H * W * 4
+
+    def publish(self):
+        """Order the producer's writes of ``own`` before the neighbours' reads (device-side barrier on the current
+        stream; no host synchronisation)."""
+        if self.world > 1:
+            self.handle.barrier(channel=0)
+
+
+def fused_halo_affinities(emb_own, prev_tail, out=None, compute=None):
+    """12-channel affinities of a slab in ONE launch: ``prev_tail`` (B,C,<=4,H,W; None for the first slab) is read in
+    place -- typically from the peer GPU.  Bit-identical to the same slices of the whole-volume result."""
+    compute = compute or _cuda_compute
+    B, C, depth, H, W = emb_own.shape
+    if out is None:
+        out = torch.empty((B, 12, depth, H, W), device=emb_own.device, dtype=torch.float32)
+    compute(emb_own, 0, out, prev_tail)
     return out

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_strerror():
     import pea_b200
     lib = pea_b200._lib.lib
-    assert lib.pea_abi_version() == 2
+    assert lib.pea_abi_version() == 3
     assert lib.pea_strerror(0) == b"ok"
     assert b"channel" in lib.pea_strerror(-3)
     assert lib.pea_workspace_bytes(1, 16, 1, 8, 8, 2, 0) > 0
@@ -45,13 +45,13 @@ def test_argument_rejection_without_touching_the_device():
     import pea_b200
     lib = pea_b200._lib.lib
     offs = (ctypes.c_int32 * 6)(0, -1, 0, 0, 0, -1)
-    assert lib.pea_affs_fwd(None, None, 1, 16, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, None, None, 0, None) == -1
+    assert lib.pea_affs_fwd(None, None, 1, 16, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, None, 0, 0, None, None, 0, None) == -1
     one = ctypes.c_void_p(16)
-    assert lib.pea_affs_fwd(one, None, 0, 16, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, one, one, 0, None) == -2
-    assert lib.pea_affs_fwd(one, None, 1, 5, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, one, one, 0, None) == -3
-    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 0, 0, 0, 0, 0, 0, one, one, 0, None) == -4
-    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 2, 7, 0, 0, 0, 0, one, one, 0, None) == -8
-    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, one, one, 0, None) == -5
+    assert lib.pea_affs_fwd(one, None, 0, 16, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, None, 0, 0, one, one, 0, None) == -2
+    assert lib.pea_affs_fwd(one, None, 1, 5, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, None, 0, 0, one, one, 0, None) == -3
+    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 0, 0, 0, 0, 0, 0, None, 0, 0, one, one, 0, None) == -4
+    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 2, 7, 0, 0, 0, 0, None, 0, 0, one, one, 0, None) == -8
+    assert lib.pea_affs_fwd(one, None, 1, 16, 1, 8, 8, offs, 2, 0, 0, 0, 0, 0, None, 0, 0, one, one, 0, None) == -5
     assert lib.pea_gt_affs2d(one, 99, 1, 8, 8, offs, 2, 0, 1, one, one, None) == -6
 
 

@@ -579,6 +579,31 @@ def test_zshard_emulated_on_one_gpu_is_bit_identical(P, O, world, D):
     assert torch.equal(torch.cat(parts, dim=2), whole)
 
 
+@pytest.mark.parametrize("world,D", [(2, 11), (3, 20), (4, 17)])
+def test_zshard_fused_peer_halo_is_bit_identical(P, O, world, D):
+    """The halo is not exchanged at all: each slab's kernel reads the previous slab's last four slices in place through
+    the `halo` pointer of pea_affs_fwd (on a multi-GPU box that pointer is peer memory; here another local buffer)."""
+    from pea_b200.zshard import shard_ranges, fused_halo_affinities, HALO
+    torch.manual_seed(world * 1000 + D)
+    vol = torch.randn(2, 16, D, 40, 64, device="cuda")
+    whole = P.inf_embedding_loss_norm5(vol)
+    ranges = shard_ranges(D, world)
+    cap = max(b - a for a, b in ranges)
+    slabs = []
+    for z0, z1 in ranges:                      # same-size buffers like symmetric memory: slabs are z-range views
+        buf = torch.full((2, 16, cap, 40, 64), float("nan"), device="cuda")
+        buf[:, :, :z1 - z0].copy_(vol[:, :, z0:z1])
+        slabs.append(buf[:, :, :z1 - z0])
+    parts = []
+    for r in range(world):
+        tail = slabs[r - 1][:, :, -HALO:] if r else None
+        parts.append(fused_halo_affinities(slabs[r], tail))
+    assert torch.equal(torch.cat(parts, dim=2), whole)
+    # a halo thinner than four slices: zero border applies beyond it (first slab of a volume cut at z = 2)
+    part = fused_halo_affinities(vol[:, :, 2:], vol[:, :, :2])
+    assert torch.equal(part, whole[:, :, 2:])
+
+
 def test_fused_batch_gt_matches_oracle(P, O):
     """make_targets_2d / _3d (two fused passes, 4 voxels per thread) vs the oracle, per (sample, channel) weights."""
     offsets = O.multi_offset([1, 3, 5, 9, 27], neighbor=4) + [[2, 3], [0, 40]]

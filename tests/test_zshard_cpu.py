@@ -60,3 +60,24 @@ def test_thin_slab_is_refused():
     from pea_b200.zshard import ZShard
     with pytest.raises(ValueError):
         ZShard(1, 16, 6, 8, 8, rank=1, world=2, device="cpu")
+
+
+def test_fused_halo_host_logic_with_oracle_compute():
+    """fused_halo_affinities passes (own slab, 0, out, previous tail) to the kernel; with the oracle standing in for the
+    kernel the concatenated slabs reproduce the whole volume."""
+    from pea_b200.zshard import shard_ranges, fused_halo_affinities, HALO
+
+    def compute(emb_own, z_skip, out_view, halo):
+        assert z_skip == 0
+        full = emb_own if halo is None else torch.cat([halo, emb_own], dim=2)
+        n = 0 if halo is None else halo.shape[2]
+        out_view.copy_(O.inf_embedding_loss_norm5(full.contiguous())[:, :, n:])
+
+    torch.manual_seed(3)
+    vol = torch.randn(1, 16, 14, 30, 32)
+    ref = O.inf_embedding_loss_norm5(vol)
+    parts = []
+    for r, (z0, z1) in enumerate(shard_ranges(14, 3)):
+        tail = vol[:, :, z0 - HALO:z0] if r else None
+        parts.append(fused_halo_affinities(vol[:, :, z0:z1], tail, compute=compute))
+    assert torch.allclose(torch.cat(parts, dim=2), ref, rtol=0, atol=5e-7)

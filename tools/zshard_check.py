@@ -27,6 +27,21 @@ for it in range(3):
     out = sharded_affinities(sh)
     ok = torch.equal(out, whole[:, :, sh.z0:sh.z1])
     assert ok, f"rank {rank} iteration {it}: slab differs from the whole-volume result"
+# fused halo through symmetric memory: no exchange step, the kernel reads the peer's slab tail in place
+from pea_b200.zshard import PeerZShard, fused_halo_affinities  # noqa: E402
+try:
+    ps = PeerZShard(1, 16, D, H, W, rank, world, dev)
+except Exception as ex:  # noqa: BLE001
+    ps = None
+    print(f"rank {rank}: symmetric memory unavailable ({type(ex).__name__}: {ex})", flush=True)
+if ps is not None:
+    ps.own.copy_(vol[:, :, ps.z0:ps.z1])
+    for it in range(3):
+        ps.publish()
+        out = fused_halo_affinities(ps.own, ps.prev_tail)
+        assert torch.equal(out, whole[:, :, ps.z0:ps.z1]), f"rank {rank} iteration {it}: fused-halo slab differs"
+        ps.publish()   # nobody overwrites a slab while a neighbour may still be reading it
+    print(f"zshard_check fused-halo OK rank {rank}/{world}", flush=True)
 torch.cuda.synchronize()
 dist.barrier()
 print(f"zshard_check OK rank {rank}/{world} slab [{sh.z0},{sh.z1}) halo {sh.halo_bytes()} B", flush=True)
