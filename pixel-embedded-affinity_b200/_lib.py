@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpea_b200.so")
+# PEA_B200_LIB: development knob for A/B runs of alternative builds of the same ABI (never a CPU path)
+LIB_PATH = os.environ.get("PEA_B200_LIB") or os.path.join(_HERE, "csrc", "libpea_b200.so")
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)

@@ -383,6 +383,376 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
 
 
 // ================================================================================================================
+// Fused kernel, TMEM variant (the default for the loss + backward path).
+//
+// fused3d_norm5 above keeps the z rings (5 slices x (unit vector + gradient accumulator) = 165 registers per thread) in
+// the register file: 250 registers, 8 warps per SM -- and measurements show the kernel's time is inversely
+// proportional to the number of resident warps (latency-bound: TY = 6 -> 240 us, TY = 8 -> 187 us at cfg3).
+// Blackwell's Tensor Memory (256 KB per SM, 512 columns x 128 lanes x 32 bit) is a second register file when no MMA
+// uses it: tcgen05.st / tcgen05.ld with the 32x32b shape move 16 or 32 consecutive columns of ONE lane to / from the
+// registers of ONE thread.  Here the four older ring slots live in TMEM (4 x 32 columns per thread, slot of slice z =
+// z & 3, addressed at run time: no ring shifting at all), which brings the kernel to <= 168 registers and lets a
+// CTA of 12 warps (12 x 32 voxel columns) run per SM.  Own target / weight values come straight from global memory
+// (coalesced 128-byte rows, read once), so shared memory holds only the embedding boxes (178 KB).
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const f32x2 (&v)[kC2]) {
+    float r[16];
+#pragma unroll
+    for (int i = 0; i < kC2; ++i) unpack2(v[i], r[2 * i], r[2 * i + 1]);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]),
+        "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15])
+        : "memory");
+}
+// load + wait in one statement: the destination registers are valid when it returns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, f32x2 (&v)[kC2]) {
+    float r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < kC2; ++i) v[i] = pack2(r[2 * i], r[2 * i + 1]);
+}
+// two 16-column loads (unit vector + gradient accumulator of one slot) behind a single wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, f32x2 (&a)[kC2], f32x2 (&b)[kC2]) {
+    float r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),
+          "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),
+          "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < kC2; ++i) {
+        a[i] = pack2(r[2 * i], r[2 * i + 1]);
+        b[i] = pack2(r[16 + 2 * i], r[16 + 2 * i + 1]);
+    }
+}
+// predicated read-only global load that the compiler may not sink towards its use (volatile): issued where it is
+// written, i.e. half a slice before the value is needed
+__device__ __forceinline__ float ldg_early(const float* p, bool pred) {
+    float v;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+        : "=f"(v)
+        : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr uint32_t kTmemCols = 512;
+
+template <int TY>
+struct alignas(128) StageM {
+    float sY[kC][TY + 2 * HY][TX];  // rows y0-9 .. y0+TY+8
+    float sAm[kC][TY][TX];          // rows y0-27 ..
+    float sAp[kC][TY][TX];          // rows y0+27 ..
+    float sX[kC][TY][XW];           // cols x0-28 .. x0+59
+    // own target / weight tile, grouped by the part of the slice that consumes it (each group is refilled as soon as
+    // its part is over, like the embedding boxes): [part y/x/z][target, weight][4 channels]
+    float sTW[3][2][4][TY][TX];
+};
+
+template <int TY, bool GRAD>
+__global__ void __launch_bounds__(TY * 32, 1)
+fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
+                 const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT,
+                 const __grid_constant__ CUtensorMap mapW, const Params P) {
+    static_assert(TY <= 16, "four lane quarters x (512 / 128) column groups");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    StageM<TY>& S = *reinterpret_cast<StageM<TY>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    __shared__ uint64_t barY, barX, barZ;
+    __shared__ uint32_t cntY, cntX, cntZ, s_tmem;
+    __shared__ float s_red[12][TY];
+
+    constexpr uint32_t kBytesTW = sizeof(S.sTW[0]);
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + kBytesTW;
+    constexpr uint32_t kBytesX = sizeof(S.sX) + kBytesTW;
+    constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
+    constexpr uint32_t kWarps = TY;
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int D = P.D, H = P.H, W = P.W;
+    const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+    int bid = blockIdx.x;
+    const int tix = bid % tiles_x;
+    bid /= tiles_x;
+    const int tiy = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int x0 = tix * TX, y0 = tiy * TY;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool live = (x < W) && (y < H);
+    const int64_t HW = (int64_t)H * W, N = HW * D;
+    const int64_t pix = (int64_t)(live ? y : 0) * W + (live ? x : 0);
+
+    // channels 3 g + c0 (g = 0..3) of target and weight in one strided copy each
+    auto issueTW = [&](int part, int c0, int z, uint64_t* bar) {
+        tma_load_5d(&S.sTW[part][0][0][0][0], &mapT, bar, x0, y0, z, c0, b);
+        tma_load_5d(&S.sTW[part][1][0][0][0], &mapW, bar, x0, y0, z, c0, b);
+    };
+    auto issueY = [&](int z) {
+        mbar_arrive_expect_tx(&barY, kBytesY);
+        tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
+        issueTW(0, 1, z, &barY);
+        tma_load_5d(&S.sAm[0][0][0], &mapA, &barY, x0, y0 - FAR, z, 0, b);
+        tma_load_5d(&S.sAp[0][0][0], &mapA, &barY, x0, y0 + FAR, z, 0, b);
+    };
+    auto issueX = [&](int z) {
+        mbar_arrive_expect_tx(&barX, kBytesX);
+        tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
+        issueTW(1, 2, z, &barX);
+    };
+    auto issueZ = [&](int z) {
+        mbar_arrive_expect_tx(&barZ, kBytesTW);
+        issueTW(2, 0, z, &barZ);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&barY, 1);
+        mbar_init(&barX, 1);
+        mbar_init(&barZ, 1);
+        cntY = cntX = cntZ = 0;
+        mbar_fence_init();
+        issueY(0);
+        issueX(0);
+        issueZ(0);
+    }
+    if (ty == 0) {  // one warp allocates the whole Tensor Memory of this SM (one CTA per SM anyway: shared memory)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+    // this thread's private strip: lane = 32 * (warp % 4) + lane id, 128 columns starting at 128 * (warp / 4);
+    // slot s (slice z with z & 3 == s): columns [32 s, 32 s + 16) unit vector, [32 s + 16, 32 s + 32) gradient accumulator
+    const uint32_t tq = tmem_base + (((uint32_t)(ty & 3) * 32u) << 16) + (uint32_t)(ty >> 2) * 128u;
+
+    float rr1 = 0.f, rr2 = 0.f, rr3 = 0.f, rr4 = 0.f;  // 1/|x| of slices z-1 .. z-4 (for the normalisation backward)
+    float lossacc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) lossacc[k] = 0.f;
+
+    const float* tgt_b = P.target + (int64_t)b * 12 * N + pix;
+    const float* wgt_b = P.weight + (int64_t)b * 12 * N + pix;
+    float* affs_b = P.affs ? P.affs + (int64_t)b * 12 * N + pix : nullptr;
+    float* grad_b = P.grad ? P.grad + (int64_t)b * kC * N + pix : nullptr;
+
+    // back through the normalisation:  (G - e^ <e^, G>) / |x|   (eps branch of F.normalize: G / eps)
+    auto retire = [&](const f32x2 (&e)[kC2], const f32x2 (&G)[kC2], float r, int zf) {
+        if (!GRAD || !live) return;
+        f32x2 p0 = 0ull, p1 = 0ull;
+#pragma unroll
+        for (int i = 0; i < kC2; i += 2) {
+            p0 = fma2(e[i], G[i], p0);
+            p1 = fma2(e[i + 1], G[i + 1], p1);
+        }
+        float eg = hsum2(p0, p1);
+        if (!(r < 1e12f)) eg = 0.f;
+        const f32x2 neg = pack2(-eg, -eg), r2 = pack2(r, r);
+        float* dst = grad_b + (int64_t)zf * HW;
+#pragma unroll
+        for (int i = 0; i < kC2; ++i) {
+            float lo, hi;
+            unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
+            dst[(int64_t)(2 * i) * N] = lo;
+            dst[(int64_t)(2 * i + 1) * N] = hi;
+        }
+    };
+
+    // target / weight of the pairs anchored at the +s neighbours (gather-form backward), straight from global memory
+    // (zero when the anchor is outside the volume).  Loaded half a slice ahead: the x values at the start of the y part,
+    // the y values of the NEXT slice at the start of the x part.
+    float t2y[4], w2y[4], t2x[4], w2x[4];
+    auto load_t2y = [&](int z) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const bool v = live && (y + s < H);
+            const int64_t o = (int64_t)(3 * g + 1) * N + (int64_t)z * HW + (int64_t)s * W;
+            t2y[g] = ldg_early(tgt_b + o, v);
+            w2y[g] = ldg_early(wgt_b + o, v);
+        }
+    };
+    auto load_t2x = [&](int z) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const bool v = live && (x + s < W);
+            const int64_t o = (int64_t)(3 * g + 2) * N + (int64_t)z * HW + s;
+            t2x[g] = ldg_early(tgt_b + o, v);
+            w2x[g] = ldg_early(wgt_b + o, v);
+        }
+    };
+    if (GRAD) load_t2y(0);
+
+    const float* sTy = &S.sTW[0][0][0][ty][tx];
+    const float* sTx = &S.sTW[1][0][0][ty][tx];
+    const float* sTz = &S.sTW[2][0][0][ty][tx];
+    constexpr int kW = 4 * CHS_A;  // weight plane of a group = target plane + kW
+
+    for (int z = 0; z < D; ++z) {
+        const uint32_t par = (uint32_t)(z & 1);
+        const int64_t zoff = (int64_t)z * HW;
+        if (GRAD) load_t2x(z);
+
+        f32x2 e[kC2], G[kC2];
+        float rp;
+        // ---------------- y part
+        mbar_wait(&barY, par);
+        {
+            const float* own = &S.sY[0][ty + HY][tx];
+            f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) e[i] = pack2(own[(2 * i) * CHS_Y], own[(2 * i + 1) * CHS_Y]);
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                s0 = fma2(e[i], e[i], s0);
+                s1 = fma2(e[i + 1], e[i + 1], s1);
+            }
+            rp = inv_norm(hsum2(s0, s1));
+            const f32x2 rp2 = pack2(rp, rp);
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) {
+                e[i] = mul2(e[i], rp2);
+                G[i] = 0ull;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const int k = 3 * g + 1;
+            const float* nb_m = (g < 3) ? &S.sY[0][ty + HY - s][tx] : &S.sAm[0][ty][tx];
+            const float* nb_p = (g < 3) ? &S.sY[0][ty + HY + s][tx] : &S.sAp[0][ty][tx];
+            const int chs = (g < 3) ? CHS_Y : CHS_A;
+            const bool vf = y >= s;  // out-of-volume voxels have zero weight (TMA zero fill)
+            float a;
+            lossacc[k] += inplane_pair<GRAD>(nb_m, chs, e, G, sTy[g * CHS_A], vf ? sTy[kW + g * CHS_A] : 0.f, P.gcoef[k], a);
+            if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;  // partner outside the volume: zero fill, a == 0
+            if (GRAD) {
+                float a2;
+                inplane_pair<true>(nb_p, chs, e, G, t2y[g], w2y[g], P.gcoef[k], a2);
+            }
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueY(z + 1);
+
+        // ---------------- x part
+        if (GRAD && z + 1 < D) load_t2y(z + 1);
+        mbar_wait(&barX, par);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const int k = 3 * g + 2;
+            const bool vf = x >= s;
+            float a;
+            lossacc[k] += inplane_pair<GRAD>(&S.sX[0][ty][tx + XPAD - s], CHS_X, e, G, sTx[g * CHS_A],
+                                             vf ? sTx[kW + g * CHS_A] : 0.f, P.gcoef[k], a);
+            if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
+            if (GRAD) {
+                float a2;
+                inplane_pair<true>(&S.sX[0][ty][tx + XPAD + s], CHS_X, e, G, t2x[g], w2x[g], P.gcoef[k], a2);
+            }
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueX(z + 1);
+
+        // ---------------- z part: pairs (z, z - j); slice z - j comes out of its Tensor-Memory slot, its updated
+        // gradient accumulator goes back (j < 4) or -- all pairs of slice z - 4 seen -- straight through the
+        // normalisation backward to global memory
+        mbar_wait(&barZ, par);
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) {
+            const int k = 3 * (j - 1);
+            if (z >= j) {  // CTA-uniform
+                const uint32_t slot = tq + ((uint32_t)((z - j) & 3) << 5);
+                f32x2 ej[kC2], Gj[kC2];
+                if (GRAD) tmem_ld16x2(slot, ej, Gj);
+                else tmem_ld16(slot, ej);
+                f32x2 d0 = 0ull, d1 = 0ull;
+#pragma unroll
+                for (int i = 0; i < kC2; i += 2) {
+                    d0 = fma2(e[i], ej[i], d0);
+                    d1 = fma2(e[i + 1], ej[i + 1], d1);
+                }
+                const float a = hsum2(d0, d1);
+                const float diff = a - sTz[(j - 1) * CHS_A];
+                const float wv = sTz[kW + (j - 1) * CHS_A];  // 0 outside the volume
+                lossacc[k] += wv * diff * diff;
+                if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
+                if (GRAD) {
+                    const float gg = P.gcoef[k] * wv * diff;
+                    const f32x2 gg2 = pack2(gg, gg);
+#pragma unroll
+                    for (int i = 0; i < kC2; ++i) {
+                        G[i] = fma2(gg2, ej[i], G[i]);
+                        Gj[i] = fma2(gg2, e[i], Gj[i]);
+                    }
+                    if (j < 4) tmem_st16(slot + 16, Gj);
+                    else retire(ej, Gj, rr4, z - 4);
+                }
+            } else if (affs_b && live) {
+                affs_b[(int64_t)k * N + zoff] = 0.f;
+            }
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntZ) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueZ(z + 1);
+        // this slice takes the slot of slice z - 4 (retired above)
+        {
+            const uint32_t slot = tq + ((uint32_t)(z & 3) << 5);
+            tmem_st16(slot, e);
+            if (GRAD) tmem_st16(slot + 16, G);
+            tmem_wait_st();
+        }
+        rr4 = rr3;
+        rr3 = rr2;
+        rr2 = rr1;
+        rr1 = rp;
+    }
+    // drain: slices D-4 .. D-1 (those >= 0) still hold their gradient in Tensor Memory; rr_j belongs to slice D - j
+    if (GRAD) {
+#pragma unroll
+        for (int j = 4; j >= 1; --j) {
+            if (D - j >= 0) {
+                f32x2 ej[kC2], Gj[kC2];
+                tmem_ld16x2(tq + ((uint32_t)((D - j) & 3) << 5), ej, Gj);
+                retire(ej, Gj, j == 4 ? rr4 : (j == 3 ? rr3 : (j == 2 ? rr2 : rr1)), D - j);
+            }
+        }
+    }
+
+    // ---------------- loss partials: thread -> warp -> CTA row
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const float v = warp_sum(lossacc[k]);
+        if (tx == 0) s_red[k][ty] = v;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (ty == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+    if (threadIdx.x < 12) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < TY; ++i) v += s_red[threadIdx.x][i];
+        P.partials[(int64_t)blockIdx.x * 12 + threadIdx.x] = v;
+    }
+}
+
+
+// ================================================================================================================
 // Forward only: inf_embedding_loss_norm5 (scripts_ac3ac4/loss/loss_embedding_mse.py:212-234) and the z-sharded
 // full-volume inference.  Same z-march, but only the "-shift" side of every offset is needed: a 4-slice register
 // ring of unit vectors, a y-column box with 9 rows of upper halo, the y-27 arm and an x-row box with 28 columns of
@@ -824,7 +1194,7 @@ int tiled3d_norm5_blocks(int B, int H, int W) {
     return B * ((H + TY - 1) / TY) * ((W + t3::TX - 1) / t3::TX);
 }
 
-int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
+int launch_fused3d_norm5_rf(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st) {
     constexpr int TY = kTileY;
     CUtensorMap mY, mA, mX, mT, mW;
@@ -851,6 +1221,58 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
         kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
     }
     return (int)cudaGetLastError();
+}
+
+
+#ifndef PEA_K4_TMEM
+#define PEA_K4_TMEM 1
+#endif
+#ifndef PEA_TILE_Y3D_TM
+#define PEA_TILE_Y3D_TM 12
+#endif
+constexpr int kTileYTm = PEA_TILE_Y3D_TM;  // rows (= warps) per CTA of the Tensor-Memory variant
+
+// number of CTAs (= rows of loss partials) of the self (one-view) fused kernel
+int fused3d_norm5_blocks(int B, int H, int W) {
+#if PEA_K4_TMEM
+    return B * ((H + kTileYTm - 1) / kTileYTm) * ((W + t3::TX - 1) / t3::TX);
+#else
+    return tiled3d_norm5_blocks(B, H, W);
+#endif
+}
+
+int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
+                         const float* weight, float* affs, float* partials, float* grad, cudaStream_t st) {
+#if !PEA_K4_TMEM
+    return launch_fused3d_norm5_rf(emb, d, tab, target, weight, affs, partials, grad, st);
+#else
+    constexpr int TY = kTileYTm;
+    CUtensorMap mY, mA, mX, mT, mW;
+    int rc;
+    if ((rc = encode_volume_map(&mY, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY + 2 * t3::HY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mA, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mX, emb, d.B, 16, d.D, d.H, d.W, t3::XW, TY, 1, 16))) return rc;
+    // every third channel from the start coordinate: 4 planes (c0, c0 + 3, c0 + 6, c0 + 9) per copy
+    if ((rc = encode_volume_map(&mT, target, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 10, 0, 3))) return rc;
+    if ((rc = encode_volume_map(&mW, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 10, 0, 3))) return rc;
+    t3::Params P;
+    P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
+    for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
+    const int grid = fused3d_norm5_blocks(d.B, d.H, d.W);
+    const size_t smem = sizeof(t3::StageM<TY>) + 128;
+    cudaError_t e;
+    if (grad) {
+        auto kern = t3::fused3d_norm5_tm<TY, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
+    } else {
+        auto kern = t3::fused3d_norm5_tm<TY, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
+    }
+    return (int)cudaGetLastError();
+#endif
 }
 
 bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
