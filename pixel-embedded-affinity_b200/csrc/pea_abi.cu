@@ -33,6 +33,14 @@ int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const 
                    const float* target, const float* weight, const void* mask, int mask_dtype, float* affs,
                    float* partials, float* grad, cudaStream_t st);
 
+// pea_affs2d_axis.cu
+bool axis2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wrap, bool need_grad_partner, const float* emb,
+                     const float* partner);
+int axis2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap);
+int launch_axis2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap,
+                  const float* target, const float* weight, const void* mask, int mask_dtype, float* affs, float* partials,
+                  float* grad, cudaStream_t st);
+
 int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab,
                          const float* target, const float* weight, float* affs, float* partials, float* grad,
                          cudaStream_t st);
@@ -230,6 +238,17 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
                            grad_partner == nullptr;
     const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr);
     if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
+    if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC &&
+        axis2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr, emb, partner ? partner : emb) &&
+        !((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(weight)) & 3)) {
+        // axis-aligned tables (every shipped 2-D config): TMA-staged kernel
+        float* parts = ws.rinvE;
+        if ((rc = launch_axis2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts,
+                                grad_emb, st)))
+            return rc;
+        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, axis2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
+        return (int)cudaGetLastError();
+    }
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC) {
         float* parts = ws.rinvE;
         if ((rc = launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs,
