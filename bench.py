@@ -212,7 +212,10 @@ def our_step(P, w, e, tgt, wgt, msk, offsets, crit, partner=None):
     return loss
 
 
-LAUNCHES_PER_STEP = 4  # rinv, fused, finalize_loss, scale_inplace (see DESIGN.md "kernels per step")
+LAUNCHES_PER_STEP = 3  # fused3d_norm5_tm, finalize_loss, scale_inplace (profiles/r1_launches_bench_cfg3.csv)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused kernel at cfg3, from the committed
+# `ncu --set full` capture (profiles/r1_fused3d_tm_cfg3.txt); the algorithmic figure is 501.35 MB
+NCU_TRAFFIC_BYTES = {"cfg3": 304.12e6 + 166.33e6, "cfg2": 454.19e6 + 273.47e6}
 
 
 def time_workload(P, w, steps, warmup, device, flush, dist_on):
@@ -502,7 +505,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "flushed between timed steps (256 MiB memset, untimed); step working set also exceeds L2",
                        "timing": "CUDA events around a CUDA-graph replay of the public-API fwd+bwd, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic, "peak_source": peak_src,
+                         "traffic": args.traffic if args.traffic is not None else NCU_TRAFFIC_BYTES.get(args.workload),
+                         "peak_source": peak_src,
                          "kernel": "whole fused step (all pea kernels of one fwd+bwd)",
                          "algorithmic_bytes_per_step": alg_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -541,6 +541,67 @@ def test_tiled2d_matches_generic_and_oracle(P, O, B, H, W, shifts, nb, seed):
     close_t(res["tiled"][8], res["generic"][8], what="zero-border forward")
 
 
+@pytest.mark.parametrize("B,H,W,shifts,seed", [
+    (2, 40, 64, [1, 3, 5, 9, 11], 85),      # every CTA on the image edge (hand-filled boxes under the circular border)
+    (1, 130, 128, [1, 3, 5, 9, 11], 86),    # interior CTAs (TMA boxes) and edge CTAs in one launch
+    (1, 67, 96, [1, 3, 5, 9, 27], 87),      # CVPPP shifts: the 28-pixel halo variant, partial tiles in y
+    (1, 150, 160, [1, 3, 5, 9, 27], 88),
+])
+def test_axis2d_kernel_matches_generic_and_oracle(P, O, B, H, W, shifts, seed):
+    """multi_offset(shifts, neighbor=4) tables at W % 4 == 0 take the TMA-staged axis-aligned kernel (AUTO); it must
+    agree with the table-driven kernel and with the oracle, for both masks, both views and with / without gradient."""
+    from pea_b200 import _ops as ops
+    offsets = O.multi_offset(shifts, neighbor=4)
+    for float_mask in (False, True):
+        emb, ema, tgt, wgt, msk = _inputs_2d(O, B, 16, H, W, offsets, seed, float_mask=float_mask)
+        res = {}
+        for name, impl in (("generic", ops.IMPL_GENERIC), ("auto", ops.IMPL_AUTO)):
+            ops.set_default_impl(impl)
+            try:
+                e = dev(emb, True)
+                l, a, al = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+                l.backward()
+                e2 = dev(emb, True)
+                l2, a2 = P.ema_embedding_loss(e2, dev(ema), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets,
+                                              affs0_weight=0.25)
+                l2.backward()
+                with torch.no_grad():
+                    l3, a3, _ = P.embedding_loss(dev(emb), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+                res[name] = (float(l.detach()), a.detach().cpu(), e.grad.cpu(), np.asarray(list(al)), float(l2.detach()),
+                             a2.detach().cpu(), e2.grad.cpu(), float(l3), a3.cpu())
+            finally:
+                ops.set_default_impl(ops.IMPL_AUTO)
+        eo = torch.tensor(emb, requires_grad=True)
+        lo, ao, allo = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), O.WeightedMSE(), offsets)
+        lo.backward()
+        eo2 = torch.tensor(emb, requires_grad=True)
+        lo2, ao2 = O.ema_embedding_loss(eo2, torch.tensor(ema), torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk),
+                                        O.WeightedMSE(), offsets, affs0_weight=0.25)
+        lo2.backward()
+        for name in ("generic", "auto"):
+            l, a, g, al, l2, a2, g2, l3, a3 = res[name]
+            close_s(l, lo, what=f"{name} loss")
+            close_t(a, ao, what=f"{name} affs")
+            close_t(g, eo.grad, what=f"{name} grad")
+            close_t(al, np.asarray(allo), what=f"{name} all_loss")
+            close_s(l2, lo2, what=f"{name} ema loss")
+            close_t(a2, ao2, what=f"{name} ema affs")
+            close_t(g2, eo2.grad, what=f"{name} ema grad")
+            close_s(l3, lo, what=f"{name} loss (no grad)")
+            close_t(a3, ao, what=f"{name} affs (no grad)")
+    # zero border (D = 1 volumes straight through the C ABI), mixed-sign offsets, no mask: kernels agree
+    offs3 = ops.offsets3([[3, 0], [-12, 0], [0, 7], [0, -1]], 2)
+    g = torch.Generator().manual_seed(seed)
+    e5 = torch.randn((B, 16, 1, H, W), generator=g).cuda()
+    t5 = (torch.rand((B, 4, 1, H, W), generator=g) > 0.5).float().cuda()
+    w5 = (torch.rand((B, 4, 1, H, W), generator=g) + 0.1).cuda()
+    norm, coef = np.full(4, float(B * W), np.float32), np.asarray([1.0, 0.5, 2.0, 1.0], np.float32)
+    outs = [ops.affs_loss_fwd_bwd(e5, None, offs3, ops.BORDER_ZERO, t5, w5, None, norm, coef, impl=impl)
+            for impl in (ops.IMPL_GENERIC, ops.IMPL_AUTO)]
+    for i, what in ((0, "loss"), (1, "affs"), (2, "grad")):
+        close_t(outs[1][i].cpu(), outs[0][i].cpu(), what=f"zero-border axis kernel {what}")
+
+
 # =========================================================================== forward-only tiled kernel + z-shards
 @pytest.mark.parametrize("B,D,H,W,seed", [(1, 18, 64, 96, 91), (2, 7, 37, 44, 92), (1, 5, 28, 28, 93)])
 def test_tiled3d_forward_matches_generic_and_oracle(P, O, B, D, H, W, seed):
