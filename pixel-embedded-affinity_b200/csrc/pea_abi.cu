@@ -51,24 +51,41 @@ struct LossScale {
 };
 
 // partials[blk][k] -> loss_out[0] = sum_k coef_k * (S_k / norm_k), loss_out[1+k] = S_k / norm_k.
-// Fixed summation order (double accumulation over blocks) => run-to-run reproducible loss.
+// One block: thread t owns channel t % K and every G-th row of partials (G = 1024 / K row groups; consecutive threads
+// read consecutive addresses), accumulates in double, then one thread per channel adds the G group sums in a fixed
+// order => run-to-run reproducible loss, and a few microseconds even for the ~10^4 CTAs of a 2-D batch.
 __global__ void __launch_bounds__(1024) finalize_loss_kernel(const float* __restrict__ partials, int nblocks, int K,
                                                              LossScale sc, float* __restrict__ loss_out) {
+    __shared__ double s_acc[1024];
     __shared__ float s_loss[PEA_MAX_OFFSETS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < K; k += 32) {
-        double acc = 0.0;
-        for (int b = lane; b < nblocks; b += 32) acc += (double)partials[(int64_t)b * K + k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) s_loss[k] = (float)acc / sc.norm[k];
+    const int G = 1024 / K;
+    const int k = threadIdx.x % K, g = threadIdx.x / K;
+    double acc = 0.0;
+    if (g < G) {
+        int b = g;
+        for (; b + 3 * G < nblocks; b += 4 * G) {  // four independent loads in flight
+            const float v0 = partials[(int64_t)b * K + k], v1 = partials[(int64_t)(b + G) * K + k];
+            const float v2 = partials[(int64_t)(b + 2 * G) * K + k], v3 = partials[(int64_t)(b + 3 * G) * K + k];
+            acc += (double)v0;
+            acc += (double)v1;
+            acc += (double)v2;
+            acc += (double)v3;
+        }
+        for (; b < nblocks; b += G) acc += (double)partials[(int64_t)b * K + k];
+        s_acc[g * K + k] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double tot = 0.0;
+        for (int i = 0; i < G; ++i) tot += s_acc[i * K + threadIdx.x];
+        s_loss[threadIdx.x] = (float)tot / sc.norm[threadIdx.x];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         float total = 0.f;
-        for (int k = 0; k < K; ++k) {
-            loss_out[1 + k] = s_loss[k];
-            total += s_loss[k] * sc.coef[k];
+        for (int kk = 0; kk < K; ++kk) {
+            loss_out[1 + kk] = s_loss[kk];
+            total += s_loss[kk] * sc.coef[kk];
         }
         loss_out[0] = total;
     }
