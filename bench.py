@@ -323,7 +323,7 @@ def time_zshard(P, device, rank, world, steps, shape=(100, 1024, 1024)):
     algorithmic).  Strong scaling: the volume is fixed.  Halo transport, best available first: "peer" = slabs in
     symmetric memory, the kernel reads the previous rank's last 4 slices in place over NVLink (one launch, no exchange
     step; a device-side barrier orders producer writes before the reads); "nccl" = send/recv in place, overlapped."""
-    from pea_b200.zshard import ZShard, PeerZShard, sharded_affinities, fused_halo_affinities
+    from pea_b200.zshard import ZShard, PeerZShard, sharded_affinities, fused_halo_affinities, overlapped_halo_affinities
     D, H, W = shape
     dist_on = world > 1
     transport, sh = "none", None
@@ -346,7 +346,10 @@ def time_zshard(P, device, rank, world, steps, shape=(100, 1024, 1024)):
     def step():
         if transport == "peer":
             sh.publish()                       # producer's slab visible to the next rank
-            fused_halo_affinities(sh.own, sh.prev_tail, out=out)
+            if os.environ.get("PEA_ZSHARD_OVERLAP", "0") == "1":
+                overlapped_halo_affinities(sh, out=out)
+            else:
+                fused_halo_affinities(sh.own, sh.prev_tail, out=out)
         else:
             sharded_affinities(sh, out=out)
 

@@ -837,31 +837,33 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
     const int nwarm = ext ? P.halo_n : (zs > 4 ? 4 : zs);
     const int64_t wplane = ext ? P.halo_plane : P.emb_plane;
     const float* warm_b = (ext ? P.halo : P.emb + (int64_t)(zs - nwarm) * HW) + (int64_t)b * kC * wplane + pix;
-    for (int zw = 0; zw < nwarm; ++zw) {
-        // same arithmetic order as the tile path below, so slabs reproduce the whole-volume result bit for bit
-        f32x2 v[kC2];
-        const float* p = warm_b + (int64_t)zw * HW;
+    // All (up to four) halo slices are requested at once, straight into their ring slots (slot j = slice -j relative to
+    // the first output slice): over NVLink one round trip costs microseconds, four dependent ones dominated the CTA.
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) {
+        const bool on = live && j <= nwarm;
+        const float* p = warm_b + (int64_t)(on ? nwarm - j : 0) * HW;
 #pragma unroll
         for (int i = 0; i < kC2; ++i) {
-            const float lo = live ? __ldg(p) : 0.f;
-            const float hi = live ? __ldg(p + wplane) : 0.f;
+            const float lo = on ? __ldg(p) : 0.f;
+            const float hi = on ? __ldg(p + wplane) : 0.f;
             p += 2 * wplane;
-            v[i] = pack2(lo, hi);
+            re[j][i] = pack2(lo, hi);
         }
+    }
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) {
+        // same arithmetic order as the tile path below, so slabs reproduce the whole-volume result bit for bit
         f32x2 s0 = 0ull, s1 = 0ull;
 #pragma unroll
         for (int i = 0; i < kC2; i += 2) {
-            s0 = fma2(v[i], v[i], s0);
-            s1 = fma2(v[i + 1], v[i + 1], s1);
+            s0 = fma2(re[j][i], re[j][i], s0);
+            s1 = fma2(re[j][i + 1], re[j][i + 1], s1);
         }
         const float r = inv_norm(hsum2(s0, s1));
         const f32x2 r2 = pack2(r, r);
 #pragma unroll
-        for (int s = 4; s >= 2; --s)
-#pragma unroll
-            for (int i = 0; i < kC2; ++i) re[s][i] = re[s - 1][i];
-#pragma unroll
-        for (int i = 0; i < kC2; ++i) re[1][i] = mul2(v[i], r2);
+        for (int i = 0; i < kC2; ++i) re[j][i] = mul2(re[j][i], r2);
     }
 
     const int zprev = ext ? P.halo_n : 0;  // slices that precede emb's slice 0 (zero border applies when none do)

@@ -28,7 +28,7 @@ for it in range(3):
     ok = torch.equal(out, whole[:, :, sh.z0:sh.z1])
     assert ok, f"rank {rank} iteration {it}: slab differs from the whole-volume result"
 # fused halo through symmetric memory: no exchange step, the kernel reads the peer's slab tail in place
-from pea_b200.zshard import PeerZShard, fused_halo_affinities  # noqa: E402
+from pea_b200.zshard import PeerZShard, fused_halo_affinities, overlapped_halo_affinities  # noqa: E402
 try:
     ps = PeerZShard(1, 16, D, H, W, rank, world, dev)
 except Exception as ex:  # noqa: BLE001
@@ -40,6 +40,8 @@ if ps is not None:
         ps.publish()
         out = fused_halo_affinities(ps.own, ps.prev_tail)
         assert torch.equal(out, whole[:, :, ps.z0:ps.z1]), f"rank {rank} iteration {it}: fused-halo slab differs"
+        out2 = overlapped_halo_affinities(ps)
+        assert torch.equal(out2, whole[:, :, ps.z0:ps.z1]), f"rank {rank} iteration {it}: overlapped-halo slab differs"
         ps.publish()   # nobody overwrites a slab while a neighbour may still be reading it
     print(f"zshard_check fused-halo OK rank {rank}/{world}", flush=True)
 torch.cuda.synchronize()
