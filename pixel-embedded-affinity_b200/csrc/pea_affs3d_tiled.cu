@@ -578,6 +578,7 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int s = shift_yx(g);
+            if (ty + s < TY) continue;  // warp-uniform: the anchor row lies in this CTA's own tile -> shared memory below
             const bool v = live && (y + s < H);
             const int64_t o = (int64_t)(3 * g + 1) * N + (int64_t)z * HW + (int64_t)s * W;
             t2y[g] = ldg_early(tgt_b + o, v);
@@ -640,8 +641,13 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             lossacc[k] += inplane_pair<GRAD>(nb_m, chs, e, G, sTy[g * CHS_A], vf ? sTy[kW + g * CHS_A] : 0.f, P.gcoef[k], a);
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;  // partner outside the volume: zero fill, a == 0
             if (GRAD) {
+                // pair anchored at y + s: its target / weight sit in the own tile group when that row belongs to this CTA
+                // (rows beyond the image are zero fill there), else they were fetched from global half a slice ago
+                const bool own_tile = ty + s < TY;  // warp-uniform
+                const float t_r = own_tile ? sTy[g * CHS_A + s * TX] : t2y[g];
+                const float w_r = own_tile ? sTy[kW + g * CHS_A + s * TX] : w2y[g];
                 float a2;
-                inplane_pair<true>(nb_p, chs, e, G, t2y[g], w2y[g], P.gcoef[k], a2);
+                inplane_pair<true>(nb_p, chs, e, G, t_r, w_r, P.gcoef[k], a2);
             }
         }
         __syncwarp();
