@@ -1,0 +1,161 @@
+"""GPU parity at BASELINE.json's FULL sizes, through size-independent properties (the oracle needs seconds to minutes at
+these sizes, so it is not the checker here): specialised kernel == table-driven kernel, scale invariance of the loss,
+gradient orthogonal to the embedding, analytic loss of a constant embedding, equivariance under circular shifts (2-D),
+z-shard concatenation == whole volume (bit for bit), GT targets == an independent torch formulation (bit for bit)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5   # fp32 tolerance of BASELINE.json's north_star, relative to the largest reference magnitude
+
+
+def close(a, b, what, rtol=RTOL):
+    scale = float(b.abs().max())
+    err = float((a - b).abs().max())
+    assert err <= rtol * max(scale, 1e-30), f"{what}: |delta| {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pea_b200
+    return pea_b200
+
+
+def _voronoi_gpu(shape, n, seed, bg=0.1):
+    """Synthetic instance labels on the device (nearest of n random seeds, a fraction of them background)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    nd = len(shape)
+    pts = torch.rand((n, nd), device="cuda", generator=g) * torch.tensor(shape, device="cuda", dtype=torch.float32)
+    grids = torch.meshgrid(*[torch.arange(s, device="cuda", dtype=torch.float32) for s in shape], indexing="ij")
+    best = torch.full(shape, 3.0e38, device="cuda")
+    lab = torch.zeros(shape, device="cuda", dtype=torch.int32)
+    for i in range(n):
+        d = sum((gr - pts[i, k]) ** 2 * (64.0 if (nd == 3 and k == 0) else 1.0) for k, gr in enumerate(grids))
+        upd = d < best
+        best = torch.where(upd, d, best)
+        lab = torch.where(upd, torch.full_like(lab, 0 if i < int(n * bg) else i + 1), lab)
+    return lab
+
+
+def test_cfg3_full_size_3d(P):
+    from pea_b200 import _ops as ops
+    B, D, H, W = 4, 18, 160, 160
+    g = torch.Generator(device="cuda").manual_seed(3)
+    emb = torch.randn((B, 16, D, H, W), device="cuda", generator=g)
+    lab = torch.stack([_voronoi_gpu((D, H, W), 40, 10 + b) for b in range(B)])
+    tgt, wgt = P.make_targets_3d(lab)
+    # GT against an independent torch formulation: background-aware equality with the shifted volume, zero border
+    shifts = [1, 1, 1, 2, 3, 3, 3, 9, 9, 4, 27, 27]
+    for k, s in enumerate(shifts):
+        ax = 1 + k % 3
+        ref = torch.zeros((B, D, H, W), device="cuda")
+        a = lab.narrow(ax, s, lab.shape[ax] - s)
+        b_ = lab.narrow(ax, 0, lab.shape[ax] - s)
+        ref.narrow(ax, s, lab.shape[ax] - s).copy_(((a == b_) & (a > 0) & (b_ > 0)).float())
+        assert torch.equal(tgt[:, k], ref), f"3D target channel {k}"
+        n1 = int(ref.sum())  # weights: two values per (sample, channel); uniform channels get ones
+        vals = torch.unique(wgt[:, k])
+        assert vals.numel() <= 2 * B and float(wgt[:, k].min()) > 0 and n1 >= 0
+    res = {}
+    for name, impl in (("generic", ops.IMPL_GENERIC), ("tiled", ops.IMPL_AUTO)):
+        ops.set_default_impl(impl)
+        try:
+            e = emb.clone().requires_grad_(True)
+            l, a = P.embedding_loss_norm5(e, tgt, wgt, P.WeightedMSE(), affs0_weight=1.0)
+            l.backward()
+            res[name] = (l.detach(), a, e.grad)
+        finally:
+            ops.set_default_impl(ops.IMPL_AUTO)
+    close(res["tiled"][0], res["generic"][0], "loss: Tensor-Memory kernel vs table-driven kernel")
+    close(res["tiled"][1], res["generic"][1], "affs")
+    close(res["tiled"][2], res["generic"][2], "grad")
+    l, a, gr = res["tiled"]
+    assert float(a.abs().max()) <= 1.0 + 1e-5                       # cosine similarities
+    assert float(a[:, 9, :4].abs().max()) == 0.0 and float(a[:, 11, :, :, :27].abs().max()) == 0.0   # zero border
+    # the loss only sees x / |x|: the gradient is orthogonal to x at every voxel, and scaling x by c leaves the loss
+    # unchanged and divides the gradient by c
+    dot = (gr * emb).sum(1)
+    assert float(dot.abs().max()) <= 1e-5 * float((gr.abs() * emb.abs()).sum(1).max())
+    e2 = (emb * 4.0).requires_grad_(True)        # power of two: the arithmetic is exactly scaled
+    l2, a2 = P.embedding_loss_norm5(e2, tgt, wgt, P.WeightedMSE(), affs0_weight=1.0)
+    l2.backward()
+    close(l2.detach(), l, "scale invariance of the loss")
+    close(e2.grad * 4.0, gr, "gradient scales with 1 / c")
+    # constant embedding: every valid affinity is 1 -> loss_k = sum w (1 - t)^2 / norm_k, known in closed form
+    ec = torch.ones_like(emb)
+    lc, ac = P.embedding_loss_norm5(ec, tgt, wgt, P.WeightedMSE(), affs0_weight=1.0)
+    want = 0.0
+    for k, s in enumerate(shifts):
+        ax = 1 + k % 3
+        ext = [D, H, W]
+        ext[k % 3] -= s
+        valid_t = tgt[:, k].narrow(ax, s, lab.shape[ax] - s)
+        valid_w = wgt[:, k].narrow(ax, s, lab.shape[ax] - s)
+        want += float((valid_w.double() * (1.0 - valid_t.double()) ** 2).sum()) / (float(np.prod(ext)) * B)
+    assert abs(float(lc) - want) <= 1e-5 * want, (float(lc), want)
+
+
+def test_cfg2_full_size_2d(P):
+    from pea_b200 import _ops as ops
+    B, H, W = 8, 520, 696
+    offsets = P.multi_offset([1, 3, 5, 9, 11], 4)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    emb = torch.randn((B, 16, H, W), device="cuda", generator=g)
+    lab = torch.stack([_voronoi_gpu((H, W), 20, 100 + b, bg=0.3) for b in range(B)]).to(torch.uint8)
+    tgt, msk, wgt = P.make_targets_2d(lab, offsets)
+    # GT against torch: equality with the shifted image where the partner exists, padding value 1 and mask 0 elsewhere
+    for k, (dy, dx) in enumerate(offsets):
+        ref = torch.ones((B, H, W), device="cuda")
+        mref = torch.zeros((B, H, W), device="cuda", dtype=torch.uint8)
+        ys, xs = slice(max(0, -dy), H - max(0, dy)), slice(max(0, -dx), W - max(0, dx))
+        yq, xq = slice(max(0, dy), H - max(0, -dy)), slice(max(0, dx), W - max(0, -dx))
+        ref[:, ys, xs] = (lab[:, ys, xs] == lab[:, yq, xq]).float()
+        mref[:, ys, xs] = 1
+        assert torch.equal(tgt[:, k], ref), f"2D target channel {k}"
+        assert torch.equal(msk[:, k], mref), f"2D mask channel {k}"
+    res = {}
+    for name, impl in (("generic", ops.IMPL_GENERIC), ("axis", ops.IMPL_AUTO)):
+        ops.set_default_impl(impl)
+        try:
+            e = emb.clone().requires_grad_(True)
+            l, a, each = P.embedding_loss(e, tgt, wgt, msk, P.WeightedMSE(), offsets)
+            l.backward()
+            res[name] = (l.detach(), a.detach(), e.grad, each.device_tensor if hasattr(each, "device_tensor") else None)
+        finally:
+            ops.set_default_impl(ops.IMPL_AUTO)
+    close(res["axis"][0], res["generic"][0], "loss: axis-aligned TMA kernel vs table-driven kernel")
+    close(res["axis"][1], res["generic"][1], "affs")
+    close(res["axis"][2], res["generic"][2], "grad")
+    l, a, gr, _ = res["axis"]
+    dot = (gr * emb).sum(1)
+    assert float(dot.abs().max()) <= 1e-5 * float((gr.abs() * emb.abs()).sum(1).max())
+    # circular border: rolling every input by (ry, rx) rolls affinities and gradient and leaves the loss unchanged
+    ry, rx = 37, 100   # rx multiple of 4 keeps the kernel's alignment path; ry arbitrary
+    roll = lambda t: torch.roll(t, shifts=(ry, rx), dims=(-2, -1)).contiguous()
+    e2 = roll(emb).requires_grad_(True)
+    l2, a2, _ = P.embedding_loss(e2, roll(tgt), roll(wgt), roll(msk), P.WeightedMSE(), offsets)
+    l2.backward()
+    close(l2.detach(), l, "loss under a circular shift")
+    close(a2.detach(), roll(a), "affinities under a circular shift")
+    close(e2.grad, roll(gr), "gradient under a circular shift")
+
+
+def test_cfg4_full_volume_zshards(P):
+    from pea_b200.zshard import shard_ranges, fused_halo_affinities, HALO
+    D, H, W = 100, 1024, 1024
+    g = torch.Generator(device="cuda").manual_seed(4)
+    vol = torch.randn((1, 16, D, H, W), device="cuda", generator=g)
+    whole = P.inf_embedding_loss_norm5(vol)
+    assert float(whole.abs().max()) <= 1.0 + 1e-5
+    assert float(whole[:, 9, :4].abs().max()) == 0.0 and float(whole[:, 10, :, :27].abs().max()) == 0.0
+    # affinities are symmetric in the pair: channel 0 (z - 1) of the flipped volume is channel 0 shifted by one slice
+    flip = P.inf_embedding_loss_norm5(torch.flip(vol, dims=(2,)).contiguous())
+    close(torch.flip(flip[:, 0, 1:], dims=(1,)), whole[:, 0, 1:], "z-pair symmetry under a flip")
+    del flip
+    for world in (8,):
+        for r, (z0, z1) in enumerate(shard_ranges(D, world)):
+            tail = vol[:, :, z0 - HALO:z0] if r else None
+            part = fused_halo_affinities(vol[:, :, z0:z1], tail)
+            assert torch.equal(part, whole[:, :, z0:z1]), f"slab {r} of {world} differs from the whole volume"
+            del part
