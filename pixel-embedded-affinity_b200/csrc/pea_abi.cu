@@ -256,6 +256,7 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr);
     if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC &&
+        B <= 65535 &&
         axis2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr, emb, partner ? partner : emb) &&
         !((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(weight)) & 3)) {
         // axis-aligned tables (every shipped 2-D config): TMA-staged kernel

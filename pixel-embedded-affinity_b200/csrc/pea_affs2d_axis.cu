@@ -189,12 +189,8 @@ fused2d_axis(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ C
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int H = P.H, W = P.W, K = P.K;
-    const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
-    int bid = blockIdx.x;
-    const int tix = bid % tiles_x;
-    bid /= tiles_x;
-    const int tiy = bid % tiles_y;
-    const int b = bid / tiles_y;
+    const int tix = blockIdx.x, tiy = blockIdx.y, b = blockIdx.z;  // 3-D grid: no div / mod chain
+    const int lin_block = (b * (int)gridDim.y + tiy) * (int)gridDim.x + tix;
     const int x0 = tix * TX, y0 = tiy * TY;
     const int x = x0 + tx, y = y0 + ty;
     const bool live = (x < W) && (y < H);
@@ -278,18 +274,48 @@ fused2d_axis(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ C
     };
 
     if (manual) {
+        // two staged pixels per iteration: 32 independent loads in flight (the chain of L2 round trips is what an edge
+        // CTA waits for)
         const float* src = (CROSS ? P.par : P.emb) + (int64_t)b * kC * Nu;
-        for (int idx = threadIdx.x; idx < YR * TX; idx += NT) {
-            const int row = idx >> 5, col = idx & 31;
-            const uint32_t o = (uint32_t)(wrap3(y0 - PMAX + row, H) * W + wrap3(x0 + col, W));
+        float* sYf = &S.sY[0][0][0];
+        float* sXf = &S.sX[0][0][0];
+        for (int idx = threadIdx.x; idx < YR * TX; idx += 2 * NT) {
+            const int idx2 = idx + NT;
+            const bool two = idx2 < YR * TX;
+            const int row = idx >> 5, col = idx & 31, row2 = (two ? idx2 : idx) >> 5;
+            const uint32_t gx = (uint32_t)wrap3(x0 + col, W);
+            const uint32_t o = (uint32_t)(wrap3(y0 - PMAX + row, H) * W) + gx;
+            const uint32_t o2 = (uint32_t)(wrap3(y0 - PMAX + row2, H) * W) + gx;
+            float v[kC], v2[kC];
 #pragma unroll
-            for (int c = 0; c < kC; ++c) S.sY[c][row][col] = __ldg(src + (o + (uint32_t)c * Nu));
+            for (int c = 0; c < kC; ++c) {
+                v[c] = __ldg(src + (o + (uint32_t)c * Nu));
+                v2[c] = __ldg(src + (o2 + (uint32_t)c * Nu));
+            }
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                sYf[c * CHS_Y + idx] = v[c];
+                if (two) sYf[c * CHS_Y + idx2] = v2[c];
+            }
         }
-        for (int idx = threadIdx.x; idx < TY * XW; idx += NT) {
+        for (int idx = threadIdx.x; idx < TY * XW; idx += 2 * NT) {
+            const int idx2 = idx + NT;
+            const bool two = idx2 < TY * XW;
             const int row = idx / XW, col = idx - row * XW;
+            const int j2 = two ? idx2 : idx, row2 = j2 / XW, col2 = j2 - row2 * XW;
             const uint32_t o = (uint32_t)(wrap3(y0 + row, H) * W + wrap3(x0 - PX + col, W));
+            const uint32_t o2 = (uint32_t)(wrap3(y0 + row2, H) * W + wrap3(x0 - PX + col2, W));
+            float v[kC], v2[kC];
 #pragma unroll
-            for (int c = 0; c < kC; ++c) S.sX[c][row][col] = __ldg(src + (o + (uint32_t)c * Nu));
+            for (int c = 0; c < kC; ++c) {
+                v[c] = __ldg(src + (o + (uint32_t)c * Nu));
+                v2[c] = __ldg(src + (o2 + (uint32_t)c * Nu));
+            }
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                sXf[c * CHS_X + idx] = v[c];
+                if (two) sXf[c * CHS_X + idx2] = v2[c];
+            }
         }
     }
     const float* ownY = &S.sY[0][ty + PMAX][tx];
@@ -404,7 +430,7 @@ fused2d_axis(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < TY; ++i) v += S.sL[k][i * 32 + tx];
         v = warp_sum(v);
-        if (tx == 0) P.partials[(int64_t)blockIdx.x * K + k] = v;
+        if (tx == 0) P.partials[(int64_t)lin_block * K + k] = v;
     }
 }
 
@@ -448,6 +474,7 @@ bool axis2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wra
                      const float* partner) {
     if (C != 16 || D != 1 || need_grad_partner) return false;
     if ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(partner)) & 15) return false;
+    if (H > 65535 * 8) return false;  // grid.y
     PlanAxis p;
     return plan_axis(tab, H, W, wrap, p);
 }
@@ -459,7 +486,8 @@ int axis2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap) {
 }
 
 template <int TY, int PMAX, bool CROSS, int MASK>
-static int launch_axis_g(const CUtensorMap& mY, const CUtensorMap& mX, const a2::Params& P, int grid, cudaStream_t st) {
+static int launch_axis_g(const CUtensorMap& mY, const CUtensorMap& mX, const a2::Params& P, int, cudaStream_t st) {
+    const dim3 grid((unsigned)((P.W + a2::TX - 1) / a2::TX), (unsigned)((P.H + TY - 1) / TY), (unsigned)P.B);
     const size_t smem = sizeof(a2::Stage<TY, PMAX>) + 128;
     cudaError_t e;
     if (P.grad) {
