@@ -56,8 +56,12 @@ def check_embedding(name, t, ndim=None, make_contiguous=True):
         raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
     if not t.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor: pea_b200 has no CPU path")
+    if t.dtype in (torch.bfloat16, torch.float16):
+        # autocast backbones hand over half-precision embeddings: the path computes in fp32 on the exactly representable
+        # upcast values (differentiable cast; the gradient comes back rounded to the input dtype: 2^-8 / 2^-11 relative)
+        t = t.float()
     if t.dtype != torch.float32:
-        raise TypeError(f"{name} must be float32, got {t.dtype}")
+        raise TypeError(f"{name} must be float32 (or bfloat16 / float16, upcast here), got {t.dtype}")
     if ndim is not None and t.dim() != ndim:
         raise ValueError(f"{name} must have {ndim} dimensions, got shape {tuple(t.shape)}")
     return t.contiguous() if make_contiguous else t

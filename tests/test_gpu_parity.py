@@ -386,6 +386,29 @@ def test_backward_scaling_retain_graph_and_no_grad(P, O):
     assert float(l3) == float(l2)
 
 
+def test_half_precision_embedding_inputs(P, O):
+    """bf16 / fp16 embeddings (autocast backbones): the path runs in fp32 on the upcast values -- loss and affinities
+    equal the fp32 call on those values exactly; the gradient returns in the input dtype, so it matches the fp32
+    gradient to the rounding of that dtype (bf16: 2^-8, fp16: 2^-11 relative; tolerance 2x that of the largest entry)."""
+    emb, ema, tgt, wgt = _inputs_3d(O, 1, 16, 7, 40, 48, 12, 31)
+    for dt, tol in ((torch.bfloat16, 2.0 ** -7), (torch.float16, 2.0 ** -10)):
+        eh = torch.tensor(emb).cuda().to(dt).requires_grad_(True)
+        e32 = eh.detach().float().requires_grad_(True)
+        lh, ah = P.embedding_loss_norm5(eh, dev(tgt), dev(wgt), P.WeightedMSE())
+        l32, a32 = P.embedding_loss_norm5(e32, dev(tgt), dev(wgt), P.WeightedMSE())
+        lh.backward()
+        l32.backward()
+        assert float(lh) == float(l32) and torch.equal(ah, a32)
+        assert eh.grad.dtype == dt
+        close_t(eh.grad.float().cpu(), e32.grad.cpu(), rtol=tol, what=f"{dt} gradient")
+    offsets = O.multi_offset([1, 3, 5], neighbor=4)
+    e2, _, t2, w2, m2 = _inputs_2d(O, 1, 16, 40, 64, offsets, 32)
+    eh = torch.tensor(e2).cuda().bfloat16()
+    lh, ah, _ = P.embedding_loss(eh, dev(t2), dev(w2), dev(m2), P.WeightedMSE(), offsets)
+    l32, a32, _ = P.embedding_loss(eh.float(), dev(t2), dev(w2), dev(m2), P.WeightedMSE(), offsets)
+    assert float(lh) == float(l32) and torch.equal(ah, a32)
+
+
 def test_non_contiguous_and_wrong_inputs(P, O):
     offsets = [[-1, 0], [0, -1]]
     emb, ema, tgt, wgt, msk = _inputs_2d(O, 2, 16, 12, 14, offsets, 41)
