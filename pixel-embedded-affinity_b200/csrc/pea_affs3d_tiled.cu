@@ -819,14 +819,22 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
         mbar_arrive_expect_tx(&barX, kBytesX);
         tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
     };
+    // Slice order.  With an external (peer) halo every CTA has to pull 4 slices x 16 channels over NVLink before it can
+    // produce slice 0; if all resident CTAs do that at the same moment the link is the bottleneck while the SMs idle.
+    // Odd CTAs therefore start with the part of the slab that needs no halo (slices 4 .. D-1, ring warmed up on the
+    // slab's own first slices) and visit slices 0 .. 3 last: NVLink demand is spread over the whole kernel.
+    const bool ext = P.halo != nullptr;
+    const int rot = (ext && zs == 0 && D > 4 && (blockIdx.x & 1)) ? 4 : 0;
+    const int nz = D - zs;
+    auto slice_of = [&](int i) { const int r = i + rot; return zs + (r >= nz ? r - nz : r); };
     if (threadIdx.x == 0) {
         mbar_init(&barY, 1);
         mbar_init(&barX, 1);
         cntY = cntX = 0;
         mbar_fence_init();
         if (zs < D) {
-            issueY(zs);
-            issueX(zs);
+            issueY(slice_of(0));
+            issueX(slice_of(0));
         }
     }
     __syncthreads();
@@ -837,45 +845,59 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < kC2; ++i) re[s][i] = 0ull;
 
-    // ---- ring warm-up on the halo slices (previous shard's last slices): own column straight from global -- either
-    //      the leading z_skip slices of emb, or the external (peer) halo buffer
-    const bool ext = P.halo != nullptr;
-    const int nwarm = ext ? P.halo_n : (zs > 4 ? 4 : zs);
-    const int64_t wplane = ext ? P.halo_plane : P.emb_plane;
-    const float* warm_b = (ext ? P.halo : P.emb + (int64_t)(zs - nwarm) * HW) + (int64_t)b * kC * wplane + pix;
-    // All (up to four) halo slices are requested at once, straight into their ring slots (slot j = slice -j relative to
-    // the first output slice): over NVLink one round trip costs microseconds, four dependent ones dominated the CTA.
+    // ---- ring warm-up: the (up to four) slices that precede the next output slice, own column straight from global --
+    //      the leading z_skip slices of emb, the slab's own slices (rotated order), or the external (peer) halo buffer.
+    //      All of them are requested at once, straight into their ring slots (slot j = slice -j): over NVLink one round
+    //      trip costs microseconds, four dependent ones dominated the CTA.
+    // issue: volatile loads (the compiler may not sink them), raw values land in the ring slots; finish: normalise them.
+    // Between the two the y and x parts of the next slice run (they need only the own vector and shared memory), so
+    // the NVLink round trip of the halo is hidden behind ~80 % of a slice.
+    auto warm_issue = [&](const float* src, int64_t wplane, int nwarm) {
+        const float* warm_b = src + (int64_t)b * kC * wplane + pix;
 #pragma unroll
-    for (int j = 1; j <= 4; ++j) {
-        const bool on = live && j <= nwarm;
-        const float* p = warm_b + (int64_t)(on ? nwarm - j : 0) * HW;
+        for (int j = 1; j <= 4; ++j) {
+            const bool on = live && j <= nwarm;
+            const float* p = warm_b + (int64_t)(on ? nwarm - j : 0) * HW;
 #pragma unroll
-        for (int i = 0; i < kC2; ++i) {
-            const float lo = on ? __ldg(p) : 0.f;
-            const float hi = on ? __ldg(p + wplane) : 0.f;
-            p += 2 * wplane;
-            re[j][i] = pack2(lo, hi);
+            for (int i = 0; i < kC2; ++i) {
+                const float lo = ldg_early(p, on);
+                const float hi = ldg_early(p + wplane, on);
+                p += 2 * wplane;
+                re[j][i] = pack2(lo, hi);
+            }
         }
-    }
+    };
+    auto warm_finish = [&]() {
 #pragma unroll
-    for (int j = 1; j <= 4; ++j) {
-        // same arithmetic order as the tile path below, so slabs reproduce the whole-volume result bit for bit
-        f32x2 s0 = 0ull, s1 = 0ull;
+        for (int j = 1; j <= 4; ++j) {
+            // same arithmetic order as the tile path below, so slabs reproduce the whole-volume result bit for bit
+            f32x2 s0 = 0ull, s1 = 0ull;
 #pragma unroll
-        for (int i = 0; i < kC2; i += 2) {
-            s0 = fma2(re[j][i], re[j][i], s0);
-            s1 = fma2(re[j][i + 1], re[j][i + 1], s1);
+            for (int i = 0; i < kC2; i += 2) {
+                s0 = fma2(re[j][i], re[j][i], s0);
+                s1 = fma2(re[j][i + 1], re[j][i + 1], s1);
+            }
+            const float r = inv_norm(hsum2(s0, s1));
+            const f32x2 r2 = pack2(r, r);
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) re[j][i] = mul2(re[j][i], r2);
         }
-        const float r = inv_norm(hsum2(s0, s1));
-        const f32x2 r2 = pack2(r, r);
-#pragma unroll
-        for (int i = 0; i < kC2; ++i) re[j][i] = mul2(re[j][i], r2);
-    }
+    };
+    bool pending = true;  // raw halo values sit in the ring slots, to be normalised before the next z part
+    if (rot) warm_issue(P.emb, P.emb_plane, 4);                    // slices 0 .. 3 of the slab precede slice 4
+    else if (ext) warm_issue(P.halo, P.halo_plane, P.halo_n);
+    else warm_issue(P.emb + (int64_t)(zs - (zs > 4 ? 4 : zs)) * HW, P.emb_plane, zs > 4 ? 4 : zs);
 
     const int zprev = ext ? P.halo_n : 0;  // slices that precede emb's slice 0 (zero border applies when none do)
     float* affs_b = P.affs + (int64_t)b * 12 * P.affs_plane + pix;
-    int it = 0;
-    for (int z = zs; z < D; ++z, ++it) {
+    for (int it = 0; it < nz; ++it) {
+        const int z = slice_of(it);
+        const bool more = it + 1 < nz;
+        const int znext = more ? slice_of(it + 1) : 0;
+        if (rot && z == zs) {   // rotated order: back at slice 0, now the peer halo
+            warm_issue(P.halo, P.halo_plane, P.halo_n);
+            pending = true;
+        }
         const uint32_t par = (uint32_t)(it & 1);
         float* out = affs_b + (int64_t)(z - zs) * HW;
         f32x2 (&e)[kC2] = re[0];
@@ -906,7 +928,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             if (live) out[(int64_t)(3 * g + 1) * P.affs_plane] = (y >= s) ? a : 0.f;
         }
         __syncwarp();
-        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(it + 1) - 1 && z + 1 < D) issueY(z + 1);
+        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(it + 1) - 1 && more) issueY(znext);
         // ---------------- x part
         mbar_wait(&barX, par);
 #pragma unroll
@@ -917,8 +939,12 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             if (live) out[(int64_t)(3 * g + 2) * P.affs_plane] = (x >= s) ? a : 0.f;
         }
         __syncwarp();
-        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(it + 1) - 1 && z + 1 < D) issueX(z + 1);
+        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(it + 1) - 1 && more) issueX(znext);
         // ---------------- z part: ring
+        if (pending) {  // CTA-uniform
+            warm_finish();
+            pending = false;
+        }
 #pragma unroll
         for (int j = 1; j <= 4; ++j) {
             f32x2 d0 = 0ull, d1 = 0ull;
