@@ -19,6 +19,7 @@ bool tiled3d_norm5_eligible(int C, int D, int H, int W, const OffsetTable& tab, 
                             const float* emb, const float* target, const float* weight);
 int tiled3d_norm5_blocks(int B, int H, int W);
 int fused3d_norm5_blocks(int B, int H, int W);
+int cross3d_norm5_blocks(int B, int H, int W);
 bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
                           int64_t emb_plane);
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
@@ -282,7 +283,7 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         rc = cross ? launch_cross3d_norm5(emb, partner, d, tab, target, weight, affs, parts, grad_emb, st)
                    : launch_fused3d_norm5(emb, d, tab, target, weight, affs, parts, grad_emb, st);
         if (rc) return rc;
-        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, cross ? tiled3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W),
+        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, cross ? cross3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W),
                                                  K, sc, loss_out);
         return (int)cudaGetLastError();
     }

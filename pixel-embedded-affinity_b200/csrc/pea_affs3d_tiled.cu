@@ -1203,6 +1203,244 @@ cross3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     }
 }
 
+// Two-view kernel, Tensor-Memory variant: the partner ring (4 older slices x 16 floats) lives in TMEM, which brings the
+// kernel from 202 to <= 168 registers and lets a CTA of 12 warps (12 x 32 voxel columns) run per SM.
+template <int TY, bool GRAD>
+__global__ void __launch_bounds__(TY * 32, 1)
+cross3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
+              const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapO,
+              const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapW, const Params P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    StageX<TY>& S = *reinterpret_cast<StageX<TY>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    __shared__ uint64_t barY, barX, barO, barT[2];
+    __shared__ uint32_t cntY, cntX, cntO, cntZ, s_tmem;
+    __shared__ float s_red[12][TY];
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm);
+    constexpr uint32_t kBytesX = sizeof(S.sX);
+    constexpr uint32_t kBytesO = sizeof(S.sO);
+    constexpr uint32_t kBytesT = sizeof(S.sT[0]) + sizeof(S.sW[0]);
+    constexpr int CHS_Y = (TY + HY) * TX, CHS_A = TY * TX, XWF = TX + XPAD, CHS_X = TY * XWF;
+    constexpr uint32_t kWarps = TY;
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int D = P.D, H = P.H, W = P.W;
+    const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+    int bid = blockIdx.x;
+    const int tix = bid % tiles_x;
+    bid /= tiles_x;
+    const int tiy = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int x0 = tix * TX, y0 = tiy * TY;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool live = (x < W) && (y < H);
+    const int64_t HW = (int64_t)H * W, N = HW * D;
+    const int64_t pix = (int64_t)(live ? y : 0) * W + (live ? x : 0);
+
+    auto issueY = [&](int z) {
+        mbar_arrive_expect_tx(&barY, kBytesY);
+        tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
+        tma_load_5d(&S.sAm[0][0][0], &mapA, &barY, x0, y0 - FAR, z, 0, b);
+    };
+    auto issueX = [&](int z) {
+        mbar_arrive_expect_tx(&barX, kBytesX);
+        tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
+    };
+    auto issueO = [&](int z) {
+        mbar_arrive_expect_tx(&barO, kBytesO);
+        tma_load_5d(&S.sO[0][0][0], &mapO, &barO, x0, y0, z, 0, b);
+    };
+    auto issueT = [&](int z) {
+        mbar_arrive_expect_tx(&barT[z & 1], kBytesT);
+        tma_load_5d(&S.sT[z & 1][0][0][0], &mapT, &barT[z & 1], x0, y0, z, 0, b);
+        tma_load_5d(&S.sW[z & 1][0][0][0], &mapW, &barT[z & 1], x0, y0, z, 0, b);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&barY, 1);
+        mbar_init(&barX, 1);
+        mbar_init(&barO, 1);
+        mbar_init(&barT[0], 1);
+        mbar_init(&barT[1], 1);
+        cntY = cntX = cntO = cntZ = 0;
+        mbar_fence_init();
+        issueO(0);
+        issueY(0);
+        issueX(0);
+        issueT(0);
+        if (D > 1) issueT(1);
+    }
+    if (ty == 0) {  // Tensor Memory holds the partner ring (see fused3d_norm5_tm): 4 slots x 16 columns per thread
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+    const uint32_t tq = tmem_base + (((uint32_t)(ty & 3) * 32u) << 16) + (uint32_t)(ty >> 2) * 64u;
+
+    float lossacc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) lossacc[k] = 0.f;
+
+    float* affs_b = P.affs ? P.affs + (int64_t)b * 12 * N + pix : nullptr;
+    float* grad_b = P.grad ? P.grad + (int64_t)b * kC * N + pix : nullptr;
+
+    for (int z = 0; z < D; ++z) {
+        const uint32_t par = (uint32_t)(z & 1);
+        const int64_t zoff = (int64_t)z * HW;
+        const int tb = z & 1;
+        f32x2 e[kC2], G[kC2], u0[kC2];  // u0: partner unit vector of this slice (goes into its Tensor-Memory slot)
+        float rp;
+        // ---------------- own unit vector (anchor view)
+        mbar_wait(&barO, par);
+        {
+            const float* own = &S.sO[0][ty][tx];
+            f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) e[i] = pack2(own[(2 * i) * CHS_A], own[(2 * i + 1) * CHS_A]);
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                s0 = fma2(e[i], e[i], s0);
+                s1 = fma2(e[i + 1], e[i + 1], s1);
+            }
+            rp = inv_norm(hsum2(s0, s1));
+            const f32x2 rp2 = pack2(rp, rp);
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) {
+                e[i] = mul2(e[i], rp2);
+                G[i] = 0ull;
+            }
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntO) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueO(z + 1);
+
+        // ---------------- y part; the partner's own column (ring entry of this slice) comes from the same box
+        mbar_wait(&barY, par);
+        {
+            const float* pc = &S.sY[0][ty + HY][tx];
+            f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) u0[i] = pack2(pc[(2 * i) * CHS_Y], pc[(2 * i + 1) * CHS_Y]);
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                s0 = fma2(u0[i], u0[i], s0);
+                s1 = fma2(u0[i + 1], u0[i + 1], s1);
+            }
+            const float ru_r = inv_norm(hsum2(s0, s1));
+            const f32x2 r2 = pack2(ru_r, ru_r);
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) u0[i] = mul2(u0[i], r2);
+        }
+        mbar_wait(&barT[tb], (uint32_t)((z >> 1) & 1));
+        const float* sTo = &S.sT[tb][0][ty][tx];
+        const float* sWo = &S.sW[tb][0][ty][tx];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const int k = 3 * g + 1;
+            const float* nb = (g < 3) ? &S.sY[0][ty + HY - s][tx] : &S.sAm[0][ty][tx];
+            const bool vf = live && (y >= s);
+            float a;
+            const float l = inplane_pair<GRAD>(nb, (g < 3) ? CHS_Y : CHS_A, e, G, sTo[k * CHS_A], vf ? sWo[k * CHS_A] : 0.f,
+                                               P.gcoef[k], a);
+            lossacc[k] += vf ? l : 0.f;
+            if (affs_b && live) affs_b[(int64_t)k * N + zoff] = vf ? a : 0.f;
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueY(z + 1);
+
+        // ---------------- x part
+        mbar_wait(&barX, par);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = shift_yx(g);
+            const int k = 3 * g + 2;
+            const bool vf = live && (x >= s);
+            float a;
+            const float l = inplane_pair<GRAD>(&S.sX[0][ty][tx + XPAD - s], CHS_X, e, G, sTo[k * CHS_A],
+                                               vf ? sWo[k * CHS_A] : 0.f, P.gcoef[k], a);
+            lossacc[k] += vf ? l : 0.f;
+            if (affs_b && live) affs_b[(int64_t)k * N + zoff] = vf ? a : 0.f;
+        }
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueX(z + 1);
+
+        // ---------------- z part: partner vectors of slices z - 1 .. z - 4 come out of Tensor Memory
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) {
+            const int k = 3 * (j - 1);
+            if (z >= j) {  // CTA-uniform
+                f32x2 uj[kC2];
+                tmem_ld16(tq + ((uint32_t)((z - j) & 3) << 4), uj);
+                f32x2 d0 = 0ull, d1 = 0ull;
+#pragma unroll
+                for (int i = 0; i < kC2; i += 2) {
+                    d0 = fma2(e[i], uj[i], d0);
+                    d1 = fma2(e[i + 1], uj[i + 1], d1);
+                }
+                const float a = hsum2(d0, d1);
+                const float diff = a - sTo[k * CHS_A];
+                const float wv = live ? sWo[k * CHS_A] : 0.f;
+                lossacc[k] += wv * diff * diff;
+                if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
+                if (GRAD) {
+                    const float gg = P.gcoef[k] * wv * diff;
+                    const f32x2 gg2 = pack2(gg, gg);
+#pragma unroll
+                    for (int i = 0; i < kC2; ++i) G[i] = fma2(gg2, uj[i], G[i]);
+                }
+            } else if (affs_b && live) {
+                affs_b[(int64_t)k * N + zoff] = 0.f;
+            }
+        }
+        tmem_st16(tq + ((uint32_t)(z & 3) << 4), u0);  // slot of slice z - 4, no longer needed
+        tmem_wait_st();
+        __syncwarp();
+        if (tx == 0 && arrive_count(&cntZ) == kWarps * (uint32_t)(z + 1) - 1 && z + 2 < D) issueT(z + 2);
+
+        // ---------------- gradient of this slice is complete: back through the normalisation
+        if (GRAD && live) {
+            f32x2 p0 = 0ull, p1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                p0 = fma2(e[i], G[i], p0);
+                p1 = fma2(e[i + 1], G[i + 1], p1);
+            }
+            float eg = hsum2(p0, p1);
+            if (!(rp < 1e12f)) eg = 0.f;
+            const f32x2 neg = pack2(-eg, -eg), r2 = pack2(rp, rp);
+            float* dst = grad_b + zoff;
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) {
+                float lo, hi;
+                unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
+                dst[(int64_t)(2 * i) * N] = lo;
+                dst[(int64_t)(2 * i + 1) * N] = hi;
+            }
+        }
+    }
+
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const float v = warp_sum(lossacc[k]);
+        if (tx == 0) s_red[k][ty] = v;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (ty == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+    if (threadIdx.x < 12) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < TY; ++i) v += s_red[threadIdx.x][i];
+        P.partials[(int64_t)blockIdx.x * 12 + threadIdx.x] = v;
+    }
+}
+
+
 }  // namespace t3
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1341,10 +1579,17 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
     return (int)cudaGetLastError();
 }
 
+#ifndef PEA_K4X_TMEM
+#define PEA_K4X_TMEM 1
+#endif
+constexpr int kTileYX = PEA_K4X_TMEM ? 12 : kTileY;  // rows per CTA of the two-view kernel
+
+int cross3d_norm5_blocks(int B, int H, int W) { return B * ((H + kTileYX - 1) / kTileYX) * ((W + t3::TX - 1) / t3::TX); }
+
 int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab,
                          const float* target, const float* weight, float* affs, float* partials, float* grad,
                          cudaStream_t st) {
-    constexpr int TY = kTileY;
+    constexpr int TY = kTileYX;
     if (reinterpret_cast<uintptr_t>(partner) & 15) return PEA_E_ALIGN;
     CUtensorMap mY, mA, mX, mO, mT, mW;
     int rc;
@@ -1358,9 +1603,21 @@ int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, 
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
     P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
-    const int grid = tiled3d_norm5_blocks(d.B, d.H, d.W);
+    const int grid = cross3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::StageX<TY>) + 1024;
     cudaError_t e;
+#if PEA_K4X_TMEM
+    if (grad) {
+        auto kern = t3::cross3d_norm5_tm<TY, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mO, mT, mW, P);
+    } else {
+        auto kern = t3::cross3d_norm5_tm<TY, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mO, mT, mW, P);
+    }
+    return (int)cudaGetLastError();
+#endif
     if (grad) {
         auto kern = t3::cross3d_norm5<TY, true>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
