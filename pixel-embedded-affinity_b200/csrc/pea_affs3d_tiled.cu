@@ -456,8 +456,9 @@ struct alignas(128) StageM {
     float sAm[kC][TY][TX];          // rows y0-27 ..
     float sAp[kC][TY][TX];          // rows y0+27 ..
     float sX[kC][TY][XW];           // cols x0-28 .. x0+59
-    // own target / weight tile, grouped by the part of the slice that consumes it (each group is refilled as soon as
-    // its part is over, like the embedding boxes): [part y/x/z][target, weight][4 channels]
+    // own target / weight tiles, grouped by the part of the slice that consumes them (each group is refilled as soon as
+    // its part is over, like the embedding boxes): [y channels | x channels | x channels of the next 32 columns]
+    // [target, weight][4 channels]; the four z channels come straight from global memory (needed last, requested first)
     float sTW[3][2][4][TY][TX];
 };
 
@@ -469,13 +470,13 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     static_assert(TY <= 16, "four lane quarters x (512 / 128) column groups");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     StageM<TY>& S = *reinterpret_cast<StageM<TY>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    __shared__ uint64_t barY, barX, barZ;
-    __shared__ uint32_t cntY, cntX, cntZ, s_tmem;
+    __shared__ uint64_t barY, barX;
+    __shared__ uint32_t cntY, cntX, s_tmem;
     __shared__ float s_red[12][TY];
 
     constexpr uint32_t kBytesTW = sizeof(S.sTW[0]);
     constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + kBytesTW;
-    constexpr uint32_t kBytesX = sizeof(S.sX) + kBytesTW;
+    constexpr uint32_t kBytesX = sizeof(S.sX) + 2 * kBytesTW;
     constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
     constexpr uint32_t kWarps = TY;
 
@@ -509,21 +510,19 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         mbar_arrive_expect_tx(&barX, kBytesX);
         tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
         issueTW(1, 2, z, &barX);
-    };
-    auto issueZ = [&](int z) {
-        mbar_arrive_expect_tx(&barZ, kBytesTW);
-        issueTW(2, 0, z, &barZ);
+        // the same four x channels of the NEXT 32 columns: target / weight of the pairs anchored at x + s beyond the tile
+        // (TMA wants a 16-byte aligned start coordinate, so a box shifted by s itself is not an option)
+        tma_load_5d(&S.sTW[2][0][0][0][0], &mapT, &barX, x0 + TX, y0, z, 2, b);
+        tma_load_5d(&S.sTW[2][1][0][0][0], &mapW, &barX, x0 + TX, y0, z, 2, b);
     };
 
     if (threadIdx.x == 0) {
         mbar_init(&barY, 1);
         mbar_init(&barX, 1);
-        mbar_init(&barZ, 1);
-        cntY = cntX = cntZ = 0;
+        cntY = cntX = 0;
         mbar_fence_init();
         issueY(0);
         issueX(0);
-        issueZ(0);
     }
     if (ty == 0) {  // one warp allocates the whole Tensor Memory of this SM (one CTA per SM anyway: shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols)
@@ -573,7 +572,7 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     // target / weight of the pairs anchored at the +s neighbours (gather-form backward), straight from global memory
     // (zero when the anchor is outside the volume).  Loaded half a slice ahead: the x values at the start of the y part,
     // the y values of the NEXT slice at the start of the x part.
-    float t2y[4], w2y[4], t2x[4], w2x[4];
+    float t2y[4], w2y[4], tz[4], wz[4];
     auto load_t2y = [&](int z) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -585,27 +584,26 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             w2y[g] = ldg_early(wgt_b + o, v);
         }
     };
-    auto load_t2x = [&](int z) {
+    // own target / weight of the four z channels (0, 3, 6, 9): needed only at the end of the slice, requested at its start
+    auto load_tz = [&](int z) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int s = shift_yx(g);
-            const bool v = live && (x + s < W);
-            const int64_t o = (int64_t)(3 * g + 2) * N + (int64_t)z * HW + s;
-            t2x[g] = ldg_early(tgt_b + o, v);
-            w2x[g] = ldg_early(wgt_b + o, v);
+        for (int j = 0; j < 4; ++j) {
+            const int64_t o = (int64_t)(3 * j) * N + (int64_t)z * HW;
+            tz[j] = ldg_early(tgt_b + o, live);
+            wz[j] = ldg_early(wgt_b + o, live);
         }
     };
     if (GRAD) load_t2y(0);
 
     const float* sTy = &S.sTW[0][0][0][ty][tx];
     const float* sTx = &S.sTW[1][0][0][ty][tx];
-    const float* sTz = &S.sTW[2][0][0][ty][tx];
+    const float* sTn = &S.sTW[2][0][0][ty][tx];  // next 32 columns of the x channels
     constexpr int kW = 4 * CHS_A;  // weight plane of a group = target plane + kW
 
     for (int z = 0; z < D; ++z) {
         const uint32_t par = (uint32_t)(z & 1);
         const int64_t zoff = (int64_t)z * HW;
-        if (GRAD) load_t2x(z);
+        load_tz(z);
 
         f32x2 e[kC2], G[kC2];
         float rp;
@@ -666,8 +664,10 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
                                              vf ? sTx[kW + g * CHS_A] : 0.f, P.gcoef[k], a);
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
             if (GRAD) {
+                // pair anchored at x + s: its target / weight sit in the own tile group, or in the next 32 columns
+                const float* pr = (tx + s < TX) ? sTx + (g * CHS_A + s) : sTn + (g * CHS_A + s - TX);
                 float a2;
-                inplane_pair<true>(&S.sX[0][ty][tx + XPAD + s], CHS_X, e, G, t2x[g], w2x[g], P.gcoef[k], a2);
+                inplane_pair<true>(&S.sX[0][ty][tx + XPAD + s], CHS_X, e, G, pr[0], pr[kW], P.gcoef[k], a2);
             }
         }
         __syncwarp();
@@ -676,7 +676,6 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         // ---------------- z part: pairs (z, z - j); slice z - j comes out of its Tensor-Memory slot, its updated
         // gradient accumulator goes back (j < 4) or -- all pairs of slice z - 4 seen -- straight through the
         // normalisation backward to global memory
-        mbar_wait(&barZ, par);
 #pragma unroll
         for (int j = 1; j <= 4; ++j) {
             const int k = 3 * (j - 1);
@@ -692,8 +691,8 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
                     d1 = fma2(e[i + 1], ej[i + 1], d1);
                 }
                 const float a = hsum2(d0, d1);
-                const float diff = a - sTz[(j - 1) * CHS_A];
-                const float wv = sTz[kW + (j - 1) * CHS_A];  // 0 outside the volume
+                const float diff = a - tz[j - 1];
+                const float wv = wz[j - 1];  // 0 on dead lanes
                 lossacc[k] += wv * diff * diff;
                 if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
                 if (GRAD) {
@@ -711,8 +710,6 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
                 affs_b[(int64_t)k * N + zoff] = 0.f;
             }
         }
-        __syncwarp();
-        if (tx == 0 && arrive_count(&cntZ) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueZ(z + 1);
         // this slice takes the slot of slice z - 4 (retired above)
         {
             const uint32_t slot = tq + ((uint32_t)(z & 3) << 5);
