@@ -459,14 +459,16 @@ struct alignas(128) StageM {
     // own target / weight tiles, grouped by the part of the slice that consumes them (each group is refilled as soon as
     // its part is over, like the embedding boxes): [y channels | x channels | x channels of the next 32 columns]
     // [target, weight][4 channels]; the four z channels come straight from global memory (needed last, requested first)
-    float sTW[3][2][4][TY][TX];
+    float sTW[4][2][4][TY][TX];   // [3]: y channels, the TY rows below the tile (anchors y + 1 / 3 / 9 beyond it)
+    float sFar[2][TY][TX];        // channel 10 (y shift 27), rows y0 + 27 ..: [target, weight]
 };
 
 template <int TY, bool GRAD>
 __global__ void __launch_bounds__(TY * 32, 1)
 fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
                  const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT,
-                 const __grid_constant__ CUtensorMap mapW, const Params P) {
+                 const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapT1,
+                 const __grid_constant__ CUtensorMap mapW1, const Params P) {
     static_assert(TY <= 16, "four lane quarters x (512 / 128) column groups");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     StageM<TY>& S = *reinterpret_cast<StageM<TY>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
@@ -475,7 +477,7 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     __shared__ float s_red[12][TY];
 
     constexpr uint32_t kBytesTW = sizeof(S.sTW[0]);
-    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + kBytesTW;
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + 2 * kBytesTW + sizeof(S.sFar);
     constexpr uint32_t kBytesX = sizeof(S.sX) + 2 * kBytesTW;
     constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
     constexpr uint32_t kWarps = TY;
@@ -503,6 +505,11 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         mbar_arrive_expect_tx(&barY, kBytesY);
         tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
         issueTW(0, 1, z, &barY);
+        // rows below the tile for the pairs anchored at y + s (zero fill below the volume == pair dropped)
+        tma_load_5d(&S.sTW[3][0][0][0][0], &mapT, &barY, x0, y0 + TY, z, 1, b);
+        tma_load_5d(&S.sTW[3][1][0][0][0], &mapW, &barY, x0, y0 + TY, z, 1, b);
+        tma_load_5d(&S.sFar[0][0][0], &mapT1, &barY, x0, y0 + FAR, z, 10, b);
+        tma_load_5d(&S.sFar[1][0][0], &mapW1, &barY, x0, y0 + FAR, z, 10, b);
         tma_load_5d(&S.sAm[0][0][0], &mapA, &barY, x0, y0 - FAR, z, 0, b);
         tma_load_5d(&S.sAp[0][0][0], &mapA, &barY, x0, y0 + FAR, z, 0, b);
     };
@@ -569,22 +576,8 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         }
     };
 
-    // target / weight of the pairs anchored at the +s neighbours (gather-form backward), straight from global memory
-    // (zero when the anchor is outside the volume).  Loaded half a slice ahead: the x values at the start of the y part,
-    // the y values of the NEXT slice at the start of the x part.
-    float t2y[4], w2y[4], tz[4], wz[4];
-    auto load_t2y = [&](int z) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int s = shift_yx(g);
-            if (ty + s < TY) continue;  // warp-uniform: the anchor row lies in this CTA's own tile -> shared memory below
-            const bool v = live && (y + s < H);
-            const int64_t o = (int64_t)(3 * g + 1) * N + (int64_t)z * HW + (int64_t)s * W;
-            t2y[g] = ldg_early(tgt_b + o, v);
-            w2y[g] = ldg_early(wgt_b + o, v);
-        }
-    };
     // own target / weight of the four z channels (0, 3, 6, 9): needed only at the end of the slice, requested at its start
+    float tz[4], wz[4];
     auto load_tz = [&](int z) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -593,11 +586,11 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             wz[j] = ldg_early(wgt_b + o, live);
         }
     };
-    if (GRAD) load_t2y(0);
 
     const float* sTy = &S.sTW[0][0][0][ty][tx];
     const float* sTx = &S.sTW[1][0][0][ty][tx];
     const float* sTn = &S.sTW[2][0][0][ty][tx];  // next 32 columns of the x channels
+    const float* sTb = &S.sTW[3][0][0][ty][tx];  // next TY rows of the y channels
     constexpr int kW = 4 * CHS_A;  // weight plane of a group = target plane + kW
 
     for (int z = 0; z < D; ++z) {
@@ -639,11 +632,13 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             lossacc[k] += inplane_pair<GRAD>(nb_m, chs, e, G, sTy[g * CHS_A], vf ? sTy[kW + g * CHS_A] : 0.f, P.gcoef[k], a);
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;  // partner outside the volume: zero fill, a == 0
             if (GRAD) {
-                // pair anchored at y + s: its target / weight sit in the own tile group when that row belongs to this CTA
-                // (rows beyond the image are zero fill there), else they were fetched from global half a slice ago
-                const bool own_tile = ty + s < TY;  // warp-uniform
-                const float t_r = own_tile ? sTy[g * CHS_A + s * TX] : t2y[g];
-                const float w_r = own_tile ? sTy[kW + g * CHS_A + s * TX] : w2y[g];
+                // pair anchored at y + s: its target / weight sit in the own tile group when that row belongs to this CTA,
+                // else in the group of the TY rows below; shift 27 always lands in the far box (rows beyond the image
+                // are zero fill everywhere == pair dropped).  Warp-uniform choice.
+                const float* pr = (g == 3) ? &S.sFar[0][ty][tx]
+                                           : (ty + s < TY ? sTy + (g * CHS_A + s * TX) : sTb + (g * CHS_A + (s - TY) * TX));
+                const float t_r = pr[0];
+                const float w_r = pr[(g == 3) ? CHS_A : kW];
                 float a2;
                 inplane_pair<true>(nb_p, chs, e, G, t_r, w_r, P.gcoef[k], a2);
             }
@@ -652,7 +647,6 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueY(z + 1);
 
         // ---------------- x part
-        if (GRAD && z + 1 < D) load_t2y(z + 1);
         mbar_wait(&barX, par);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -1524,6 +1518,9 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
     // every third channel from the start coordinate: 4 planes (c0, c0 + 3, c0 + 6, c0 + 9) per copy
     if ((rc = encode_volume_map(&mT, target, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 10, 0, 3))) return rc;
     if ((rc = encode_volume_map(&mW, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 10, 0, 3))) return rc;
+    CUtensorMap mT1, mW1;
+    if ((rc = encode_volume_map(&mT1, target, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 1))) return rc;
+    if ((rc = encode_volume_map(&mW1, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 1))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
     P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
@@ -1534,11 +1531,11 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
     if (grad) {
         auto kern = t3::fused3d_norm5_tm<TY, true>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, mT1, mW1, P);
     } else {
         auto kern = t3::fused3d_norm5_tm<TY, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, P);
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, mT1, mW1, P);
     }
     return (int)cudaGetLastError();
 #endif
