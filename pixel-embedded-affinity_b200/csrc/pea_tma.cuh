@@ -18,18 +18,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// try_wait blocks in hardware until the phase completes or the time hint expires: with a generous hint a waiting warp
+// sleeps instead of spinning through SYNCS + BRA pairs (measured: 7 % of the fused 3-D kernel's instruction stream)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "PEA_MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra PEA_MBAR_DONE_%=;\n\t"
+        "bra PEA_MBAR_WAIT_%=;\n"
+        "PEA_MBAR_DONE_%=:\n\t}"
+        ::"r"(addr), "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 
 // global (5-D tensor map) -> shared, completion counted in bytes on `bar`
