@@ -392,8 +392,8 @@ fused3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
 // uses it: tcgen05.st / tcgen05.ld with the 32x32b shape move 16 or 32 consecutive columns of ONE lane to / from the
 // registers of ONE thread.  Here the four older ring slots live in TMEM (4 x 32 columns per thread, slot of slice z =
 // z & 3, addressed at run time: no ring shifting at all), which brings the kernel to <= 168 registers and lets a
-// CTA of 12 warps (12 x 32 voxel columns) run per SM.  Own target / weight values come straight from global memory
-// (coalesced 128-byte rows, read once), so shared memory holds only the embedding boxes (178 KB).
+// CTA of 12 warps (12 x 32 voxel columns) run per SM.  Shared memory (230 KB) holds the embedding boxes (178 KB) and the
+// single-buffered target / weight groups; only the z channels' target / weight are per-thread loads.
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const f32x2 (&v)[kC2]) {
     float r[16];
 #pragma unroll
@@ -456,11 +456,12 @@ struct alignas(128) StageM {
     float sAm[kC][TY][TX];          // rows y0-27 ..
     float sAp[kC][TY][TX];          // rows y0+27 ..
     float sX[kC][TY][XW];           // cols x0-28 .. x0+59
-    // own target / weight tiles, grouped by the part of the slice that consumes them (each group is refilled as soon as
-    // its part is over, like the embedding boxes): [y channels | x channels | x channels of the next 32 columns]
-    // [target, weight][4 channels]; the four z channels come straight from global memory (needed last, requested first)
-    float sTW[4][2][4][TY][TX];   // [3]: y channels, the TY rows below the tile (anchors y + 1 / 3 / 9 beyond it)
-    float sFar[2][TY][TX];        // channel 10 (y shift 27), rows y0 + 27 ..: [target, weight]
+    // target / weight tiles [group][target, weight][4 channels], each group refilled as soon as the part of the slice that
+    // consumes it is over (like the embedding boxes).  Group 0: y channels (1, 4, 7, 10) of the tile; 1: x channels
+    // (2, 5, 8, 11) of the tile; 2: x channels of the NEXT 32 columns and 3: y channels of the TY rows BELOW the tile
+    // (pairs anchored at p + s beyond the tile, gather-form backward).  The z channels come straight from global memory.
+    float sTW[4][2][4][TY][TX];
+    float sFar[2][TY][TX];  // channel 10 (y shift 27), rows y0 + 27 ..: [target, weight]
 };
 
 template <int TY, bool GRAD>
@@ -477,8 +478,8 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     __shared__ float s_red[12][TY];
 
     constexpr uint32_t kBytesTW = sizeof(S.sTW[0]);
-    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + 2 * kBytesTW + sizeof(S.sFar);
-    constexpr uint32_t kBytesX = sizeof(S.sX) + 2 * kBytesTW;
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + kBytesTW + (GRAD ? kBytesTW + sizeof(S.sFar) : 0);
+    constexpr uint32_t kBytesX = sizeof(S.sX) + kBytesTW + (GRAD ? kBytesTW : 0);
     constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
     constexpr uint32_t kWarps = TY;
 
@@ -505,11 +506,12 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         mbar_arrive_expect_tx(&barY, kBytesY);
         tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
         issueTW(0, 1, z, &barY);
-        // rows below the tile for the pairs anchored at y + s (zero fill below the volume == pair dropped)
-        tma_load_5d(&S.sTW[3][0][0][0][0], &mapT, &barY, x0, y0 + TY, z, 1, b);
-        tma_load_5d(&S.sTW[3][1][0][0][0], &mapW, &barY, x0, y0 + TY, z, 1, b);
-        tma_load_5d(&S.sFar[0][0][0], &mapT1, &barY, x0, y0 + FAR, z, 10, b);
-        tma_load_5d(&S.sFar[1][0][0], &mapW1, &barY, x0, y0 + FAR, z, 10, b);
+        if (GRAD) {  // rows below the tile for the pairs anchored at y + s (zero fill below the volume == pair dropped)
+            tma_load_5d(&S.sTW[3][0][0][0][0], &mapT, &barY, x0, y0 + TY, z, 1, b);
+            tma_load_5d(&S.sTW[3][1][0][0][0], &mapW, &barY, x0, y0 + TY, z, 1, b);
+            tma_load_5d(&S.sFar[0][0][0], &mapT1, &barY, x0, y0 + FAR, z, 10, b);
+            tma_load_5d(&S.sFar[1][0][0], &mapW1, &barY, x0, y0 + FAR, z, 10, b);
+        }
         tma_load_5d(&S.sAm[0][0][0], &mapA, &barY, x0, y0 - FAR, z, 0, b);
         tma_load_5d(&S.sAp[0][0][0], &mapA, &barY, x0, y0 + FAR, z, 0, b);
     };
@@ -517,10 +519,12 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         mbar_arrive_expect_tx(&barX, kBytesX);
         tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
         issueTW(1, 2, z, &barX);
-        // the same four x channels of the NEXT 32 columns: target / weight of the pairs anchored at x + s beyond the tile
-        // (TMA wants a 16-byte aligned start coordinate, so a box shifted by s itself is not an option)
-        tma_load_5d(&S.sTW[2][0][0][0][0], &mapT, &barX, x0 + TX, y0, z, 2, b);
-        tma_load_5d(&S.sTW[2][1][0][0][0], &mapW, &barX, x0 + TX, y0, z, 2, b);
+        if (GRAD) {
+            // the same four x channels of the NEXT 32 columns: target / weight of the pairs anchored at x + s beyond the
+            // tile (TMA wants a 16-byte aligned start coordinate, so a box shifted by s itself is not an option)
+            tma_load_5d(&S.sTW[2][0][0][0][0], &mapT, &barX, x0 + TX, y0, z, 2, b);
+            tma_load_5d(&S.sTW[2][1][0][0][0], &mapW, &barX, x0 + TX, y0, z, 2, b);
+        }
     };
 
     if (threadIdx.x == 0) {
