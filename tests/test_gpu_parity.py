@@ -386,6 +386,59 @@ def test_backward_scaling_retain_graph_and_no_grad(P, O):
     assert float(l3) == float(l2)
 
 
+def test_3d_kernels_reproducible_graph_capturable_and_stream_safe(P, O):
+    """The Tensor-Memory kernels: (a) bit-identical results run to run (fixed-order loss reduction, no atomics on
+    floats), (b) capturable in a CUDA graph, (c) two streams may run them at the same time (each CTA allocates the
+    SM's Tensor Memory; shared memory keeps two of them off one SM)."""
+    emb, ema, tgt, wgt = _inputs_3d(O, 2, 16, 9, 52, 68, 12, 51)
+    T, Wt = dev(tgt), dev(wgt)
+
+    def run(e_np, partner=None):
+        e = dev(e_np, True)
+        if partner is None:
+            l, a = P.embedding_loss_norm5(e, T, Wt, P.WeightedMSE())
+        else:
+            l, a = P.ema_embedding_loss_norm5(e, dev(partner), T, Wt, P.WeightedMSE())
+        l.backward()
+        return l.detach().clone(), a.clone(), e.grad.clone()
+
+    first, second = run(emb), run(emb)
+    for x, y in zip(first, second):
+        assert torch.equal(x, y), "self loss: run-to-run bits differ"
+    fx, sx = run(emb, ema), run(emb, ema)
+    for x, y in zip(fx, sx):
+        assert torch.equal(x, y), "two-view loss: run-to-run bits differ"
+    # (b) graph capture and replay
+    e = dev(emb, True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            l, _ = P.embedding_loss_norm5(e, T, Wt, P.WeightedMSE())
+            l.backward()
+            e.grad = None
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        lg, ag = P.embedding_loss_norm5(e, T, Wt, P.WeightedMSE())
+        lg.backward()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(lg.detach(), first[0]) and torch.equal(ag, first[1]) and torch.equal(e.grad, first[2])
+    # (c) the self kernel and the two-view kernel on two streams at once
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        r1 = run(emb)
+    with torch.cuda.stream(s2):
+        r2 = run(emb, ema)
+    torch.cuda.synchronize()
+    for x, y in zip(r1, first):
+        assert torch.equal(x, y)
+    for x, y in zip(r2, fx):
+        assert torch.equal(x, y)
+
+
 def test_half_precision_embedding_inputs(P, O):
     """bf16 / fp16 embeddings (autocast backbones): the path runs in fp32 on the upcast values -- loss and affinities
     equal the fp32 call on those values exactly; the gradient returns in the input dtype, so it matches the fp32
