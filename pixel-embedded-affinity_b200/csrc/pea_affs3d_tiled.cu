@@ -779,7 +779,7 @@ struct ParamsF {
 };
 
 template <int TY>
-__global__ void __launch_bounds__(TY * 32, 2)
+__global__ void __launch_bounds__(TY * 32, (TY <= 8) ? 2 : 1)
 fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
             const __grid_constant__ CUtensorMap mapX, const ParamsF P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1558,7 +1558,10 @@ bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool
 
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
                        const float* halo, int halo_n, int64_t halo_plane, cudaStream_t st) {
-    constexpr int TY = 8;
+#ifndef PEA_TILE_Y3D_FWD
+#define PEA_TILE_Y3D_FWD 8
+#endif
+    constexpr int TY = PEA_TILE_Y3D_FWD;
     CUtensorMap mY, mA, mX;
     int rc;
     if ((rc = encode_volume_map(&mY, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY + t3::HY, 1, 16, emb_plane))) return rc;
