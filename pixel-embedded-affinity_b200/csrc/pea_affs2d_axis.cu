@@ -461,7 +461,10 @@ static bool plan_axis(const OffsetTable& tab, int H, int W, int wrap, PlanAxis& 
     }
     if (P > 28) return false;
     p.pmax = P <= 12 ? 12 : 28;
-    p.ty = P <= 12 ? 8 : 12;
+#ifndef PEA_AXIS_TY
+#define PEA_AXIS_TY 8
+#endif
+    p.ty = P <= 12 ? PEA_AXIS_TY : 12;
     // the hand fill of edge CTAs maps coordinates through wrap3 (-n <= v < 4n); TMA needs 16-byte row pitch
     if (W % 4 != 0 || H < 32 || W < 64) return false;
     if ((int64_t)(tab.K > 16 ? tab.K : 16) * H * W >= ((int64_t)1 << 31)) return false;
@@ -540,7 +543,7 @@ int launch_axis2d(const float* emb, const float* partner, const Dims& d, const O
     for (int i = pl.ny + pl.nx; i < a2::kMaxK; ++i) { P.chan[i] = 0; P.shift[i] = 0; P.gcoef[i] = 0.f; }
     const int grid = d.B * ((d.H + pl.ty - 1) / pl.ty) * ((d.W + a2::TX - 1) / a2::TX);
     const float* src = partner ? partner : emb;
-    if (pl.pmax == 12) return launch_axis_p<8, 12>(src, d, P, partner != nullptr, mask_dtype, grid, st);
+    if (pl.pmax == 12) return launch_axis_p<PEA_AXIS_TY, 12>(src, d, P, partner != nullptr, mask_dtype, grid, st);
     return launch_axis_p<12, 28>(src, d, P, partner != nullptr, mask_dtype, grid, st);
 }
 
