@@ -13,6 +13,7 @@
 //   * runtime offset table, two compact loops (y offsets, x offsets): per offset one forward pair and -- self variant
 //     with gradient -- one reverse pair (gather-form backward), target / weight / mask fetched two offsets ahead;
 //   * per-offset loss terms -> shared scratch -> fixed-order CTA sum -> one row of partials per CTA.
+#include <cstdlib>
 #include "pea_common.cuh"
 #include "pea_tma.cuh"
 
@@ -434,6 +435,322 @@ fused2d_axis(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ C
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent flavour (the default): the same tile body, but a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x,
+// ... and the TMA boxes of its NEXT tile are requested as soon as the last warp has finished reading the current ones
+// (y-column box after the last y offset, x-row box after the last x offset: release / acquire counters as in the 3-D
+// kernels, no CTA barrier in the loop).  The one-tile kernel above waits ~2 us for its boxes at the start of every
+// 8 us CTA; here that latency hides behind the other half of the previous tile, the gradient stores and the next
+// tile's first target / weight / mask fetches.  Tiles on the image edge under the circular border are still filled by
+// hand (two CTA barriers around the fill).  Loss terms accumulate per thread and offset in shared memory over all the
+// CTA's tiles and are summed in a fixed order at the end: gridDim.x rows of partials.
+__device__ __forceinline__ uint32_t arrive_count(uint32_t* cnt) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+    return old;
+}
+
+template <int TY, int PMAX, bool CROSS, int MASK, bool GRAD>
+__global__ void __launch_bounds__(TY * 32, (TY <= 8) ? 2 : 1)
+fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, const Params P,
+               const int tiles_x, const int tiles_y, const int n_tiles) {
+    using G_ = Geo<TY, PMAX>;
+    constexpr int PX = G_::PX, YR = G_::YR, XW = G_::XW, CHS_Y = G_::CHS_Y, CHS_X = G_::CHS_X, NT = G_::NT;
+    constexpr uint32_t kWarps = TY;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Stage<TY, PMAX>& S = *reinterpret_cast<Stage<TY, PMAX>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    __shared__ uint64_t barY, barX;
+    __shared__ uint32_t cntY, cntX;
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int H = P.H, W = P.W, K = P.K;
+    const bool wrap = P.wrap != 0;
+    const uint32_t Nu = (uint32_t)(H * W);
+    const int ny = P.ny, ntot = P.ny + P.nx;
+
+    auto tile_origin = [&](int t, int& b, int& y0, int& x0) {
+        const int r = t / tiles_x;
+        x0 = (t - r * tiles_x) * TX;
+        b = r / tiles_y;
+        y0 = (r - b * tiles_y) * TY;
+    };
+    auto tile_inner = [&](int y0, int x0) { return y0 >= PMAX && y0 + TY + PMAX <= H && x0 >= PX && x0 + TX + PX <= W; };
+    auto issueY = [&](int b, int y0, int x0) {
+        mbar_arrive_expect_tx(&barY, (uint32_t)sizeof(S.sY));
+        tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - PMAX, 0, 0, b);
+    };
+    auto issueX = [&](int b, int y0, int x0) {
+        mbar_arrive_expect_tx(&barX, (uint32_t)sizeof(S.sX));
+        tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - PX, y0, 0, 0, b);
+    };
+
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) S.sL[k][threadIdx.x] = 0.f;  // own column only: no barrier needed before the += below
+    int t = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&barY, 1);
+        mbar_init(&barX, 1);
+        cntY = cntX = 0;
+        mbar_fence_init();
+        int b, y0, x0;
+        tile_origin(t, b, y0, x0);
+        if (!(wrap && !tile_inner(y0, x0))) {
+            issueY(b, y0, x0);
+            issueX(b, y0, x0);
+        }
+    }
+    __syncthreads();
+    uint32_t phY = 0, phX = 0, it = 0;
+
+    for (; t < n_tiles; t += (int)gridDim.x, ++it) {
+        int b, y0, x0;
+        tile_origin(t, b, y0, x0);
+        int bn = 0, y0n = 0, x0n = 0;
+        bool next_tma = false;
+        if (t + (int)gridDim.x < n_tiles) {
+            tile_origin(t + (int)gridDim.x, bn, y0n, x0n);
+            next_tma = !(wrap && !tile_inner(y0n, x0n));
+        }
+        const int x = x0 + tx, y = y0 + ty;
+        const bool live = (x < W) && (y < H);
+        const uint32_t pix = (uint32_t)((live ? y : 0) * W + (live ? x : 0));
+        const bool inner = tile_inner(y0, x0);
+        const bool manual = wrap && !inner;
+        const uint32_t goal = kWarps * (it + 1) - 1;
+
+        const float* tgt_b = P.target + (int64_t)b * K * Nu + pix;
+        const float* wgt_b = P.weight + (int64_t)b * K * Nu + pix;
+        const uint8_t* m8_b = MASK == PEA_MASK_U8 ? reinterpret_cast<const uint8_t*>(P.mask) + (int64_t)b * K * Nu + pix : nullptr;
+        const float* mf_b = MASK == PEA_MASK_F32 ? reinterpret_cast<const float*>(P.mask) + (int64_t)b * K * Nu + pix : nullptr;
+
+        auto fetch_inner = [&](int i) -> KV {
+            KV v = {0.f, 0.f, 0.f, 0.f, 0u, 0u};
+            if (i >= ntot) return v;
+            const int s = P.shift[i];
+            const uint32_t koff = (uint32_t)P.chan[i] * Nu;
+            const int64_t back = i >= ny ? (int64_t)s : (int64_t)s * W;  // p - o in elements
+            v.t = ldg_f32_now(tgt_b + koff);
+            v.w = ldg_f32_now(wgt_b + koff);
+            if (MASK == PEA_MASK_U8) v.m = ldg_u8_now(m8_b + koff);
+            if (MASK == PEA_MASK_F32) v.m = __float_as_uint(ldg_f32_now(mf_b + koff));
+            if (GRAD && !CROSS) {
+                v.t2 = ldg_f32_now(tgt_b + koff - back);
+                v.w2 = ldg_f32_now(wgt_b + koff - back);
+                if (MASK == PEA_MASK_U8) v.m2 = ldg_u8_now(m8_b + koff - back);
+                if (MASK == PEA_MASK_F32) v.m2 = __float_as_uint(ldg_f32_now(mf_b + koff - back));
+            }
+            return v;
+        };
+        auto fetch_edge = [&](int i) -> KV {
+            KV v = {0.f, 0.f, 0.f, 0.f, 0u, 0u};
+            if (i >= ntot) return v;
+            const bool isx = i >= ny;
+            const int s = P.shift[i];
+            const uint32_t koff = (uint32_t)P.chan[i] * Nu;
+            bool vf = live;
+            if (!wrap) vf = vf && (isx ? (unsigned)(x + s) < (unsigned)W : (unsigned)(y + s) < (unsigned)H);
+            v.t = ldg_f32_early(tgt_b + koff, vf);
+            v.w = ldg_f32_early(wgt_b + koff, vf);
+            if (MASK == PEA_MASK_U8) v.m = ldg_u8_early(m8_b + koff, vf);
+            if (MASK == PEA_MASK_F32) v.m = __float_as_uint(ldg_f32_early(mf_b + koff, vf));
+            if (GRAD && !CROSS) {
+                int qy = y, qx = x;
+                bool vr = live;
+                if (isx) {
+                    qx = x - s;
+                    if (wrap) qx = wrap1(qx, W);
+                    else vr = vr && (unsigned)qx < (unsigned)W;
+                } else {
+                    qy = y - s;
+                    if (wrap) qy = wrap1(qy, H);
+                    else vr = vr && (unsigned)qy < (unsigned)H;
+                }
+                const int64_t i2 = (int64_t)koff + (vr ? (int64_t)(qy * W + qx) - (int64_t)pix : 0);
+                v.t2 = ldg_f32_early(tgt_b + i2, vr);
+                v.w2 = ldg_f32_early(wgt_b + i2, vr);
+                if (MASK == PEA_MASK_U8) v.m2 = ldg_u8_early(m8_b + i2, vr);
+                if (MASK == PEA_MASK_F32) v.m2 = __float_as_uint(ldg_f32_early(mf_b + i2, vr));
+            }
+            return v;
+        };
+
+        if (manual) {
+            __syncthreads();  // every warp has left the previous tile: the boxes may be overwritten
+            const float* src = (CROSS ? P.par : P.emb) + (int64_t)b * kC * Nu;
+            float* sYf = &S.sY[0][0][0];
+            float* sXf = &S.sX[0][0][0];
+            for (int idx = threadIdx.x; idx < YR * TX; idx += 2 * NT) {
+                const int idx2 = idx + NT;
+                const bool two = idx2 < YR * TX;
+                const int row = idx >> 5, col = idx & 31, row2 = (two ? idx2 : idx) >> 5;
+                const uint32_t gx = (uint32_t)wrap3(x0 + col, W);
+                const uint32_t o = (uint32_t)(wrap3(y0 - PMAX + row, H) * W) + gx;
+                const uint32_t o2 = (uint32_t)(wrap3(y0 - PMAX + row2, H) * W) + gx;
+                float v[kC], v2[kC];
+#pragma unroll
+                for (int c = 0; c < kC; ++c) {
+                    v[c] = __ldg(src + (o + (uint32_t)c * Nu));
+                    v2[c] = __ldg(src + (o2 + (uint32_t)c * Nu));
+                }
+#pragma unroll
+                for (int c = 0; c < kC; ++c) {
+                    sYf[c * CHS_Y + idx] = v[c];
+                    if (two) sYf[c * CHS_Y + idx2] = v2[c];
+                }
+            }
+            for (int idx = threadIdx.x; idx < TY * XW; idx += 2 * NT) {
+                const int idx2 = idx + NT;
+                const bool two = idx2 < TY * XW;
+                const int row = idx / XW, col = idx - row * XW;
+                const int j2 = two ? idx2 : idx, row2 = j2 / XW, col2 = j2 - row2 * XW;
+                const uint32_t o = (uint32_t)(wrap3(y0 + row, H) * W + wrap3(x0 - PX + col, W));
+                const uint32_t o2 = (uint32_t)(wrap3(y0 + row2, H) * W + wrap3(x0 - PX + col2, W));
+                float v[kC], v2[kC];
+#pragma unroll
+                for (int c = 0; c < kC; ++c) {
+                    v[c] = __ldg(src + (o + (uint32_t)c * Nu));
+                    v2[c] = __ldg(src + (o2 + (uint32_t)c * Nu));
+                }
+#pragma unroll
+                for (int c = 0; c < kC; ++c) {
+                    sXf[c * CHS_X + idx] = v[c];
+                    if (two) sXf[c * CHS_X + idx2] = v2[c];
+                }
+            }
+        }
+        const float* ownY = &S.sY[0][ty + PMAX][tx];
+        const float* ownX = &S.sX[0][ty][tx + PX];
+        float* affs_b = P.affs ? P.affs + (int64_t)b * K * Nu + pix : nullptr;
+        f32x2 e[kC2], G[kC2];
+        float rp = 0.f;
+
+        // the last warp to leave a box requests the next tile's copy of it
+        auto releaseY = [&]() {
+            __syncwarp();
+            if (tx == 0 && arrive_count(&cntY) == goal && next_tma) issueY(bn, y0n, x0n);
+        };
+        auto releaseX = [&]() {
+            __syncwarp();
+            if (tx == 0 && arrive_count(&cntX) == goal && next_tma) issueX(bn, y0n, x0n);
+        };
+
+        auto run = [&](auto inner_c) {
+            constexpr bool INNER = decltype(inner_c)::value;
+            auto fetch = [&](int i) -> KV { return INNER ? fetch_inner(i) : fetch_edge(i); };
+            KV kv0 = fetch(0), kv1 = fetch(1), kv2;
+            if (manual) __syncthreads();  // hand-filled boxes complete
+            else mbar_wait(&barY, phY & 1u);
+            if (CROSS) {
+                const float* eb = P.emb + (int64_t)b * kC * Nu;
+#pragma unroll
+                for (int i = 0; i < kC2; ++i)
+                    e[i] = pack2(live ? __ldg(eb + (pix + (uint32_t)(2 * i) * Nu)) : 0.f,
+                                 live ? __ldg(eb + (pix + (uint32_t)(2 * i + 1) * Nu)) : 0.f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kC2; ++i) e[i] = pack2(ownY[(2 * i) * CHS_Y], ownY[(2 * i + 1) * CHS_Y]);
+            }
+            {
+                f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+                for (int i = 0; i < kC2; i += 2) {
+                    s0 = fma2(e[i], e[i], s0);
+                    s1 = fma2(e[i + 1], e[i + 1], s1);
+                }
+                rp = inv_norm(hsum2(s0, s1));
+                const f32x2 rp2 = pack2(rp, rp);
+#pragma unroll
+                for (int i = 0; i < kC2; ++i) {
+                    e[i] = mul2(e[i], rp2);
+                    G[i] = 0ull;
+                }
+            }
+            auto body = [&](int i, const KV& cur) {
+                const int c = P.chan[i], s = P.shift[i];
+                const float gco = P.gcoef[i];
+                float a, lt;
+                if (i >= ny) {  // CTA-uniform
+                    lt = pair<CHS_X, GRAD>(ownX + s, e, G, cur.t, cur.w * mask_sq<MASK>(cur.m), gco, a);
+                    if (GRAD && !CROSS) {
+                        float a2;
+                        pair<CHS_X, true>(ownX - s, e, G, cur.t2, cur.w2 * mask_sq<MASK>(cur.m2), gco, a2);
+                    }
+                } else {
+                    lt = pair<CHS_Y, GRAD>(ownY + s * TX, e, G, cur.t, cur.w * mask_sq<MASK>(cur.m), gco, a);
+                    if (GRAD && !CROSS) {
+                        float a2;
+                        pair<CHS_Y, true>(ownY - s * TX, e, G, cur.t2, cur.w2 * mask_sq<MASK>(cur.m2), gco, a2);
+                    }
+                }
+                if (affs_b && (INNER || live)) affs_b[(uint32_t)c * Nu] = a;
+                S.sL[c][threadIdx.x] += lt;
+            };
+            bool xready = manual, yfree = false;
+#pragma unroll 1
+            for (int i = 0; i < ntot; i += 3) {
+                if (!yfree && i >= ny) {  // every y offset done: the y-column box is free
+                    releaseY();
+                    yfree = true;
+                }
+                if (!xready && i + 2 >= ny) {
+                    mbar_wait(&barX, phX & 1u);
+                    xready = true;
+                }
+                kv2 = fetch(i + 2);
+                body(i, kv0);
+                if (i + 1 < ntot) {
+                    kv0 = fetch(i + 3);
+                    body(i + 1, kv1);
+                }
+                if (i + 2 < ntot) {
+                    kv1 = fetch(i + 4);
+                    body(i + 2, kv2);
+                }
+            }
+            if (!yfree) releaseY();
+            if (!xready) mbar_wait(&barX, phX & 1u);  // (no x offsets) consume the phase all the same
+            releaseX();
+        };
+        if (inner) run(TrueT{});
+        else run(FalseT{});
+        if (!manual) {
+            ++phY;
+            ++phX;
+        }
+
+        // ---- gradient back through the normalisation
+        if (GRAD && live) {
+            f32x2 p0 = 0ull, p1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < kC2; i += 2) {
+                p0 = fma2(e[i], G[i], p0);
+                p1 = fma2(e[i + 1], G[i + 1], p1);
+            }
+            float eg = hsum2(p0, p1);
+            if (!(rp < 1e12f)) eg = 0.f;
+            const f32x2 neg = pack2(-eg, -eg), r2 = pack2(rp, rp);
+            float* gb = P.grad + (int64_t)b * kC * Nu + pix;
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) {
+                float lo, hi;
+                unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
+                gb[(uint32_t)(2 * i) * Nu] = lo;
+                gb[(uint32_t)(2 * i + 1) * Nu] = hi;
+            }
+        }
+    }
+
+    // ---- loss partials: fixed-order CTA sum per channel
+    __syncthreads();
+    for (int k = ty; k < K; k += TY) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < TY; ++i) v += S.sL[k][i * 32 + tx];
+        v = warp_sum(v);
+        if (tx == 0) P.partials[(int64_t)blockIdx.x * K + k] = v;
+    }
+}
+
 }  // namespace a2
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -482,10 +799,30 @@ bool axis2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wra
     return plan_axis(tab, H, W, wrap, p);
 }
 
+#ifndef PEA_AXIS_PERSIST
+#define PEA_AXIS_PERSIST 1  // 0: one CTA per tile (fused2d_axis), for A/B runs
+#endif
+
+// CTAs of the persistent kernel: every SM's resident set (2 CTAs of 8 warps, or 1 of 12), never more than tiles
+static int persistent_grid(int n_tiles, int ty) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 148;
+    int g = sms * (ty <= 8 ? 2 : 1);
+    // test knob: a small grid makes every CTA walk many tiles even on small images (read per call, no state kept)
+    if (const char* cap = getenv("PEA_AXIS_MAX_CTAS")) {
+        const int c = atoi(cap);
+        if (c > 0 && c < g) g = c;
+    }
+    return n_tiles < g ? n_tiles : g;
+}
+
+// rows of loss partials the kernel writes
 int axis2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap) {
     PlanAxis p;
     if (!plan_axis(tab, H, W, wrap, p)) return 0;
-    return B * ((H + p.ty - 1) / p.ty) * ((W + a2::TX - 1) / a2::TX);
+    const int n_tiles = B * ((H + p.ty - 1) / p.ty) * ((W + a2::TX - 1) / a2::TX);
+    return PEA_AXIS_PERSIST ? persistent_grid(n_tiles, p.ty) : n_tiles;
 }
 
 template <int TY, int PMAX, bool CROSS, int MASK>
@@ -493,6 +830,22 @@ static int launch_axis_g(const CUtensorMap& mY, const CUtensorMap& mX, const a2:
     const dim3 grid((unsigned)((P.W + a2::TX - 1) / a2::TX), (unsigned)((P.H + TY - 1) / TY), (unsigned)P.B);
     const size_t smem = sizeof(a2::Stage<TY, PMAX>) + 128;
     cudaError_t e;
+#if PEA_AXIS_PERSIST
+    {
+        const int tiles_x = (int)grid.x, tiles_y = (int)grid.y, n_tiles = tiles_x * tiles_y * P.B;
+        const int g = persistent_grid(n_tiles, TY);
+        if (P.grad) {
+            auto kern = a2::fused2d_axis_p<TY, PMAX, CROSS, MASK, true>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+            kern<<<g, TY * 32, smem, st>>>(mY, mX, P, tiles_x, tiles_y, n_tiles);
+        } else {
+            auto kern = a2::fused2d_axis_p<TY, PMAX, CROSS, MASK, false>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+            kern<<<g, TY * 32, smem, st>>>(mY, mX, P, tiles_x, tiles_y, n_tiles);
+        }
+        return (int)cudaGetLastError();
+    }
+#endif
     if (P.grad) {
         auto kern = a2::fused2d_axis<TY, PMAX, CROSS, MASK, true>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;

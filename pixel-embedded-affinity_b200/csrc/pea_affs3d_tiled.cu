@@ -84,10 +84,18 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return d;
 }
 __device__ __forceinline__ float hsum2(f32x2 a, f32x2 b) {
+#ifdef PEA_HSUM_ADD2
+    f32x2 t;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(a), "l"(b));
+    float lo, hi;
+    unpack2(t, lo, hi);
+    return lo + hi;
+#else
     float a0, a1, b0, b1;
     unpack2(a, a0, a1);
     unpack2(b, b0, b1);
     return (a0 + a1) + (b0 + b1);
+#endif
 }
 
 // Arrive on a CTA-wide counter with release/acquire semantics; returns the value before the increment.
@@ -125,6 +133,50 @@ __device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int 
         for (int i = 0; i < kC2; ++i) G[i] = fma2(gr2, xq[i], G[i]);
     }
     return w * diff * diff;
+}
+
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Two in-plane neighbours of the own voxel p at once, LANE-packed: X_c = (x_A[c], x_B[c]) shares one FFMA2 per channel
+// for the two norms, the two dot products (own unit vector as the scalar-broadcast operand) and the two gradient
+// updates, so there are no horizontal sums and the scalar tail runs packed.  A is the forward pair (anchored at p:
+// affinity and loss term returned), B the pair anchored at the other neighbour (gradient only).  GL[c] accumulates
+// (g_A x_A[c], g_B x_B[c]); the halves are added once per slice.
+__device__ __forceinline__ float inplane_pair2(const float* __restrict__ nbA, const float* __restrict__ nbB, int chs,
+                                               const f32x2 (&e)[kC2], f32x2 (&GL)[kC], float tA, float wA, float tB,
+                                               float wB, float gco, float& a_out) {
+    f32x2 X[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) X[c] = pack2(nbA[c * chs], nbB[c * chs]);
+    f32x2 ss0 = 0ull, ss1 = 0ull, d0 = 0ull, d1 = 0ull;
+#pragma unroll
+    for (int i = 0; i < kC2; ++i) {
+        float elo, ehi;
+        unpack2(e[i], elo, ehi);
+        ss0 = fma2(X[2 * i], X[2 * i], ss0);
+        ss1 = fma2(X[2 * i + 1], X[2 * i + 1], ss1);
+        d0 = fma2(pack2(elo, elo), X[2 * i], d0);
+        d1 = fma2(pack2(ehi, ehi), X[2 * i + 1], d1);
+    }
+    float ssA, ssB;
+    unpack2(add2(ss0, ss1), ssA, ssB);
+    const f32x2 rq2 = pack2(inv_norm(ssA), inv_norm(ssB));
+    const f32x2 a2 = mul2(add2(d0, d1), rq2);
+    const f32x2 diff2 = add2(a2, pack2(-tA, -tB));
+    const f32x2 wd2 = mul2(pack2(wA, wB), diff2);
+    const f32x2 gr2 = mul2(mul2(pack2(gco, gco), wd2), rq2);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) GL[c] = fma2(gr2, X[c], GL[c]);
+    float aA, aB, wdA, wdB, dA, dB;
+    unpack2(a2, aA, aB);
+    unpack2(wd2, wdA, wdB);
+    unpack2(diff2, dA, dB);
+    a_out = aA;
+    return wdA * dA;
 }
 
 template <int TY, bool GRAD>
@@ -449,6 +501,20 @@ __device__ __forceinline__ float ldg_early(const float* p, bool pred) {
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 constexpr uint32_t kTmemCols = 512;
+#ifndef PEA_K4_LANEPACK
+#define PEA_K4_LANEPACK 0  // forward + reverse in-plane pair of a shift evaluated together, lane-packed (inplane_pair2)
+#endif
+#ifndef PEA_K4_DUP
+#define PEA_K4_DUP 0  // timing experiments only: extra warps that repeat the work of rows 0.. (no stores)
+#endif
+#ifdef PEA_K4_NOREFILL  // timing experiments only: boxes loaded once, never refilled (wrong results)
+#define PEA_K4_REFILL 0
+#else
+#define PEA_K4_REFILL 1
+#endif
+#ifndef PEA_K4_NG
+#define PEA_K4_NG 4  // timing experiments only: < 4 drops the far in-plane shifts (wrong results)
+#endif
 
 template <int TY>
 struct alignas(128) StageM {
@@ -465,7 +531,11 @@ struct alignas(128) StageM {
 };
 
 template <int TY, bool GRAD>
+#ifdef PEA_K4_MAXNREG
+__global__ void __maxnreg__(PEA_K4_MAXNREG)
+#else
 __global__ void __launch_bounds__(TY * 32, 1)
+#endif
 fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
                  const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT,
                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapT1,
@@ -481,9 +551,9 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + kBytesTW + (GRAD ? kBytesTW + sizeof(S.sFar) : 0);
     constexpr uint32_t kBytesX = sizeof(S.sX) + kBytesTW + (GRAD ? kBytesTW : 0);
     constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
-    constexpr uint32_t kWarps = TY;
+    constexpr uint32_t kWarps = TY + PEA_K4_DUP;
 
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x & 31, wid = threadIdx.x >> 5, ty = wid % TY;
     const int D = P.D, H = P.H, W = P.W;
     const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
     int bid = blockIdx.x;
@@ -493,7 +563,7 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     const int b = bid / tiles_y;
     const int x0 = tix * TX, y0 = tiy * TY;
     const int x = x0 + tx, y = y0 + ty;
-    const bool live = (x < W) && (y < H);
+    const bool live = (x < W) && (y < H) && (wid < TY);
     const int64_t HW = (int64_t)H * W, N = HW * D;
     const int64_t pix = (int64_t)(live ? y : 0) * W + (live ? x : 0);
 
@@ -535,7 +605,7 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         issueY(0);
         issueX(0);
     }
-    if (ty == 0) {  // one warp allocates the whole Tensor Memory of this SM (one CTA per SM anyway: shared memory)
+    if (wid == 0) {  // one warp allocates the whole Tensor Memory of this SM (one CTA per SM anyway: shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -546,7 +616,7 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     const uint32_t tmem_base = s_tmem;
     // this thread's private strip: lane = 32 * (warp % 4) + lane id, 128 columns starting at 128 * (warp / 4);
     // slot s (slice z with z & 3 == s): columns [32 s, 32 s + 16) unit vector, [32 s + 16, 32 s + 32) gradient accumulator
-    const uint32_t tq = tmem_base + (((uint32_t)(ty & 3) * 32u) << 16) + (uint32_t)(ty >> 2) * 128u;
+    const uint32_t tq = tmem_base + (((uint32_t)(wid & 3) * 32u) << 16) + (uint32_t)(wid >> 2) * 128u;
 
     float rr1 = 0.f, rr2 = 0.f, rr3 = 0.f, rr4 = 0.f;  // 1/|x| of slices z-1 .. z-4 (for the normalisation backward)
     float lossacc[12];
@@ -555,7 +625,11 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
 
     const float* tgt_b = P.target + (int64_t)b * 12 * N + pix;
     const float* wgt_b = P.weight + (int64_t)b * 12 * N + pix;
+#ifdef PEA_K4_NOSTORE
+    float* affs_b = nullptr;
+#else
     float* affs_b = P.affs ? P.affs + (int64_t)b * 12 * N + pix : nullptr;
+#endif
     float* grad_b = P.grad ? P.grad + (int64_t)b * kC * N + pix : nullptr;
 
     // back through the normalisation:  (G - e^ <e^, G>) / |x|   (eps branch of F.normalize: G / eps)
@@ -569,6 +643,9 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         }
         float eg = hsum2(p0, p1);
         if (!(r < 1e12f)) eg = 0.f;
+#ifdef PEA_K4_NOSTORE
+        if (eg != 12345.678f) return;
+#endif
         const f32x2 neg = pack2(-eg, -eg), r2 = pack2(r, r);
         float* dst = grad_b + (int64_t)zf * HW;
 #pragma unroll
@@ -603,8 +680,12 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         load_tz(z);
 
         f32x2 e[kC2], G[kC2];
+        f32x2 GL[kC];  // lane-packed accumulators of the in-plane parts
         float rp;
         // ---------------- y part
+#ifdef PEA_K4_NOREFILL
+        if (z == 0)
+#endif
         mbar_wait(&barY, par);
         {
             const float* own = &S.sY[0][ty + HY][tx];
@@ -623,9 +704,13 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
                 e[i] = mul2(e[i], rp2);
                 G[i] = 0ull;
             }
+            if (PEA_K4_LANEPACK && GRAD) {
+#pragma unroll
+                for (int c = 0; c < kC; ++c) GL[c] = 0ull;
+            }
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < PEA_K4_NG; ++g) {
             const int s = shift_yx(g);
             const int k = 3 * g + 1;
             const float* nb_m = (g < 3) ? &S.sY[0][ty + HY - s][tx] : &S.sAm[0][ty][tx];
@@ -633,6 +718,13 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             const int chs = (g < 3) ? CHS_Y : CHS_A;
             const bool vf = y >= s;  // out-of-volume voxels have zero weight (TMA zero fill)
             float a;
+            if (PEA_K4_LANEPACK && GRAD) {
+                const float* pr = (g == 3) ? &S.sFar[0][ty][tx]
+                                           : (ty + s < TY ? sTy + (g * CHS_A + s * TX) : sTb + (g * CHS_A + (s - TY) * TX));
+                lossacc[k] += inplane_pair2(nb_m, nb_p, chs, e, GL, sTy[g * CHS_A], vf ? sTy[kW + g * CHS_A] : 0.f, pr[0],
+                                            pr[(g == 3) ? CHS_A : kW], P.gcoef[k], a);
+                if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
+            } else {
             lossacc[k] += inplane_pair<GRAD>(nb_m, chs, e, G, sTy[g * CHS_A], vf ? sTy[kW + g * CHS_A] : 0.f, P.gcoef[k], a);
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;  // partner outside the volume: zero fill, a == 0
             if (GRAD) {
@@ -646,18 +738,28 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
                 float a2;
                 inplane_pair<true>(nb_p, chs, e, G, t_r, w_r, P.gcoef[k], a2);
             }
+            }
         }
         __syncwarp();
-        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueY(z + 1);
+        if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D && PEA_K4_REFILL) issueY(z + 1);
 
         // ---------------- x part
+#ifdef PEA_K4_NOREFILL
+        if (z == 0)
+#endif
         mbar_wait(&barX, par);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < PEA_K4_NG; ++g) {
             const int s = shift_yx(g);
             const int k = 3 * g + 2;
             const bool vf = x >= s;
             float a;
+            if (PEA_K4_LANEPACK && GRAD) {
+                const float* pr = (tx + s < TX) ? sTx + (g * CHS_A + s) : sTn + (g * CHS_A + s - TX);
+                lossacc[k] += inplane_pair2(&S.sX[0][ty][tx + XPAD - s], &S.sX[0][ty][tx + XPAD + s], CHS_X, e, GL,
+                                            sTx[g * CHS_A], vf ? sTx[kW + g * CHS_A] : 0.f, pr[0], pr[kW], P.gcoef[k], a);
+                if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
+            } else {
             lossacc[k] += inplane_pair<GRAD>(&S.sX[0][ty][tx + XPAD - s], CHS_X, e, G, sTx[g * CHS_A],
                                              vf ? sTx[kW + g * CHS_A] : 0.f, P.gcoef[k], a);
             if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
@@ -667,9 +769,19 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
                 float a2;
                 inplane_pair<true>(&S.sX[0][ty][tx + XPAD + s], CHS_X, e, G, pr[0], pr[kW], P.gcoef[k], a2);
             }
+            }
         }
         __syncwarp();
-        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D) issueX(z + 1);
+        if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(z + 1) - 1 && z + 1 < D && PEA_K4_REFILL) issueX(z + 1);
+        if (PEA_K4_LANEPACK && GRAD) {  // the two halves of every lane-packed accumulator -> channel-packed G
+#pragma unroll
+            for (int i = 0; i < kC2; ++i) {
+                float a0, a1, b0, b1;
+                unpack2(GL[2 * i], a0, a1);
+                unpack2(GL[2 * i + 1], b0, b1);
+                G[i] = pack2(a0 + a1, b0 + b1);
+            }
+        }
 
         // ---------------- z part: pairs (z, z - j); slice z - j comes out of its Tensor-Memory slot, its updated
         // gradient accumulator goes back (j < 4) or -- all pairs of slice z - 4 seen -- straight through the
@@ -736,11 +848,11 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
         const float v = warp_sum(lossacc[k]);
-        if (tx == 0) s_red[k][ty] = v;
+        if (tx == 0 && wid < TY) s_red[k][ty] = v;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (ty == 0) {
+    if (wid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
@@ -1535,11 +1647,11 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
     if (grad) {
         auto kern = t3::fused3d_norm5_tm<TY, true>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, mT1, mW1, P);
+        kern<<<grid, (TY + PEA_K4_DUP) * 32, smem, st>>>(mY, mA, mX, mT, mW, mT1, mW1, P);
     } else {
         auto kern = t3::fused3d_norm5_tm<TY, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mT, mW, mT1, mW1, P);
+        kern<<<grid, (TY + PEA_K4_DUP) * 32, smem, st>>>(mY, mA, mX, mT, mW, mT1, mW1, P);
     }
     return (int)cudaGetLastError();
 #endif

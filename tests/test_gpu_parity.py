@@ -678,6 +678,42 @@ def test_axis2d_kernel_matches_generic_and_oracle(P, O, B, H, W, shifts, seed):
         close_t(outs[1][i].cpu(), outs[0][i].cpu(), what=f"zero-border axis kernel {what}")
 
 
+@pytest.mark.parametrize("cap", [1, 3, 7])
+def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, monkeypatch):
+    """The axis-aligned 2-D kernel is persistent: a CTA walks tiles t, t + grid, ... and requests the TMA boxes of its next
+    tile while it finishes the current one; tiles on the image edge (circular border) are filled by hand in between.
+    With the grid capped to a few CTAs (PEA_AXIS_MAX_CTAS, read per call) every CTA alternates between both kinds many
+    times: affinities and gradient must be bit-identical to the uncapped launch, the loss equal up to the summation
+    order of the per-CTA partials, and everything must match the oracle."""
+    offsets = O.multi_offset([1, 3, 5, 9, 11], neighbor=4)
+    B, H, W = 2, 130, 160
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, B, 16, H, W, offsets, 95)
+    outs = {}
+    for name, val in (("full", None), ("capped", str(cap))):
+        if val is None:
+            monkeypatch.delenv("PEA_AXIS_MAX_CTAS", raising=False)
+        else:
+            monkeypatch.setenv("PEA_AXIS_MAX_CTAS", val)
+        e = dev(emb, True)
+        l, a, _ = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+        l.backward()
+        e2 = dev(emb, True)
+        l2, a2 = P.ema_embedding_loss(e2, dev(ema), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
+        l2.backward()
+        outs[name] = (float(l.detach()), a.detach().cpu(), e.grad.cpu(), float(l2.detach()), a2.detach().cpu(), e2.grad.cpu())
+    monkeypatch.delenv("PEA_AXIS_MAX_CTAS", raising=False)
+    for i in (1, 2, 4, 5):
+        assert torch.equal(outs["full"][i], outs["capped"][i])
+    close_s(outs["capped"][0], outs["full"][0], what="loss, capped grid")
+    close_s(outs["capped"][3], outs["full"][3], what="ema loss, capped grid")
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao, _ = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), O.WeightedMSE(), offsets)
+    lo.backward()
+    close_s(outs["capped"][0], lo, what="loss vs oracle")
+    close_t(outs["capped"][1], ao, what="affs vs oracle")
+    close_t(outs["capped"][2], eo.grad, what="grad vs oracle")
+
+
 # =========================================================================== forward-only tiled kernel + z-shards
 @pytest.mark.parametrize("B,D,H,W,seed", [(1, 18, 64, 96, 91), (2, 7, 37, 44, 92), (1, 5, 28, 28, 93)])
 def test_tiled3d_forward_matches_generic_and_oracle(P, O, B, D, H, W, seed):
