@@ -17,6 +17,10 @@
 #include "pea_common.cuh"
 #include "pea_tma.cuh"
 
+#ifndef PEA_AXIS_DEPTH
+#define PEA_AXIS_DEPTH 3  // rotating target / weight / mask fetch buffers of the persistent kernel (3 or 4)
+#endif
+
 namespace pea {
 namespace a2 {
 
@@ -620,7 +624,11 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
         }
         const float* ownY = &S.sY[0][ty + PMAX][tx];
         const float* ownX = &S.sX[0][ty][tx + PX];
+#ifdef PEA_AXIS_NOSTORE  // timing experiments only
+        float* affs_b = nullptr;
+#else
         float* affs_b = P.affs ? P.affs + (int64_t)b * K * Nu + pix : nullptr;
+#endif
         f32x2 e[kC2], G[kC2];
         float rp = 0.f;
 
@@ -636,8 +644,16 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
 
         auto run = [&](auto inner_c) {
             constexpr bool INNER = decltype(inner_c)::value;
+#ifdef PEA_AXIS_NOFETCH  // timing experiments only
+            auto fetch = [&](int i) -> KV { KV v = {0.5f, 1.25f, 0.25f, 0.75f, 1u, 1u}; return v; };
+#else
             auto fetch = [&](int i) -> KV { return INNER ? fetch_inner(i) : fetch_edge(i); };
+#endif
+#if PEA_AXIS_DEPTH == 4
+            KV kv0 = fetch(0), kv1 = fetch(1), kv2 = fetch(2), kv3;
+#else
             KV kv0 = fetch(0), kv1 = fetch(1), kv2;
+#endif
             if (manual) __syncthreads();  // hand-filled boxes complete
             else mbar_wait(&barY, phY & 1u);
             if (CROSS) {
@@ -686,6 +702,34 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
                 S.sL[c][threadIdx.x] += lt;
             };
             bool xready = manual, yfree = false;
+#if PEA_AXIS_DEPTH == 4
+            // four rotating fetch buffers: target / weight / mask are requested three offsets (~1 us) before their use
+#pragma unroll 1
+            for (int i = 0; i < ntot; i += 4) {
+                if (!yfree && i >= ny) {  // every y offset done: the y-column box is free
+                    releaseY();
+                    yfree = true;
+                }
+                if (!xready && i + 3 >= ny) {
+                    mbar_wait(&barX, phX & 1u);
+                    xready = true;
+                }
+                kv3 = fetch(i + 3);
+                body(i, kv0);
+                if (i + 1 < ntot) {
+                    kv0 = fetch(i + 4);
+                    body(i + 1, kv1);
+                }
+                if (i + 2 < ntot) {
+                    kv1 = fetch(i + 5);
+                    body(i + 2, kv2);
+                }
+                if (i + 3 < ntot) {
+                    kv2 = fetch(i + 6);
+                    body(i + 3, kv3);
+                }
+            }
+#else
 #pragma unroll 1
             for (int i = 0; i < ntot; i += 3) {
                 if (!yfree && i >= ny) {  // every y offset done: the y-column box is free
@@ -707,6 +751,7 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
                     body(i + 2, kv2);
                 }
             }
+#endif
             if (!yfree) releaseY();
             if (!xready) mbar_wait(&barX, phX & 1u);  // (no x offsets) consume the phase all the same
             releaseX();
@@ -728,6 +773,9 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
             }
             float eg = hsum2(p0, p1);
             if (!(rp < 1e12f)) eg = 0.f;
+#ifdef PEA_AXIS_NOSTORE
+            if (eg != 12345.678f) continue;
+#endif
             const f32x2 neg = pack2(-eg, -eg), r2 = pack2(rp, rp);
             float* gb = P.grad + (int64_t)b * kC * Nu + pix;
 #pragma unroll

@@ -678,14 +678,17 @@ def test_axis2d_kernel_matches_generic_and_oracle(P, O, B, H, W, shifts, seed):
         close_t(outs[1][i].cpu(), outs[0][i].cpu(), what=f"zero-border axis kernel {what}")
 
 
+@pytest.mark.parametrize("shifts", [[1, 3, 5, 9, 11], [1, 3, 5, 9, 27]])
 @pytest.mark.parametrize("cap", [1, 3, 7])
-def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, monkeypatch):
-    """The axis-aligned 2-D kernel is persistent: a CTA walks tiles t, t + grid, ... and requests the TMA boxes of its next
-    tile while it finishes the current one; tiles on the image edge (circular border) are filled by hand in between.
-    With the grid capped to a few CTAs (PEA_AXIS_MAX_CTAS, read per call) every CTA alternates between both kinds many
-    times: affinities and gradient must be bit-identical to the uncapped launch, the loss equal up to the summation
-    order of the per-CTA partials, and everything must match the oracle."""
-    offsets = O.multi_offset([1, 3, 5, 9, 11], neighbor=4)
+def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, shifts, monkeypatch):
+    """The 2-D kernels are persistent: a CTA walks tiles t, t + grid, ... and requests the TMA boxes of its next tile
+    while it finishes the current one; tiles on the image edge (circular border) are filled / patched by hand in between.
+    Shifts <= 12 take the fully unrolled canonical kernel (pea_affs2d_canon.cu), the CVPPP table with shift 27 the
+    table-driven one (pea_affs2d_axis.cu); the two-view loss always takes the latter.  With the grid capped to a few
+    CTAs (PEA_AXIS_MAX_CTAS, read per call) every CTA alternates between both kinds of tile many times: affinities and
+    gradient must be bit-identical to the uncapped launch, the loss equal up to the summation order of the per-CTA
+    partials, and everything must match the oracle."""
+    offsets = O.multi_offset(shifts, neighbor=4)
     B, H, W = 2, 130, 160
     emb, ema, tgt, wgt, msk = _inputs_2d(O, B, 16, H, W, offsets, 95)
     outs = {}
@@ -712,6 +715,46 @@ def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, monkeypatch):
     close_s(outs["capped"][0], lo, what="loss vs oracle")
     close_t(outs["capped"][1], ao, what="affs vs oracle")
     close_t(outs["capped"][2], eo.grad, what="grad vs oracle")
+
+
+@pytest.mark.parametrize("B,H,W,border", [(2, 130, 160, "wrap"), (1, 75, 100, "wrap"), (2, 64, 72, "zero"), (1, 131, 200, "zero")])
+@pytest.mark.parametrize("mask_kind", ["u8", "f32", "none"])
+def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, mask_kind, monkeypatch):
+    """multi_offset([1, 3, 5, 9, 11], 4) (one view) takes the fully unrolled canonical kernel; with PEA_NO_CANON set the
+    same call takes the table-driven axis-aligned kernel, with IMPL_GENERIC the generic one.  All three must agree
+    (1e-5 of the largest magnitude) on loss, affinities and gradient: both borders, partial tiles in x and y, every
+    mask type, with and without gradient."""
+    from pea_b200 import _ops as ops
+    offsets = O.multi_offset([1, 3, 5, 9, 11], neighbor=4)
+    offs3 = ops.offsets3(offsets, 2)
+    K = len(offsets)
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    emb = torch.randn((B, 16, 1, H, W), generator=g).cuda()
+    emb[0, :, 0, 3, 5] = 0.0
+    tgt = (torch.rand((B, K, 1, H, W), generator=g) > 0.5).float().cuda()
+    wgt = (torch.rand((B, K, 1, H, W), generator=g) * 2 + 0.1).cuda()
+    m8 = (torch.rand((B, K, 1, H, W), generator=g) > 0.2).to(torch.uint8).cuda()
+    msk = {"u8": m8, "f32": m8.float() * 0.5 + 0.5, "none": None}[mask_kind]
+    bd = ops.BORDER_WRAP if border == "wrap" else ops.BORDER_ZERO
+    norm = np.full(K, float(B * W), np.float32)
+    coef = np.linspace(0.5, 1.5, K).astype(np.float32)
+    for grad in (True, False):
+        outs = {}
+        for name in ("canon", "axis", "generic"):
+            if name == "axis":
+                monkeypatch.setenv("PEA_NO_CANON", "1")
+            else:
+                monkeypatch.delenv("PEA_NO_CANON", raising=False)
+            impl = ops.IMPL_GENERIC if name == "generic" else ops.IMPL_AUTO
+            lo, a, gr, _ = ops.affs_loss_fwd_bwd(emb, None, offs3, bd, tgt, wgt, msk, norm, coef, want_affs=True,
+                                                 want_grad=grad, impl=impl)
+            outs[name] = (lo.cpu(), a.cpu(), gr.cpu() if grad else None)
+        monkeypatch.delenv("PEA_NO_CANON", raising=False)
+        for other in ("axis", "generic"):
+            close_t(outs["canon"][0], outs[other][0], what=f"loss vs {other}")
+            close_t(outs["canon"][1], outs[other][1], what=f"affs vs {other}")
+            if grad:
+                close_t(outs["canon"][2], outs[other][2], what=f"grad vs {other}")
 
 
 # =========================================================================== forward-only tiled kernel + z-shards
