@@ -445,8 +445,8 @@ fused2d_axis(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ C
 // (y-column box after the last y offset, x-row box after the last x offset: release / acquire counters as in the 3-D
 // kernels, no CTA barrier in the loop).  The one-tile kernel above waits ~2 us for its boxes at the start of every
 // 8 us CTA; here that latency hides behind the other half of the previous tile, the gradient stores and the next
-// tile's first target / weight / mask fetches.  Tiles on the image edge under the circular border are still filled by
-// hand (two CTA barriers around the fill).  Loss terms accumulate per thread and offset in shared memory over all the
+// tile's first target / weight / mask fetches.  Circular border: TMA zero-fills what lies outside the image; on the
+// tiles whose boxes cross the image edge exactly those elements are patched by hand afterwards (one CTA barrier per box).  Loss terms accumulate per thread and offset in shared memory over all the
 // CTA's tiles and are summed in a fixed order at the end: gridDim.x rows of partials.
 __device__ __forceinline__ uint32_t arrive_count(uint32_t* cnt) {
     uint32_t old;
@@ -498,10 +498,8 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
         mbar_fence_init();
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
-        if (!(wrap && !tile_inner(y0, x0))) {
-            issueY(b, y0, x0);
-            issueX(b, y0, x0);
-        }
+        issueY(b, y0, x0);
+        issueX(b, y0, x0);
     }
     __syncthreads();
     uint32_t phY = 0, phX = 0, it = 0;
@@ -510,16 +508,14 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
         int bn = 0, y0n = 0, x0n = 0;
-        bool next_tma = false;
-        if (t + (int)gridDim.x < n_tiles) {
-            tile_origin(t + (int)gridDim.x, bn, y0n, x0n);
-            next_tma = !(wrap && !tile_inner(y0n, x0n));
-        }
+        const bool next_tma = t + (int)gridDim.x < n_tiles;
+        if (next_tma) tile_origin(t + (int)gridDim.x, bn, y0n, x0n);
         const int x = x0 + tx, y = y0 + ty;
         const bool live = (x < W) && (y < H);
         const uint32_t pix = (uint32_t)((live ? y : 0) * W + (live ? x : 0));
         const bool inner = tile_inner(y0, x0);
-        const bool manual = wrap && !inner;
+        // circular border: TMA zero-fills what lies outside the image; those elements are patched by hand afterwards
+        const bool patch = wrap && !inner;
         const uint32_t goal = kWarps * (it + 1) - 1;
 
         const float* tgt_b = P.target + (int64_t)b * K * Nu + pix;
@@ -578,50 +574,37 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
             return v;
         };
 
-        if (manual) {
-            __syncthreads();  // every warp has left the previous tile: the boxes may be overwritten
+        auto patchY = [&]() {
             const float* src = (CROSS ? P.par : P.emb) + (int64_t)b * kC * Nu;
             float* sYf = &S.sY[0][0][0];
+            for (int idx = threadIdx.x; idx < YR * TX; idx += NT) {
+                const int gy = y0 - PMAX + (idx >> 5), gx = x0 + (idx & 31);
+                if ((unsigned)gy < (unsigned)H && gx < W) continue;
+                const uint32_t o = (uint32_t)(wrap3(gy, H) * W + wrap3(gx, W));
+                float v[kC];
+#pragma unroll
+                for (int c = 0; c < kC; ++c) v[c] = __ldg(src + (o + (uint32_t)c * Nu));
+#pragma unroll
+                for (int c = 0; c < kC; ++c) sYf[c * CHS_Y + idx] = v[c];
+            }
+            __syncthreads();  // patched box complete
+        };
+        auto patchX = [&]() {
+            const float* src = (CROSS ? P.par : P.emb) + (int64_t)b * kC * Nu;
             float* sXf = &S.sX[0][0][0];
-            for (int idx = threadIdx.x; idx < YR * TX; idx += 2 * NT) {
-                const int idx2 = idx + NT;
-                const bool two = idx2 < YR * TX;
-                const int row = idx >> 5, col = idx & 31, row2 = (two ? idx2 : idx) >> 5;
-                const uint32_t gx = (uint32_t)wrap3(x0 + col, W);
-                const uint32_t o = (uint32_t)(wrap3(y0 - PMAX + row, H) * W) + gx;
-                const uint32_t o2 = (uint32_t)(wrap3(y0 - PMAX + row2, H) * W) + gx;
-                float v[kC], v2[kC];
-#pragma unroll
-                for (int c = 0; c < kC; ++c) {
-                    v[c] = __ldg(src + (o + (uint32_t)c * Nu));
-                    v2[c] = __ldg(src + (o2 + (uint32_t)c * Nu));
-                }
-#pragma unroll
-                for (int c = 0; c < kC; ++c) {
-                    sYf[c * CHS_Y + idx] = v[c];
-                    if (two) sYf[c * CHS_Y + idx2] = v2[c];
-                }
-            }
-            for (int idx = threadIdx.x; idx < TY * XW; idx += 2 * NT) {
-                const int idx2 = idx + NT;
-                const bool two = idx2 < TY * XW;
+            for (int idx = threadIdx.x; idx < TY * XW; idx += NT) {
                 const int row = idx / XW, col = idx - row * XW;
-                const int j2 = two ? idx2 : idx, row2 = j2 / XW, col2 = j2 - row2 * XW;
-                const uint32_t o = (uint32_t)(wrap3(y0 + row, H) * W + wrap3(x0 - PX + col, W));
-                const uint32_t o2 = (uint32_t)(wrap3(y0 + row2, H) * W + wrap3(x0 - PX + col2, W));
-                float v[kC], v2[kC];
+                const int gy = y0 + row, gx = x0 - PX + col;
+                if (gy < H && (unsigned)gx < (unsigned)W) continue;
+                const uint32_t o = (uint32_t)(wrap3(gy, H) * W + wrap3(gx, W));
+                float v[kC];
 #pragma unroll
-                for (int c = 0; c < kC; ++c) {
-                    v[c] = __ldg(src + (o + (uint32_t)c * Nu));
-                    v2[c] = __ldg(src + (o2 + (uint32_t)c * Nu));
-                }
+                for (int c = 0; c < kC; ++c) v[c] = __ldg(src + (o + (uint32_t)c * Nu));
 #pragma unroll
-                for (int c = 0; c < kC; ++c) {
-                    sXf[c * CHS_X + idx] = v[c];
-                    if (two) sXf[c * CHS_X + idx2] = v2[c];
-                }
+                for (int c = 0; c < kC; ++c) sXf[c * CHS_X + idx] = v[c];
             }
-        }
+            __syncthreads();
+        };
         const float* ownY = &S.sY[0][ty + PMAX][tx];
         const float* ownX = &S.sX[0][ty][tx + PX];
 #ifdef PEA_AXIS_NOSTORE  // timing experiments only
@@ -654,8 +637,8 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
 #else
             KV kv0 = fetch(0), kv1 = fetch(1), kv2;
 #endif
-            if (manual) __syncthreads();  // hand-filled boxes complete
-            else mbar_wait(&barY, phY & 1u);
+            mbar_wait(&barY, phY & 1u);
+            if (patch) patchY();
             if (CROSS) {
                 const float* eb = P.emb + (int64_t)b * kC * Nu;
 #pragma unroll
@@ -701,7 +684,7 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
                 if (affs_b && (INNER || live)) affs_b[(uint32_t)c * Nu] = a;
                 S.sL[c][threadIdx.x] += lt;
             };
-            bool xready = manual, yfree = false;
+            bool xready = false, yfree = false;
 #if PEA_AXIS_DEPTH == 4
             // four rotating fetch buffers: target / weight / mask are requested three offsets (~1 us) before their use
 #pragma unroll 1
@@ -712,6 +695,7 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
                 }
                 if (!xready && i + 3 >= ny) {
                     mbar_wait(&barX, phX & 1u);
+                    if (patch) patchX();
                     xready = true;
                 }
                 kv3 = fetch(i + 3);
@@ -738,6 +722,7 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
                 }
                 if (!xready && i + 2 >= ny) {
                     mbar_wait(&barX, phX & 1u);
+                    if (patch) patchX();
                     xready = true;
                 }
                 kv2 = fetch(i + 2);
@@ -758,10 +743,8 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
         };
         if (inner) run(TrueT{});
         else run(FalseT{});
-        if (!manual) {
-            ++phY;
-            ++phX;
-        }
+        ++phY;
+        ++phX;
 
         // ---- gradient back through the normalisation
         if (GRAD && live) {
