@@ -231,31 +231,48 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
 
         // ---- mask of the pair anchored here and of the pair anchored s below / s to the right, for one axis
         uint32_t mky[NS][2] = {}, mkx[NS][2] = {};
+        // `whole`: the tile and the anchors s below / to the right of it lie inside the image -- no border rule, no dead lanes
+        const bool whole = y0 + TY + PM <= H && x0 + TX + PM <= W;
         auto fetch_masks = [&](bool isx, uint32_t (&mk)[NS][2]) {
             if constexpr (MASK != PEA_MASK_NONE) {
+                const uint8_t* m8 = reinterpret_cast<const uint8_t*>(P.mask) + sample;
+                const float* mf = reinterpret_cast<const float*>(P.mask) + sample;
+                if (whole) {
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                const int s = P.shift[j];
-                const uint32_t koff = (uint32_t)(2 * j + (isx ? 1 : 0)) * Nu;
-                int qy = y + (isx ? 0 : s), qx = x + (isx ? s : 0);
-                bool vr = live;
-                if (wrap) {
-                    qy = wrap1(qy, H);
-                    qx = wrap1(qx, W);
+                    for (int j = 0; j < NS; ++j) {
+                        const uint32_t o = (uint32_t)(2 * j + (isx ? 1 : 0)) * Nu + pix;
+                        const uint32_t o2 = o + (uint32_t)(isx ? P.shift[j] : P.shift[j] * W);
+                        if (MASK == PEA_MASK_U8) {
+                            mk[j][0] = ldg_u8_early(m8 + o, true);
+                            if (GRAD) mk[j][1] = ldg_u8_early(m8 + o2, true);
+                        } else {
+                            mk[j][0] = ldg_b32_early(mf + o, true);
+                            if (GRAD) mk[j][1] = ldg_b32_early(mf + o2, true);
+                        }
+                    }
                 } else {
-                    vr = vr && qy < H && qx < W;
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        const int s = P.shift[j];
+                        const uint32_t koff = (uint32_t)(2 * j + (isx ? 1 : 0)) * Nu;
+                        int qy = y + (isx ? 0 : s), qx = x + (isx ? s : 0);
+                        bool vr = live;
+                        if (wrap) {
+                            qy = wrap1(qy, H);
+                            qx = wrap1(qx, W);
+                        } else {
+                            vr = vr && qy < H && qx < W;
+                        }
+                        const uint32_t o2 = koff + (vr ? (uint32_t)(qy * W + qx) : 0u);
+                        if (MASK == PEA_MASK_U8) {
+                            mk[j][0] = ldg_u8_early(m8 + (koff + pix), live);
+                            if (GRAD) mk[j][1] = ldg_u8_early(m8 + o2, vr);
+                        } else {
+                            mk[j][0] = ldg_b32_early(mf + (koff + pix), live);
+                            if (GRAD) mk[j][1] = ldg_b32_early(mf + o2, vr);
+                        }
+                    }
                 }
-                const uint32_t o2 = koff + (vr ? (uint32_t)(qy * W + qx) : 0u);
-                if (MASK == PEA_MASK_U8) {
-                    const uint8_t* m = reinterpret_cast<const uint8_t*>(P.mask) + sample;
-                    mk[j][0] = ldg_u8_early(m + (koff + pix), live);
-                    if (GRAD) mk[j][1] = ldg_u8_early(m + o2, vr);
-                } else {
-                    const float* m = reinterpret_cast<const float*>(P.mask) + sample;
-                    mk[j][0] = ldg_b32_early(m + (koff + pix), live);
-                    if (GRAD) mk[j][1] = ldg_b32_early(m + o2, vr);
-                }
-            }
             }
         };
         fetch_masks(false, mky);
