@@ -39,11 +39,12 @@ int launch_tiled2d(const float* emb, const float* partner, const Dims& d, const 
 bool axis2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wrap, bool need_grad_partner, const float* emb,
                      const float* partner);
 int axis2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap);
-bool canon2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, bool cross, const float* emb, const float* target,
-                      const float* weight);
+bool canon2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, const float* emb, const float* partner,
+                      const float* target, const float* weight);
 int canon2d_blocks(int B, int H, int W);
-int launch_canon2d(const float* emb, const Dims& d, const OffsetTable& tab, int wrap, const float* target, const float* weight,
-                   const void* mask, int mask_dtype, float* affs, float* partials, float* grad, cudaStream_t st);
+int launch_canon2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap, const float* target,
+                   const float* weight, const void* mask, int mask_dtype, float* affs, float* partials, float* grad,
+                   cudaStream_t st);
 int launch_axis2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap,
                   const float* target, const float* weight, const void* mask, int mask_dtype, float* affs, float* partials,
                   float* grad, cudaStream_t st);
@@ -262,13 +263,14 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
                            grad_partner == nullptr;
     const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr);
     if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
-    // canonical multi_offset(shifts <= 12, neighbor=4) table, one view: fully unrolled persistent kernel.
+    // canonical multi_offset(shifts <= 12, neighbor=4) table (one view, or two views with the second one constant):
+    // fully unrolled persistent kernel.
     // PEA_NO_CANON (read per call, no state kept): test knob that sends these calls to the table-driven axis kernel.
-    if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC && !cross && getenv("PEA_NO_CANON") == nullptr &&
-        canon2d_eligible(C, D, H, W, tab, cross != 0, emb, target, weight)) {
+    if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC && grad_partner == nullptr && getenv("PEA_NO_CANON") == nullptr &&
+        canon2d_eligible(C, D, H, W, tab, emb, partner ? partner : emb, target, weight)) {
         float* parts = ws.rinvE;
-        if ((rc = launch_canon2d(emb, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts, grad_emb,
-                                 st)))
+        if ((rc = launch_canon2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts,
+                                 grad_emb, st)))
             return rc;
         finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, canon2d_blocks(B, H, W), K, sc, loss_out);
         return (int)cudaGetLastError();

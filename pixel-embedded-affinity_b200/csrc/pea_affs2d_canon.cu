@@ -26,11 +26,19 @@ namespace c2 {
 
 constexpr int kC = 16, kC2 = 8;
 constexpr int TX = 32, TY = 16, PM = 12, NS = 5, K = 2 * NS;
-constexpr int YR = TY + 2 * PM, XW = TX + 2 * PM;
-constexpr int CHS_Y = YR * TX, CHS_X = TY * XW;
-constexpr int GY = TY + PM;  // rows of the y-channel target / weight group (tile + the rows below)
-constexpr int GX = TX + 16;  // columns of the x-channel group (tile + the next 16 columns)
 constexpr int NT = TY * 32;
+// One view (SELF): every offset is evaluated in both directions (gather-form backward), so the boxes carry a halo on
+// both sides and the target / weight groups the anchors s below / to the right of the tile.  Two views (CROSS, second
+// view constant): only the pair anchored at p exists -- upper / left halo only, tile-sized target / weight groups, and
+// the own vector of the anchor view in a box of its own.
+template <bool CROSS>
+struct Geo {
+    static constexpr int YR = CROSS ? TY + PM : TY + 2 * PM;      // rows of the y-column box, first row y0 - PM
+    static constexpr int XW = CROSS ? TX + PM : TX + 2 * PM;      // columns of the x-row box, first column x0 - PM
+    static constexpr int CHS_Y = YR * TX, CHS_X = TY * XW;
+    static constexpr int GY = CROSS ? TY : TY + PM;               // rows of the y-channel target / weight group
+    static constexpr int GX = CROSS ? TX : TX + 16;               // columns of the x-channel group
+};
 
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
@@ -102,7 +110,8 @@ struct Params {
     int tiles_x, tiles_y, n_tiles;
     int shift[NS];   // s_j > 0: channel 2j pairs p with the pixel s_j rows above, channel 2j + 1 with s_j columns to the left
     float gcoef[K];  // 2 * coef / norm of the channel
-    const float* emb;
+    const float* emb;      // anchor view
+    const float* par;      // staged view (== emb for one view)
     const float* target;
     const float* weight;
     const void* mask;
@@ -111,13 +120,15 @@ struct Params {
     float* partials;  // [gridDim.x][K]
 };
 
+template <bool CROSS>
 struct alignas(128) Stage {
-    float sY[kC][YR][TX];   // rows y0 - 12 .. y0 + 27
-    float sX[kC][TY][XW];   // cols x0 - 12 .. x0 + 43
-    float tY[NS][GY][TX];   // target, y channels (0, 2, .., 8), rows y0 .. y0 + 27
-    float wY[NS][GY][TX];   // weight
-    float tX[NS][TY][GX];   // target, x channels (1, 3, .., 9), cols x0 .. x0 + 47
-    float wX[NS][TY][GX];
+    float sY[kC][Geo<CROSS>::YR][TX];   // staged view, rows y0 - 12 .. (SELF: y0 + 27)
+    float sX[kC][TY][Geo<CROSS>::XW];   // staged view, cols x0 - 12 .. (SELF: x0 + 43)
+    float tY[NS][Geo<CROSS>::GY][TX];   // target, y channels (0, 2, .., 8), rows y0 .. (SELF: y0 + 27)
+    float wY[NS][Geo<CROSS>::GY][TX];   // weight
+    float tX[NS][TY][Geo<CROSS>::GX];   // target, x channels (1, 3, .., 9), cols x0 .. (SELF: x0 + 47)
+    float wX[NS][TY][Geo<CROSS>::GX];
+    float sO[CROSS ? kC : 1][CROSS ? TY : 1][TX];  // CROSS: the anchor view's own tile
 };
 
 // One neighbour q of the own pixel p (raw values, channels CHS floats apart): a = <e^_p, e^_q>,
@@ -128,6 +139,27 @@ __device__ __forceinline__ float pair(const float* __restrict__ nb, const f32x2 
     f32x2 xq[kC2];
 #pragma unroll
     for (int i = 0; i < kC2; ++i) xq[i] = pack2(nb[(2 * i) * CHS], nb[(2 * i + 1) * CHS]);
+#ifdef PEA_DOT_SCALAR
+    // the dot product reads three distinct register pairs per FFMA2 (3.5 clk on the register-bandwidth-bound packed
+    // pipe, tools/microbench_mix.cu): two scalar FFMAs take 2.8 clk
+    f32x2 ss0 = 0ull, ss1 = 0ull;
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kC2; i += 2) {
+        ss0 = fma2(xq[i], xq[i], ss0);
+        ss1 = fma2(xq[i + 1], xq[i + 1], ss1);
+    }
+#pragma unroll
+    for (int i = 0; i < kC2; ++i) {
+        float e0, e1, x0, x1;
+        unpack2(e[i], e0, e1);
+        unpack2(xq[i], x0, x1);
+        d0 = fmaf(e0, x0, d0);
+        d1 = fmaf(e1, x1, d1);
+    }
+    const float rq = inv_norm(hsum2(ss0, ss1));
+    const float a = (d0 + d1) * rq;
+#else
     f32x2 ss0 = 0ull, ss1 = 0ull, d0 = 0ull, d1 = 0ull;
 #pragma unroll
     for (int i = 0; i < kC2; i += 2) {
@@ -138,6 +170,7 @@ __device__ __forceinline__ float pair(const float* __restrict__ nb, const f32x2 
     }
     const float rq = inv_norm(hsum2(ss0, ss1));
     const float a = hsum2(d0, d1) * rq;
+#endif
     a_out = a;
     const float diff = a - t;
     if (GRAD) {
@@ -156,18 +189,22 @@ __device__ __forceinline__ float mask_sq(uint32_t raw) {
     return m * m;
 }
 
-template <int MASK, bool GRAD>
+template <int MASK, bool GRAD, bool CROSS>
 __global__ void __launch_bounds__(NT, 1)
 fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX,
               const __grid_constant__ CUtensorMap mapTy, const __grid_constant__ CUtensorMap mapWy,
-              const __grid_constant__ CUtensorMap mapTx, const __grid_constant__ CUtensorMap mapWx, const Params P) {
+              const __grid_constant__ CUtensorMap mapTx, const __grid_constant__ CUtensorMap mapWx,
+              const __grid_constant__ CUtensorMap mapO, const Params P) {
+    using G_ = Geo<CROSS>;
+    constexpr int YR = G_::YR, XW = G_::XW, CHS_Y = G_::CHS_Y, CHS_X = G_::CHS_X, GY = G_::GY, GX = G_::GX;
+    constexpr bool REV = GRAD && !CROSS;  // the pair anchored at p + s, whose partner is p, contributes to grad(p)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Stage& S = *reinterpret_cast<Stage*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    Stage<CROSS>& S = *reinterpret_cast<Stage<CROSS>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     __shared__ uint64_t barY, barX;
     __shared__ uint32_t cntY, cntX;
     __shared__ float s_red[K][TY];
     constexpr uint32_t kWarps = TY;
-    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.tY) + sizeof(S.wY);
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.tY) + sizeof(S.wY) + (CROSS ? sizeof(S.sO) : 0);
     constexpr uint32_t kBytesX = sizeof(S.sX) + sizeof(S.tX) + sizeof(S.wX);
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -183,12 +220,15 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         y0 = (r - b * tiles_y) * TY;
     };
     // every box of the tile lies inside the image (circular border: TMA's zero fill would be wrong outside)
-    auto tile_inner = [&](int y0, int x0) { return y0 >= PM && y0 + TY + PM <= H && x0 >= PM && x0 + GX <= W; };
+    auto tile_inner = [&](int y0, int x0) {
+        return y0 >= PM && y0 - PM + YR <= H && y0 + GY <= H && x0 >= PM && x0 - PM + XW <= W && x0 + GX <= W;
+    };
     auto issueY = [&](int b, int y0, int x0) {
         mbar_arrive_expect_tx(&barY, kBytesY);
         tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - PM, 0, 0, b);
         tma_load_5d(&S.tY[0][0][0], &mapTy, &barY, x0, y0, 0, 0, b);
         tma_load_5d(&S.wY[0][0][0], &mapWy, &barY, x0, y0, 0, 0, b);
+        if (CROSS) tma_load_5d(&S.sO[0][0][0], &mapO, &barY, x0, y0, 0, 0, b);
     };
     auto issueX = [&](int b, int y0, int x0) {
         mbar_arrive_expect_tx(&barX, kBytesX);
@@ -232,7 +272,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         // ---- mask of the pair anchored here and of the pair anchored s below / s to the right, for one axis
         uint32_t mky[NS][2] = {}, mkx[NS][2] = {};
         // `whole`: the tile and the anchors s below / to the right of it lie inside the image -- no border rule, no dead lanes
-        const bool whole = y0 + TY + PM <= H && x0 + TX + PM <= W;
+        const bool whole = y0 + TY + (CROSS ? 0 : PM) <= H && x0 + TX + (CROSS ? 0 : PM) <= W;
         auto fetch_masks = [&](bool isx, uint32_t (&mk)[NS][2]) {
             if constexpr (MASK != PEA_MASK_NONE) {
                 const uint8_t* m8 = reinterpret_cast<const uint8_t*>(P.mask) + sample;
@@ -244,10 +284,10 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                         const uint32_t o2 = o + (uint32_t)(isx ? P.shift[j] : P.shift[j] * W);
                         if (MASK == PEA_MASK_U8) {
                             mk[j][0] = ldg_u8_early(m8 + o, true);
-                            if (GRAD) mk[j][1] = ldg_u8_early(m8 + o2, true);
+                            if (REV) mk[j][1] = ldg_u8_early(m8 + o2, true);
                         } else {
                             mk[j][0] = ldg_b32_early(mf + o, true);
-                            if (GRAD) mk[j][1] = ldg_b32_early(mf + o2, true);
+                            if (REV) mk[j][1] = ldg_b32_early(mf + o2, true);
                         }
                     }
                 } else {
@@ -266,10 +306,10 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                         const uint32_t o2 = koff + (vr ? (uint32_t)(qy * W + qx) : 0u);
                         if (MASK == PEA_MASK_U8) {
                             mk[j][0] = ldg_u8_early(m8 + (koff + pix), live);
-                            if (GRAD) mk[j][1] = ldg_u8_early(m8 + o2, vr);
+                            if (REV) mk[j][1] = ldg_u8_early(m8 + o2, vr);
                         } else {
                             mk[j][0] = ldg_b32_early(mf + (koff + pix), live);
-                            if (GRAD) mk[j][1] = ldg_b32_early(mf + o2, vr);
+                            if (REV) mk[j][1] = ldg_b32_early(mf + o2, vr);
                         }
                     }
                 }
@@ -279,7 +319,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
 
         mbar_wait(&barY, phY & 1u);
         if (patch) {
-            const float* src = P.emb + (int64_t)b * kC * Nu;
+            const float* src = P.par + (int64_t)b * kC * Nu;
             float* sYf = &S.sY[0][0][0];
             for (int idx = threadIdx.x; idx < YR * TX; idx += NT) {
                 const int gy = y0 - PM + (idx >> 5), gx = x0 + (idx & 31);
@@ -314,7 +354,9 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         {
             f32x2 s0 = 0ull, s1 = 0ull;
 #pragma unroll
-            for (int i = 0; i < kC2; ++i) e[i] = pack2(ownY[(2 * i) * CHS_Y], ownY[(2 * i + 1) * CHS_Y]);
+            for (int i = 0; i < kC2; ++i)
+                e[i] = CROSS ? pack2(S.sO[CROSS ? 2 * i : 0][CROSS ? ty : 0][tx], S.sO[CROSS ? 2 * i + 1 : 0][CROSS ? ty : 0][tx])
+                             : pack2(ownY[(2 * i) * CHS_Y], ownY[(2 * i + 1) * CHS_Y]);
 #pragma unroll
             for (int i = 0; i < kC2; i += 2) {
                 s0 = fma2(e[i], e[i], s0);
@@ -343,7 +385,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 float a;
                 lossacc[2 * j] += pair<CHS_Y, GRAD>(ownY - s * TX, e, G, tq[j * GY * TX], w_f, P.gcoef[2 * j], a);
                 if (affs_b && live) affs_b[(uint32_t)(2 * j) * Nu] = a;
-                if (GRAD) {
+                if (REV) {
                     // rows below the image are zero fill in the weight box: pair dropped
                     float a2;
                     pair<CHS_Y, true>(ownY + s * TX, e, G, tq[j * GY * TX + s * TX],
@@ -357,7 +399,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         // ---------------- x part
         mbar_wait(&barX, phX & 1u);
         if (patch) {
-            const float* src = P.emb + (int64_t)b * kC * Nu;
+            const float* src = P.par + (int64_t)b * kC * Nu;
             float* sXf = &S.sX[0][0][0];
             for (int idx = threadIdx.x; idx < TY * XW; idx += NT) {
                 const int row = idx / XW, col = idx - row * XW;
@@ -396,7 +438,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 float a;
                 lossacc[2 * j + 1] += pair<CHS_X, GRAD>(ownX - s, e, G, tq[j * TY * GX], w_f, P.gcoef[2 * j + 1], a);
                 if (affs_b && live) affs_b[(uint32_t)(2 * j + 1) * Nu] = a;
-                if (GRAD) {
+                if (REV) {
                     float a2;
                     pair<CHS_X, true>(ownX + s, e, G, tq[j * TY * GX + s], wq[j * TY * GX + s] * mask_sq<MASK>(mkx[j][1]),
                                       P.gcoef[2 * j + 1], a2);
@@ -460,13 +502,14 @@ static bool canon_shifts(const OffsetTable& tab, int* shifts) {
     return true;
 }
 
-bool canon2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, bool cross, const float* emb, const float* target,
-                      const float* weight) {
+bool canon2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, const float* emb, const float* partner,
+                      const float* target, const float* weight) {
     int sh[c2::NS];
-    if (C != 16 || D != 1 || cross || !canon_shifts(tab, sh)) return false;
-    if ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(weight)) & 15)
+    if (C != 16 || D != 1 || !canon_shifts(tab, sh)) return false;
+    if ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(partner) | reinterpret_cast<uintptr_t>(target) |
+         reinterpret_cast<uintptr_t>(weight)) & 15)
         return false;
-    // the hand fill of edge tiles maps coordinates through wrap3 (-n <= v < 4n); TMA needs a 16-byte row pitch
+    // the hand patch of edge tiles maps coordinates through wrap3 (-n <= v < 4n); TMA needs a 16-byte row pitch
     if (W % 4 != 0 || H < 32 || W < 64) return false;
     return (int64_t)16 * H * W < ((int64_t)1 << 31);
 }
@@ -489,35 +532,50 @@ int canon2d_blocks(int B, int H, int W) {
     return canon_grid(B * ((H + c2::TY - 1) / c2::TY) * ((W + c2::TX - 1) / c2::TX));
 }
 
-template <int MASK>
+template <int MASK, bool CROSS>
 static int launch_canon_m(const CUtensorMap* m, const c2::Params& P, int grid, cudaStream_t st) {
-    const size_t smem = sizeof(c2::Stage) + 128;
+    const size_t smem = sizeof(c2::Stage<CROSS>) + 128;
     cudaError_t e;
     if (P.grad) {
-        auto kern = c2::fused2d_canon<MASK, true>;
+        auto kern = c2::fused2d_canon<MASK, true, CROSS>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, c2::NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+        kern<<<grid, c2::NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], P);
     } else {
-        auto kern = c2::fused2d_canon<MASK, false>;
+        auto kern = c2::fused2d_canon<MASK, false, CROSS>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        kern<<<grid, c2::NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+        kern<<<grid, c2::NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], P);
     }
     return (int)cudaGetLastError();
 }
 
-int launch_canon2d(const float* emb, const Dims& d, const OffsetTable& tab, int wrap, const float* target, const float* weight,
-                   const void* mask, int mask_dtype, float* affs, float* partials, float* grad, cudaStream_t st) {
+template <bool CROSS>
+static int launch_canon_c(const float* emb, const float* partner, const Dims& d, c2::Params& P, const float* target,
+                          const float* weight, int mask_dtype, cudaStream_t st) {
+    using G_ = c2::Geo<CROSS>;
+    const float* staged = CROSS ? partner : emb;
+    CUtensorMap m[7];
+    int rc;
+    if ((rc = encode_volume_map(&m[0], staged, d.B, 16, 1, d.H, d.W, c2::TX, G_::YR, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&m[1], staged, d.B, 16, 1, d.H, d.W, G_::XW, c2::TY, 1, 16))) return rc;
+    // every second channel from the start coordinate: 5 planes (c0, c0 + 2, .., c0 + 8) per copy
+    if ((rc = encode_volume_map(&m[2], target, d.B, c2::K, 1, d.H, d.W, c2::TX, G_::GY, 1, c2::K - 1, 0, 2))) return rc;
+    if ((rc = encode_volume_map(&m[3], weight, d.B, c2::K, 1, d.H, d.W, c2::TX, G_::GY, 1, c2::K - 1, 0, 2))) return rc;
+    if ((rc = encode_volume_map(&m[4], target, d.B, c2::K, 1, d.H, d.W, G_::GX, c2::TY, 1, c2::K - 1, 0, 2))) return rc;
+    if ((rc = encode_volume_map(&m[5], weight, d.B, c2::K, 1, d.H, d.W, G_::GX, c2::TY, 1, c2::K - 1, 0, 2))) return rc;
+    if ((rc = encode_volume_map(&m[6], emb, d.B, 16, 1, d.H, d.W, c2::TX, c2::TY, 1, 16))) return rc;  // CROSS: own tile
+    P.par = staged;
+    const int grid = canon_grid(P.n_tiles);
+    if (mask_dtype == PEA_MASK_U8) return launch_canon_m<PEA_MASK_U8, CROSS>(m, P, grid, st);
+    if (mask_dtype == PEA_MASK_F32) return launch_canon_m<PEA_MASK_F32, CROSS>(m, P, grid, st);
+    return launch_canon_m<PEA_MASK_NONE, CROSS>(m, P, grid, st);
+}
+
+// `partner` != nullptr: two-view loss, gradient w.r.t. the anchor view only
+int launch_canon2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap, const float* target,
+                   const float* weight, const void* mask, int mask_dtype, float* affs, float* partials, float* grad,
+                   cudaStream_t st) {
     c2::Params P;
     if (!canon_shifts(tab, P.shift)) return PEA_E_MODE;
-    CUtensorMap m[6];
-    int rc;
-    if ((rc = encode_volume_map(&m[0], emb, d.B, 16, 1, d.H, d.W, c2::TX, c2::YR, 1, 16))) return rc;
-    if ((rc = encode_volume_map(&m[1], emb, d.B, 16, 1, d.H, d.W, c2::XW, c2::TY, 1, 16))) return rc;
-    // every second channel from the start coordinate: 5 planes (c0, c0 + 2, .., c0 + 8) per copy
-    if ((rc = encode_volume_map(&m[2], target, d.B, c2::K, 1, d.H, d.W, c2::TX, c2::GY, 1, c2::K - 1, 0, 2))) return rc;
-    if ((rc = encode_volume_map(&m[3], weight, d.B, c2::K, 1, d.H, d.W, c2::TX, c2::GY, 1, c2::K - 1, 0, 2))) return rc;
-    if ((rc = encode_volume_map(&m[4], target, d.B, c2::K, 1, d.H, d.W, c2::GX, c2::TY, 1, c2::K - 1, 0, 2))) return rc;
-    if ((rc = encode_volume_map(&m[5], weight, d.B, c2::K, 1, d.H, d.W, c2::GX, c2::TY, 1, c2::K - 1, 0, 2))) return rc;
     P.B = d.B; P.H = d.H; P.W = d.W; P.wrap = wrap;
     P.tiles_x = (d.W + c2::TX - 1) / c2::TX;
     P.tiles_y = (d.H + c2::TY - 1) / c2::TY;
@@ -525,10 +583,8 @@ int launch_canon2d(const float* emb, const Dims& d, const OffsetTable& tab, int 
     for (int k = 0; k < c2::K; ++k) P.gcoef[k] = tab.gcoef[k];
     P.emb = emb; P.target = target; P.weight = weight; P.mask = mask;
     P.affs = affs; P.grad = grad; P.partials = partials;
-    const int grid = canon_grid(P.n_tiles);
-    if (mask_dtype == PEA_MASK_U8) return launch_canon_m<PEA_MASK_U8>(m, P, grid, st);
-    if (mask_dtype == PEA_MASK_F32) return launch_canon_m<PEA_MASK_F32>(m, P, grid, st);
-    return launch_canon_m<PEA_MASK_NONE>(m, P, grid, st);
+    if (partner) return launch_canon_c<true>(emb, partner, d, P, target, weight, mask_dtype, st);
+    return launch_canon_c<false>(emb, partner, d, P, target, weight, mask_dtype, st);
 }
 
 }  // namespace pea

@@ -114,6 +114,27 @@ __device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int 
     f32x2 xq[kC2];
 #pragma unroll
     for (int i = 0; i < kC2; ++i) xq[i] = pack2(nb[(2 * i) * chs], nb[(2 * i + 1) * chs]);
+#ifdef PEA_DOT_SCALAR
+    // the dot product reads three distinct register pairs per FFMA2 (3.5 clk on the register-bandwidth-bound packed
+    // pipe, tools/microbench_mix.cu): two scalar FFMAs take 2.8 clk
+    f32x2 ss0 = 0ull, ss1 = 0ull;
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kC2; i += 2) {
+        ss0 = fma2(xq[i], xq[i], ss0);
+        ss1 = fma2(xq[i + 1], xq[i + 1], ss1);
+    }
+#pragma unroll
+    for (int i = 0; i < kC2; ++i) {
+        float e0, e1, x0, x1;
+        unpack2(e[i], e0, e1);
+        unpack2(xq[i], x0, x1);
+        d0 = fmaf(e0, x0, d0);
+        d1 = fmaf(e1, x1, d1);
+    }
+    const float rq = inv_norm(hsum2(ss0, ss1));
+    const float a = (d0 + d1) * rq;
+#else
     f32x2 ss0 = 0ull, ss1 = 0ull, d0 = 0ull, d1 = 0ull;  // bit pattern of (+0.f, +0.f)
 #pragma unroll
     for (int i = 0; i < kC2; i += 2) {
@@ -124,6 +145,7 @@ __device__ __forceinline__ float inplane_pair(const float* __restrict__ nb, int 
     }
     const float rq = inv_norm(hsum2(ss0, ss1));
     const float a = hsum2(d0, d1) * rq;
+#endif
     a_out = a;
     const float diff = a - t;
     if (GRAD) {

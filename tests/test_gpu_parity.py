@@ -720,10 +720,10 @@ def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, shifts, monkeypatch):
 @pytest.mark.parametrize("B,H,W,border", [(2, 130, 160, "wrap"), (1, 75, 100, "wrap"), (2, 64, 72, "zero"), (1, 131, 200, "zero")])
 @pytest.mark.parametrize("mask_kind", ["u8", "f32", "none"])
 def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, mask_kind, monkeypatch):
-    """multi_offset([1, 3, 5, 9, 11], 4) (one view) takes the fully unrolled canonical kernel; with PEA_NO_CANON set the
-    same call takes the table-driven axis-aligned kernel, with IMPL_GENERIC the generic one.  All three must agree
-    (1e-5 of the largest magnitude) on loss, affinities and gradient: both borders, partial tiles in x and y, every
-    mask type, with and without gradient."""
+    """multi_offset([1, 3, 5, 9, 11], 4) takes the fully unrolled canonical kernel (one view, and two views with the
+    second one constant); with PEA_NO_CANON set the same call takes the table-driven axis-aligned kernel, with
+    IMPL_GENERIC the generic one.  All three must agree (1e-5 of the largest magnitude) on loss, affinities and
+    gradient: both borders, partial tiles in x and y, every mask type, both view counts, with and without gradient."""
     from pea_b200 import _ops as ops
     offsets = O.multi_offset([1, 3, 5, 9, 11], neighbor=4)
     offs3 = ops.offsets3(offsets, 2)
@@ -731,6 +731,8 @@ def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, 
     g = torch.Generator().manual_seed(B * 1000 + H)
     emb = torch.randn((B, 16, 1, H, W), generator=g).cuda()
     emb[0, :, 0, 3, 5] = 0.0
+    par = torch.randn((B, 16, 1, H, W), generator=g).cuda()
+    par[0, :, 0, 7, 9] = 0.0
     tgt = (torch.rand((B, K, 1, H, W), generator=g) > 0.5).float().cuda()
     wgt = (torch.rand((B, K, 1, H, W), generator=g) * 2 + 0.1).cuda()
     m8 = (torch.rand((B, K, 1, H, W), generator=g) > 0.2).to(torch.uint8).cuda()
@@ -738,7 +740,7 @@ def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, 
     bd = ops.BORDER_WRAP if border == "wrap" else ops.BORDER_ZERO
     norm = np.full(K, float(B * W), np.float32)
     coef = np.linspace(0.5, 1.5, K).astype(np.float32)
-    for grad in (True, False):
+    for grad, partner in ((True, None), (False, None), (True, par), (False, par)):
         outs = {}
         for name in ("canon", "axis", "generic"):
             if name == "axis":
@@ -746,7 +748,7 @@ def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, 
             else:
                 monkeypatch.delenv("PEA_NO_CANON", raising=False)
             impl = ops.IMPL_GENERIC if name == "generic" else ops.IMPL_AUTO
-            lo, a, gr, _ = ops.affs_loss_fwd_bwd(emb, None, offs3, bd, tgt, wgt, msk, norm, coef, want_affs=True,
+            lo, a, gr, _ = ops.affs_loss_fwd_bwd(emb, partner, offs3, bd, tgt, wgt, msk, norm, coef, want_affs=True,
                                                  want_grad=grad, impl=impl)
             outs[name] = (lo.cpu(), a.cpu(), gr.cpu() if grad else None)
         monkeypatch.delenv("PEA_NO_CANON", raising=False)

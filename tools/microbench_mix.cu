@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(512, 1) mix_kernel(float* out, int iters) {
     f32x2 e[8], G[8], G2[8];
     float es[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { e[i] = pack2(0.1f * i + tx * 0.001f, 0.05f * i); G[i] = 0ull; G2[i] = 0ull; es[2 * i] = 0.1f * i; es[2 * i + 1] = 0.05f * i + tx * 0.001f; }
+    for (int i = 0; i < 8; ++i) { e[i] = pack2(0.1f * i + tx * 0.001f, 0.05f * i); G[i] = 0ull; G2[i] = 0ull; es[2 * i] = 0.1f * i + tx * 0.002f; es[2 * i + 1] = 0.05f * i + tx * 0.001f; }
     float Gs[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) Gs[i] = 0.f;
@@ -60,6 +60,61 @@ __global__ void __launch_bounds__(512, 1) mix_kernel(float* out, int iters) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) G[i] = fma2(gr2, xq[i], G[i]);
             loss += w * diff * diff;
+        } else if (V == 7 || V == 8 || V == 9) {
+            // hybrids: ss always packed (two distinct register pairs); 7: dot scalar, G packed; 8: dot + G scalar; 9: G scalar
+            float xs[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xs[i] = nb[i * CHS];
+            f32x2 ss0 = 0ull, ss1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                ss0 = fma2(pack2(xs[2 * i], xs[2 * i + 1]), pack2(xs[2 * i], xs[2 * i + 1]), ss0);
+                ss1 = fma2(pack2(xs[2 * i + 2], xs[2 * i + 3]), pack2(xs[2 * i + 2], xs[2 * i + 3]), ss1);
+            }
+            float dsum;
+            if (V == 9) {
+                f32x2 d0 = 0ull, d1 = 0ull;
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    d0 = fma2(e[i], pack2(xs[2 * i], xs[2 * i + 1]), d0);
+                    d1 = fma2(e[i + 1], pack2(xs[2 * i + 2], xs[2 * i + 3]), d1);
+                }
+                dsum = hsum2(d0, d1);
+            } else {
+                float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    d0 = fmaf(es[i], xs[i], d0);
+                    d1 = fmaf(es[i + 1], xs[i + 1], d1);
+                }
+                dsum = d0 + d1;
+            }
+            const float rq = inv_norm(hsum2(ss0, ss1));
+            const float a = dsum * rq, diff = a - t, gr = gco * w * diff * rq;
+            if (V == 7) {
+                const f32x2 gr2 = pack2(gr, gr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) G[i] = fma2(gr2, pack2(xs[2 * i], xs[2 * i + 1]), G[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Gs[i] = fmaf(gr, xs[i], Gs[i]);
+            }
+            loss += w * diff * diff;
+        } else if (V == 10) {  // 24 FFMA2 of the form (x, x, acc): two distinct register pairs
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) G[i] = fma2(e[i], e[i], G[i]);
+        } else if (V == 11) {  // 24 FFMA2 of the form (scalar broadcast, x, acc)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) G[i] = fma2(pack2(es[i + r], es[i + r]), e[i], G[i]);
+        } else if (V == 12) {  // 48 scalar FFMA with three distinct registers
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Gs[i] = fmaf(es[i], es[(i + 1) & 15], Gs[i]);
         } else if (V == 2) {
             float xq[16];
 #pragma unroll
@@ -168,6 +223,12 @@ int main() {
     run<4>("4 FFMA2 x24 only", sms, out, 1);
     run<5>("5 two pairs interleaved", sms, out, 2);
     run<6>("6 lane-packed two neighbours", sms, out, 2);
+    run<7>("7 ss packed, dot scalar", sms, out, 1);
+    run<8>("8 ss packed, dot+G scalar", sms, out, 1);
+    run<9>("9 ss+dot packed, G scalar", sms, out, 1);
+    run<10>("10 FFMA2 (x,x,acc) x24", sms, out, 1);
+    run<11>("11 FFMA2 (s.F32,x,acc) x24", sms, out, 1);
+    run<12>("12 FFMA x48 (3 distinct)", sms, out, 1);
     CK(cudaFree(out));
     return 0;
 }
