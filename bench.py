@@ -414,6 +414,55 @@ def time_gt(P, w, device, iters=20):
             "algorithmic_bytes": per_voxel * vox, "timing": "back-to-back calls, working set may sit in L2"}
 
 
+def time_labels_pipeline(P, w, device, flush, iters=20):
+    """2-D, labels resident on the device -> loss + gradient: this package's two-step route (GT kernels, then the fused
+    loss) against the label-driven loss kernel (target / mask / weight never materialised).
+    L2 flushed between iterations (untimed), per-iteration CUDA events."""
+    lab = torch.tensor(make_labels(w, 0)).to(device)
+    lab32 = lab.to(torch.int32)
+    offsets = P.multi_offset(w["shifts"], 4)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    emb = torch.randn((w["B"], C) + tuple(w["spatial"]), generator=g).to(device)
+    crit = P.WeightedMSE()
+    e = emb.clone().requires_grad_(True)
+
+    def two_step():
+        tgt, msk, wgt = P.make_targets_2d(lab, offsets)
+        loss, _, _ = P.embedding_loss(e, tgt, wgt, msk, crit, offsets)
+        loss.backward()
+        e.grad = None
+        return loss
+
+    def fused():
+        loss, _, _ = P.embedding_loss_labels(e, lab32, crit, offsets)
+        loss.backward()
+        e.grad = None
+        return loss
+
+    out = {}
+    for name, fn in (("two_step", two_step), ("fused", fused)):
+        for _ in range(3):
+            fn()
+        per = []
+        for _ in range(iters):
+            flush.zero_()
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            loss = fn()
+            t.record()
+            torch.cuda.synchronize()
+            per.append(s.elapsed_time(t))
+        out[name + "_ms"] = statistics.median(per)
+        out[name + "_loss"] = float(loss.detach())
+    K = 2 * len(w["shifts"])
+    vox = w["B"] * int(np.prod(w["spatial"]))
+    per_voxel = 4 * C + 2 * 4 + 4 * C + 4 * K   # read E + labels (twice: count pass, loss) + write grad + affs
+    out.update({"workload": "labels -> loss + gradient, " + w["descr"], "value": K * vox / (out["fused_ms"] * 1e-3),
+                "unit": UNIT, "algorithmic_bytes": per_voxel * vox, "hbm_gbs": per_voxel * vox / (out["fused_ms"] * 1e-3) / 1e9,
+                "timing": "eager launches (no CUDA graph), median of per-iteration CUDA events, L2 flushed"})
+    return out
+
+
 def cpu_baseline(w, seconds=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -498,6 +547,8 @@ def run_ours(args, rank, world, local_rank):
             for name in ("cfg2", "cfg3"):
                 also["gt_" + name] = time_gt(P, WORKLOADS[name], device)
                 also["gt_" + name]["roofline_frac"] = also["gt_" + name]["hbm_gbs"] / peak
+            also["cfg2_labels"] = time_labels_pipeline(P, WORKLOADS["cfg2"], device, flush)
+            also["cfg2_labels"]["roofline_frac"] = also["cfg2_labels"]["hbm_gbs"] / peak
             torch.cuda.empty_cache()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

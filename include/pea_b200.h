@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PEA_ABI_VERSION 3
+#define PEA_ABI_VERSION 4
 #define PEA_MAX_OFFSETS 64
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -155,6 +155,26 @@ size_t pea_gt_counts_bytes(int B, int K);
 int pea_gt_targets(const void* labels, int label_dtype, int B, int D, int H, int W,
                    const int32_t* offsets, int K, int semantics, int ignore, int padding, double alpha,
                    float* target, uint8_t* mask, float* weight, void* counts, size_t counts_bytes, void* stream);
+
+/* Label-driven fused 2-D loss (the step before the path -- the reference's Dataset.__getitem__,
+ * scripts_cvppp/data/data_provider.py:204-225 -- folded into the path).  Two calls:
+ *   pea_gt_pair_weights       labels -> wtab (device, B*K*2 floats): the two values the class-balance weight map of each
+ *                             (sample, channel) takes where the target is 1 / 0 (weight_binary_ratio of the
+ *                             gen_affs_ours / seg_to_aff target, counted without materialising the target);
+ *   pea_affs_loss_labels_fwd_bwd   embedding + int32 labels + wtab -> loss, affinities, gradient, with
+ *                             target = gen_affs_ours(labels, offsets, ignore, padding)[0], mask = [1] (pairs across the
+ *                             image edge dropped) and weight derived inside the kernel: results equal
+ *                             pea_gt_targets followed by pea_affs_loss_fwd_bwd with a uint8 mask.
+ * Only the canonical 2-D tables multi_offset(shifts <= 12, neighbor=4) with C = 16 are implemented: anything else
+ * returns PEA_E_MODE and the caller takes the two-step route.  counts: device scratch of pea_gt_counts_bytes(B, K). */
+int pea_gt_pair_weights(const void* labels, int label_dtype, int B, int D, int H, int W,
+                        const int32_t* offsets, int K, int semantics, int ignore, int padding, double alpha,
+                        float* wtab, void* counts, size_t counts_bytes, void* stream);
+int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* labels, int B, int C, int H, int W,
+                                 const int32_t* offsets, int K, int border, int ignore, const float* wtab,
+                                 const float* loss_norm, const float* loss_coef,
+                                 float* affs, float* loss_out, float* grad_emb,
+                                 void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

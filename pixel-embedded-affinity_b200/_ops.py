@@ -288,3 +288,44 @@ def gt_targets(labels4, offsets3_, semantics, ignore=False, padding=True, alpha=
                                 nbytes, _stream())
     check("pea_gt_targets", rc)
     return target, mask, weight
+
+
+def gt_pair_weights(labels4, offsets3_, semantics, ignore=False, padding=True, alpha=1.0):
+    """labels (B,D,H,W) CUDA tensor -> wtab (B,K,2) f32: the value weight_binary_ratio gives the (sample, channel)'s
+    weight map where its target is 1 / where it is 0, counted without materialising the target."""
+    B, D, H, W = labels4.shape
+    offs = np.asarray(offsets3_, dtype=np.int32).reshape(-1, 3)
+    K = offs.shape[0]
+    dev = labels4.device
+    wtab = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    nbytes = lib.pea_gt_counts_bytes(B, K)
+    counts = torch.empty(nbytes // 8, dtype=torch.int64, device=dev)
+    keep, optr = _i32(offs)
+    with torch.cuda.device(dev):
+        rc = lib.pea_gt_pair_weights(_ptr(labels4), label_code(labels4), B, D, H, W, optr, K, int(semantics),
+                                     int(bool(ignore)), int(bool(padding)), float(alpha), _ptr(wtab), _ptr(counts), nbytes,
+                                     _stream())
+    check("pea_gt_pair_weights", rc)
+    return wtab
+
+
+def affs_loss_labels_fwd_bwd(emb, labels_i32, offs3, border, ignore, wtab, loss_norm, loss_coef, want_affs=True,
+                             want_grad=True):
+    """Label-driven fused 2-D loss (canonical tables only; PeaError with code PEA_E_MODE otherwise).
+    Returns (loss_out (1+K,), affs or None, grad_emb or None)."""
+    B, C, D, H, W = _dims5(emb)
+    K = offs3.shape[0]
+    dev = emb.device
+    affs = torch.empty((B, K) + tuple(emb.shape[2:]), dtype=torch.float32, device=dev) if want_affs else None
+    grad = torch.empty_like(emb) if want_grad else None
+    loss_out = torch.empty(1 + K, dtype=torch.float32, device=dev)
+    ws, n = _workspace(B, C, 1, H, W, K, False, dev)
+    keep_o, optr = _i32(offs3)
+    keep_n, nptr = _f32(loss_norm)
+    keep_c, cptr = _f32(loss_coef)
+    with torch.cuda.device(dev):
+        rc = lib.pea_affs_loss_labels_fwd_bwd(_ptr(emb), _ptr(labels_i32), B, C, H, W, optr, K, border, int(bool(ignore)),
+                                              _ptr(wtab), nptr, cptr, _ptr(affs), _ptr(loss_out), _ptr(grad), _ptr(ws), n,
+                                              _stream())
+    check("pea_affs_loss_labels_fwd_bwd", rc)
+    return loss_out, affs, grad

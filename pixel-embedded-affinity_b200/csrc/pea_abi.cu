@@ -45,6 +45,8 @@ int canon2d_blocks(int B, int H, int W);
 int launch_canon2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap, const float* target,
                    const float* weight, const void* mask, int mask_dtype, float* affs, float* partials, float* grad,
                    cudaStream_t st);
+int launch_canon2d_labels(const float* emb, const int32_t* labels, const float* wtab, int ignore, const Dims& d,
+                          const OffsetTable& tab, int wrap, float* affs, float* partials, float* grad, cudaStream_t st);
 int launch_axis2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap,
                   const float* target, const float* weight, const void* mask, int mask_dtype, float* affs, float* partials,
                   float* grad, cudaStream_t st);
@@ -312,6 +314,38 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
                               target, weight, mask, mask_dtype, nullptr, affs, ws.partials, grad_emb, grad_partner, st);
     if (rc) return rc;
     finalize_loss_kernel<<<1, 1024, 0, st>>>(ws.partials, generic_partial_blocks((int64_t)B * d.N), K, sc, loss_out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* labels, int B, int C, int H, int W,
+                                            const int32_t* offsets, int K, int border, int ignore, const float* wtab,
+                                            const float* loss_norm, const float* loss_coef, float* affs, float* loss_out,
+                                            float* grad_emb, void* workspace, size_t ws_bytes, void* stream) {
+    if (!emb || !labels || !offsets || !wtab || !loss_norm || !loss_coef || !loss_out || !workspace) return PEA_E_NULL;
+    Dims d;
+    int rc = check_volume(B, C, 1, H, W, K, d);
+    if (rc) return rc;
+    if (border != PEA_BORDER_WRAP && border != PEA_BORDER_ZERO) return PEA_E_MODE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
+    if ((reinterpret_cast<uintptr_t>(labels) | reinterpret_cast<uintptr_t>(wtab)) & 3) return PEA_E_ALIGN;
+    Workspace ws;
+    carve(workspace, B, d.N, K, 0, ws);
+    if (ws_bytes < ws.bytes) return PEA_E_WORKSPACE;
+    OffsetTable tab;
+    fill_offsets(offsets, K, tab);
+    LossScale sc;
+    for (int k = 0; k < K; ++k) {
+        sc.norm[k] = loss_norm[k];
+        sc.coef[k] = loss_coef[k];
+        tab.gcoef[k] = (float)(2.0 * (double)loss_coef[k] / (double)loss_norm[k]);
+    }
+    // the label plane is staged by TMA like the embedding: 16-byte aligned base
+    if (!canon2d_eligible(C, 1, H, W, tab, emb, emb, emb, reinterpret_cast<const float*>(labels))) return PEA_E_MODE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* parts = ws.rinvE;
+    if ((rc = launch_canon2d_labels(emb, labels, wtab, ignore, d, tab, border == PEA_BORDER_WRAP, affs, parts, grad_emb, st)))
+        return rc;
+    finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, canon2d_blocks(B, H, W), K, sc, loss_out);
     return (int)cudaGetLastError();
 }
 

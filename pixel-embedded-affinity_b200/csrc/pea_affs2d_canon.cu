@@ -115,20 +115,27 @@ struct Params {
     const float* target;
     const float* weight;
     const void* mask;
+    const int32_t* labels;  // LAB: (B, H, W) instance labels
+    const float* wtab;      // LAB: [B][K][2] weight where the target is 1 / where it is 0 (pea_gt_pair_weights)
+    int ignore;             // LAB: gen_affs_ours(ignore=...)
     float* affs;      // may be null
     float* grad;      // may be null
     float* partials;  // [gridDim.x][K]
 };
 
-template <bool CROSS>
+// LAB: target / mask / weight are derived in the kernel from the instance labels (staged like the embedding boxes, one
+// plane) and a per-(sample, channel) table of the two class-balance weight values: no target / weight groups at all.
+template <bool CROSS, bool LAB>
 struct alignas(128) Stage {
     float sY[kC][Geo<CROSS>::YR][TX];   // staged view, rows y0 - 12 .. (SELF: y0 + 27)
     float sX[kC][TY][Geo<CROSS>::XW];   // staged view, cols x0 - 12 .. (SELF: x0 + 43)
-    float tY[NS][Geo<CROSS>::GY][TX];   // target, y channels (0, 2, .., 8), rows y0 .. (SELF: y0 + 27)
-    float wY[NS][Geo<CROSS>::GY][TX];   // weight
-    float tX[NS][TY][Geo<CROSS>::GX];   // target, x channels (1, 3, .., 9), cols x0 .. (SELF: x0 + 47)
-    float wX[NS][TY][Geo<CROSS>::GX];
+    float tY[LAB ? 1 : NS][LAB ? 1 : Geo<CROSS>::GY][TX];   // target, y channels (0, 2, .., 8), rows y0 .. (SELF: y0 + 27)
+    float wY[LAB ? 1 : NS][LAB ? 1 : Geo<CROSS>::GY][TX];   // weight
+    float tX[LAB ? 1 : NS][LAB ? 1 : TY][Geo<CROSS>::GX];   // target, x channels (1, 3, .., 9), cols x0 .. (SELF: x0 + 47)
+    float wX[LAB ? 1 : NS][LAB ? 1 : TY][Geo<CROSS>::GX];
     float sO[CROSS ? kC : 1][CROSS ? TY : 1][TX];  // CROSS: the anchor view's own tile
+    int32_t lY[LAB ? Geo<CROSS>::YR : 1][TX];      // LAB: labels of the y-column box
+    int32_t lX[LAB ? TY : 1][Geo<CROSS>::XW];      // LAB: labels of the x-row box
 };
 
 // One neighbour q of the own pixel p (raw values, channels CHS floats apart): a = <e^_p, e^_q>,
@@ -189,7 +196,7 @@ __device__ __forceinline__ float mask_sq(uint32_t raw) {
     return m * m;
 }
 
-template <int MASK, bool GRAD, bool CROSS>
+template <int MASK, bool GRAD, bool CROSS, bool LAB = false>
 __global__ void __launch_bounds__(NT, 1)
 fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX,
               const __grid_constant__ CUtensorMap mapTy, const __grid_constant__ CUtensorMap mapWy,
@@ -199,13 +206,15 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     constexpr int YR = G_::YR, XW = G_::XW, CHS_Y = G_::CHS_Y, CHS_X = G_::CHS_X, GY = G_::GY, GX = G_::GX;
     constexpr bool REV = GRAD && !CROSS;  // the pair anchored at p + s, whose partner is p, contributes to grad(p)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Stage<CROSS>& S = *reinterpret_cast<Stage<CROSS>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    static_assert(!(LAB && (CROSS || MASK != PEA_MASK_NONE)), "label-driven flavour: one view, mask derived in the kernel");
+    Stage<CROSS, LAB>& S = *reinterpret_cast<Stage<CROSS, LAB>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    __shared__ float s_w[K][2];
     __shared__ uint64_t barY, barX;
     __shared__ uint32_t cntY, cntX;
     __shared__ float s_red[K][TY];
     constexpr uint32_t kWarps = TY;
-    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.tY) + sizeof(S.wY) + (CROSS ? sizeof(S.sO) : 0);
-    constexpr uint32_t kBytesX = sizeof(S.sX) + sizeof(S.tX) + sizeof(S.wX);
+    constexpr uint32_t kBytesY = sizeof(S.sY) + (LAB ? sizeof(S.lY) : sizeof(S.tY) + sizeof(S.wY)) + (CROSS ? sizeof(S.sO) : 0);
+    constexpr uint32_t kBytesX = sizeof(S.sX) + (LAB ? sizeof(S.lX) : sizeof(S.tX) + sizeof(S.wX));
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int H = P.H, W = P.W;
@@ -221,20 +230,28 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     };
     // every box of the tile lies inside the image (circular border: TMA's zero fill would be wrong outside)
     auto tile_inner = [&](int y0, int x0) {
-        return y0 >= PM && y0 - PM + YR <= H && y0 + GY <= H && x0 >= PM && x0 - PM + XW <= W && x0 + GX <= W;
+        return y0 >= PM && y0 - PM + YR <= H && (LAB || y0 + GY <= H) && x0 >= PM && x0 - PM + XW <= W && (LAB || x0 + GX <= W);
     };
     auto issueY = [&](int b, int y0, int x0) {
         mbar_arrive_expect_tx(&barY, kBytesY);
         tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - PM, 0, 0, b);
-        tma_load_5d(&S.tY[0][0][0], &mapTy, &barY, x0, y0, 0, 0, b);
-        tma_load_5d(&S.wY[0][0][0], &mapWy, &barY, x0, y0, 0, 0, b);
+        if (LAB) {  // mapTy / mapTx describe the label plane with the embedding boxes' footprints
+            tma_load_5d(&S.lY[0][0], &mapTy, &barY, x0, y0 - PM, 0, 0, b);
+        } else {
+            tma_load_5d(&S.tY[0][0][0], &mapTy, &barY, x0, y0, 0, 0, b);
+            tma_load_5d(&S.wY[0][0][0], &mapWy, &barY, x0, y0, 0, 0, b);
+        }
         if (CROSS) tma_load_5d(&S.sO[0][0][0], &mapO, &barY, x0, y0, 0, 0, b);
     };
     auto issueX = [&](int b, int y0, int x0) {
         mbar_arrive_expect_tx(&barX, kBytesX);
         tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - PM, y0, 0, 0, b);
-        tma_load_5d(&S.tX[0][0][0], &mapTx, &barX, x0, y0, 0, 1, b);
-        tma_load_5d(&S.wX[0][0][0], &mapWx, &barX, x0, y0, 0, 1, b);
+        if (LAB) {
+            tma_load_5d(&S.lX[0][0], &mapTx, &barX, x0 - PM, y0, 0, 0, b);
+        } else {
+            tma_load_5d(&S.tX[0][0][0], &mapTx, &barX, x0, y0, 0, 1, b);
+            tma_load_5d(&S.wX[0][0][0], &mapWx, &barX, x0, y0, 0, 1, b);
+        }
     };
 
     float lossacc[K];
@@ -254,10 +271,17 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     }
     __syncthreads();
     uint32_t phY = 0, phX = 0, it = 0;
+    int b_tab = -1;
 
     for (; t < n_tiles; t += (int)gridDim.x, ++it) {
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
+        if (LAB && b != b_tab) {  // CTA-uniform: the sample's weight pairs (a CTA changes sample a handful of times)
+            __syncthreads();
+            if (threadIdx.x < 2 * K) (&s_w[0][0])[threadIdx.x] = P.wtab[(int64_t)b * 2 * K + threadIdx.x];
+            __syncthreads();
+            b_tab = b;
+        }
         int bn = 0, y0n = 0, x0n = 0;
         const bool has_next = t + (int)gridDim.x < n_tiles;
         if (has_next) tile_origin(t + (int)gridDim.x, bn, y0n, x0n);
@@ -333,6 +357,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             }
             const float* tg = P.target + sample;
             const float* wg = P.weight + sample;
+            if (!LAB)  // labels are never patched: gen_affs_ours does not wrap, pairs across the image edge are masked out
             for (int idx = threadIdx.x; idx < GY * TX; idx += NT) {
                 const int gy = y0 + (idx >> 5), gx = x0 + (idx & 31);
                 if (gy < H && gx < W) continue;
@@ -381,15 +406,32 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 const int s = P.shift[j];
                 // zero border: a partner outside the image is zero fill (a == 0) and the pair is dropped
                 const bool vf = live && (wrap || y >= s);
-                const float w_f = vf ? wq[j * GY * TX] * mask_sq<MASK>(mky[j][0]) : 0.f;
+                float t_f, w_f, t_r = 0.f, w_r = 0.f;
+                if (LAB) {
+                    // gen_affs_ours: same label (ignore: and both non-zero); the mask drops pairs across the image edge
+                    const int32_t* lq = &S.lY[LAB ? ty + PM : 0][tx];
+                    const int32_t lp = lq[0], lm = lq[LAB ? -s * TX : 0], ll = lq[LAB ? s * TX : 0];
+                    const bool same_f = lp == lm && (!P.ignore || (lp != 0 && lm != 0));
+                    const bool same_r = ll == lp && (!P.ignore || (lp != 0 && ll != 0));
+                    t_f = same_f ? 1.f : 0.f;
+                    w_f = (live && y >= s) ? s_w[2 * j][same_f ? 0 : 1] : 0.f;
+                    t_r = same_r ? 1.f : 0.f;
+                    w_r = (y + s < H) ? s_w[2 * j][same_r ? 0 : 1] : 0.f;
+                } else {
+                    t_f = tq[j * GY * TX];
+                    w_f = vf ? wq[j * GY * TX] * mask_sq<MASK>(mky[j][0]) : 0.f;
+                    if (REV) {
+                        t_r = tq[j * GY * TX + s * TX];
+                        w_r = wq[j * GY * TX + s * TX] * mask_sq<MASK>(mky[j][1]);
+                    }
+                }
                 float a;
-                lossacc[2 * j] += pair<CHS_Y, GRAD>(ownY - s * TX, e, G, tq[j * GY * TX], w_f, P.gcoef[2 * j], a);
+                lossacc[2 * j] += pair<CHS_Y, GRAD>(ownY - s * TX, e, G, t_f, w_f, P.gcoef[2 * j], a);
                 if (affs_b && live) affs_b[(uint32_t)(2 * j) * Nu] = a;
                 if (REV) {
                     // rows below the image are zero fill in the weight box: pair dropped
                     float a2;
-                    pair<CHS_Y, true>(ownY + s * TX, e, G, tq[j * GY * TX + s * TX],
-                                      wq[j * GY * TX + s * TX] * mask_sq<MASK>(mky[j][1]), P.gcoef[2 * j], a2);
+                    pair<CHS_Y, true>(ownY + s * TX, e, G, t_r, w_r, P.gcoef[2 * j], a2);
                 }
             }
         }
@@ -414,6 +456,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             }
             const float* tg = P.target + sample;
             const float* wg = P.weight + sample;
+            if (!LAB)
             for (int idx = threadIdx.x; idx < TY * GX; idx += NT) {
                 const int row = idx / GX, col = idx - row * GX;
                 const int gy = y0 + row, gx = x0 + col;
@@ -434,14 +477,30 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             for (int j = 0; j < NS; ++j) {
                 const int s = P.shift[j];
                 const bool vf = live && (wrap || x >= s);
-                const float w_f = vf ? wq[j * TY * GX] * mask_sq<MASK>(mkx[j][0]) : 0.f;
+                float t_f, w_f, t_r = 0.f, w_r = 0.f;
+                if (LAB) {
+                    const int32_t* lq = &S.lX[LAB ? ty : 0][tx + PM];
+                    const int32_t lp = lq[0], lm = lq[LAB ? -s : 0], ll = lq[LAB ? s : 0];
+                    const bool same_f = lp == lm && (!P.ignore || (lp != 0 && lm != 0));
+                    const bool same_r = ll == lp && (!P.ignore || (lp != 0 && ll != 0));
+                    t_f = same_f ? 1.f : 0.f;
+                    w_f = (live && x >= s) ? s_w[2 * j + 1][same_f ? 0 : 1] : 0.f;
+                    t_r = same_r ? 1.f : 0.f;
+                    w_r = (x + s < W) ? s_w[2 * j + 1][same_r ? 0 : 1] : 0.f;
+                } else {
+                    t_f = tq[j * TY * GX];
+                    w_f = vf ? wq[j * TY * GX] * mask_sq<MASK>(mkx[j][0]) : 0.f;
+                    if (REV) {
+                        t_r = tq[j * TY * GX + s];
+                        w_r = wq[j * TY * GX + s] * mask_sq<MASK>(mkx[j][1]);
+                    }
+                }
                 float a;
-                lossacc[2 * j + 1] += pair<CHS_X, GRAD>(ownX - s, e, G, tq[j * TY * GX], w_f, P.gcoef[2 * j + 1], a);
+                lossacc[2 * j + 1] += pair<CHS_X, GRAD>(ownX - s, e, G, t_f, w_f, P.gcoef[2 * j + 1], a);
                 if (affs_b && live) affs_b[(uint32_t)(2 * j + 1) * Nu] = a;
                 if (REV) {
                     float a2;
-                    pair<CHS_X, true>(ownX + s, e, G, tq[j * TY * GX + s], wq[j * TY * GX + s] * mask_sq<MASK>(mkx[j][1]),
-                                      P.gcoef[2 * j + 1], a2);
+                    pair<CHS_X, true>(ownX + s, e, G, t_r, w_r, P.gcoef[2 * j + 1], a2);
                 }
             }
         }
@@ -532,16 +591,16 @@ int canon2d_blocks(int B, int H, int W) {
     return canon_grid(B * ((H + c2::TY - 1) / c2::TY) * ((W + c2::TX - 1) / c2::TX));
 }
 
-template <int MASK, bool CROSS>
+template <int MASK, bool CROSS, bool LAB = false>
 static int launch_canon_m(const CUtensorMap* m, const c2::Params& P, int grid, cudaStream_t st) {
-    const size_t smem = sizeof(c2::Stage<CROSS>) + 128;
+    const size_t smem = sizeof(c2::Stage<CROSS, LAB>) + 128;
     cudaError_t e;
     if (P.grad) {
-        auto kern = c2::fused2d_canon<MASK, true, CROSS>;
+        auto kern = c2::fused2d_canon<MASK, true, CROSS, LAB>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
         kern<<<grid, c2::NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], P);
     } else {
-        auto kern = c2::fused2d_canon<MASK, false, CROSS>;
+        auto kern = c2::fused2d_canon<MASK, false, CROSS, LAB>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
         kern<<<grid, c2::NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], P);
     }
@@ -582,9 +641,37 @@ int launch_canon2d(const float* emb, const float* partner, const Dims& d, const 
     P.n_tiles = d.B * P.tiles_x * P.tiles_y;
     for (int k = 0; k < c2::K; ++k) P.gcoef[k] = tab.gcoef[k];
     P.emb = emb; P.target = target; P.weight = weight; P.mask = mask;
+    P.labels = nullptr; P.wtab = nullptr; P.ignore = 0;
     P.affs = affs; P.grad = grad; P.partials = partials;
     if (partner) return launch_canon_c<true>(emb, partner, d, P, target, weight, mask_dtype, st);
     return launch_canon_c<false>(emb, partner, d, P, target, weight, mask_dtype, st);
+}
+
+// Label-driven flavour: target = gen_affs_ours(labels, offsets, ignore, padding)[0], mask = [1], weight =
+// weight_binary_ratio per (sample, channel) -- all derived inside the loss kernel from the int32 label plane and the
+// weight-pair table of pea_gt_pair_weights: 172 instead of 258 algorithmic bytes per pixel.
+int launch_canon2d_labels(const float* emb, const int32_t* labels, const float* wtab, int ignore, const Dims& d,
+                          const OffsetTable& tab, int wrap, float* affs, float* partials, float* grad, cudaStream_t st) {
+    c2::Params P;
+    if (!canon_shifts(tab, P.shift)) return PEA_E_MODE;
+    using G_ = c2::Geo<false>;
+    const float* lab = reinterpret_cast<const float*>(labels);  // 4-byte elements, copied bit for bit
+    CUtensorMap m[7];
+    int rc;
+    if ((rc = encode_volume_map(&m[0], emb, d.B, 16, 1, d.H, d.W, c2::TX, G_::YR, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&m[1], emb, d.B, 16, 1, d.H, d.W, G_::XW, c2::TY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&m[2], lab, d.B, 1, 1, d.H, d.W, c2::TX, G_::YR, 1, 1))) return rc;
+    if ((rc = encode_volume_map(&m[4], lab, d.B, 1, 1, d.H, d.W, G_::XW, c2::TY, 1, 1))) return rc;
+    m[3] = m[2]; m[5] = m[4]; m[6] = m[0];  // unused by this flavour
+    P.B = d.B; P.H = d.H; P.W = d.W; P.wrap = wrap;
+    P.tiles_x = (d.W + c2::TX - 1) / c2::TX;
+    P.tiles_y = (d.H + c2::TY - 1) / c2::TY;
+    P.n_tiles = d.B * P.tiles_x * P.tiles_y;
+    for (int k = 0; k < c2::K; ++k) P.gcoef[k] = tab.gcoef[k];
+    P.emb = emb; P.par = emb; P.target = nullptr; P.weight = nullptr; P.mask = nullptr;
+    P.labels = labels; P.wtab = wtab; P.ignore = ignore;
+    P.affs = affs; P.grad = grad; P.partials = partials;
+    return launch_canon_m<PEA_MASK_NONE, false, true>(m, P, canon_grid(P.n_tiles), st);
 }
 
 }  // namespace pea

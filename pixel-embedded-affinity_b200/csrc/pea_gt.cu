@@ -237,7 +237,7 @@ gt_fused_x4(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int 
             }
             const uint32_t o = (uint32_t)k * N + p;
             if (PASS == 1) {
-                if (live) {
+                if (live && target) {  // target == nullptr: counts only (pea_gt_pair_weights)
                     *reinterpret_cast<float4*>(out + o) = make_float4(a[0], a[1], a[2], a[3]);
                     if (mout) *reinterpret_cast<uint32_t*>(mout + o) = (inb & 1u) | ((inb & 2u) << 7) | ((inb & 4u) << 14) | ((inb & 8u) << 21);
                 }
@@ -278,6 +278,43 @@ static int run_gt_fused(const void* labels, int B, int D, int H, int W, const Gt
                                                  mask, counts, weight);
     gt_fused_x4<L, MODE, 2><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, alpha, target,
                                                  mask, counts, weight);
+    return (int)cudaGetLastError();
+}
+
+// per-(sample, channel) counts -> the two values of the class-balance weight map: wtab[2 i] where the target is 1,
+// wtab[2 i + 1] where it is 0 (weight_binary_ratio, scripts_cvppp/data/data_segmentation.py:205-228; same float64
+// arithmetic as PASS 2 above, so a loss kernel that derives its weights from this table sees bit-identical values)
+__global__ void gt_weight_table_kernel(const unsigned long long* __restrict__ counts, int n, unsigned long long N, double alpha,
+                                       float* __restrict__ wtab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long cnt = counts[i];
+    float w_pos = 1.f, w_neg = 1.f;
+    if (cnt != 0ull && cnt != N) {
+        double wf = (double)cnt / (double)N;
+        wf = fmin(fmax(wf, 5e-2), 0.99);
+        if (wf > 0.5) w_neg = (float)(alpha * wf / (1.0 - wf));
+        else w_pos = (float)(alpha * (1.0 - wf) / wf);
+    }
+    wtab[2 * i] = w_pos;
+    wtab[2 * i + 1] = w_neg;
+}
+
+template <typename L, int MODE>
+static int run_gt_weights(const void* labels, int B, int D, int H, int W, const GtTable& tab, int ignore, int padding,
+                          double alpha, float* wtab, unsigned long long* counts, cudaStream_t st) {
+    const int64_t N = (int64_t)D * H * W;
+    int64_t chunks = (148 * 8 + B - 1) / B;
+    const int64_t max_chunks = (N / 4 + 1023) / 1024;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)B * tab.K * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    gt_fused_x4<L, MODE, 1><<<grid, 256, 0, st>>>(static_cast<const L*>(labels), D, H, W, tab, ignore, padding, alpha, nullptr,
+                                                 nullptr, counts, nullptr);
+    const int n = B * tab.K;
+    gt_weight_table_kernel<<<(n + 127) / 128, 128, 0, st>>>(counts, n, (unsigned long long)N, alpha, wtab);
     return (int)cudaGetLastError();
 }
 
@@ -420,4 +457,38 @@ extern "C" int pea_gt_targets(const void* labels, int label_dtype, int B, int D,
         default: return PEA_E_DTYPE;
     }
 #undef PEA_GT_CASE
+}
+
+extern "C" int pea_gt_pair_weights(const void* labels, int label_dtype, int B, int D, int H, int W, const int32_t* offsets,
+                                   int K, int semantics, int ignore, int padding, double alpha, float* wtab, void* counts,
+                                   size_t counts_bytes, void* stream) {
+    if (!labels || !offsets || !wtab || !counts) return PEA_E_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535) return PEA_E_SHAPE;
+    if (K < 1 || K > PEA_MAX_OFFSETS) return PEA_E_OFFSETS;
+    if (semantics != 0 && semantics != 1) return PEA_E_MODE;
+    if (counts_bytes < pea_gt_counts_bytes(B, K)) return PEA_E_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(counts) % 8) return PEA_E_ALIGN;
+    if (W % 4 != 0 || (int64_t)K * D * H * W >= ((int64_t)1 << 31)) return PEA_E_SHAPE;
+    GtTable tab;
+    tab.K = K;
+    for (int k = 0; k < K; ++k) { tab.dz[k] = offsets[3 * k]; tab.dy[k] = offsets[3 * k + 1]; tab.dx[k] = offsets[3 * k + 2]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* c = static_cast<unsigned long long*>(counts);
+#define PEA_GW_CASE(CODE, TYPE)                                                                                        \
+    case CODE:                                                                                                         \
+        return semantics == 0 ? run_gt_weights<TYPE, 0>(labels, B, D, H, W, tab, ignore, padding, alpha, wtab, c, st)  \
+                              : run_gt_weights<TYPE, 1>(labels, B, D, H, W, tab, ignore, padding, alpha, wtab, c, st);
+    switch (label_dtype) {
+        PEA_GW_CASE(PEA_LABEL_U8, uint8_t)
+        PEA_GW_CASE(PEA_LABEL_U16, uint16_t)
+        PEA_GW_CASE(PEA_LABEL_U32, uint32_t)
+        PEA_GW_CASE(PEA_LABEL_U64, uint64_t)
+        PEA_GW_CASE(PEA_LABEL_S8, int8_t)
+        PEA_GW_CASE(PEA_LABEL_S16, int16_t)
+        PEA_GW_CASE(PEA_LABEL_S32, int32_t)
+        PEA_GW_CASE(PEA_LABEL_S64, int64_t)
+        PEA_GW_CASE(PEA_LABEL_F32, float)
+        default: return PEA_E_DTYPE;
+    }
+#undef PEA_GW_CASE
 }

@@ -10,7 +10,8 @@ import numpy as np
 import torch
 
 from . import _ops as ops
-from ._autograd import Affinities, FusedAffinityLoss, LossList, OpSpec
+from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, LossList, OpSpec
+from ._lib import PeaError
 from .loss import is_weighted_mse
 
 
@@ -93,3 +94,41 @@ def ema_embedding_loss(embedding, ema_embedding, target, weightmap, mask, criter
     affs = Affinities.apply(embedding, ema_embedding, offs3, ops.BORDER_WRAP, ops.IMPL_AUTO)
     loss, _ = _generic_criterion(affs, target, weightmap, mask, criterion, [affs0_weight if k < 2 else 1 for k in range(K)])
     return loss, affs
+
+
+def embedding_loss_labels(embedding, labels, criterion, offsets, affs0_weight=1, mode='ours', ignore=False, padding=True,
+                          alpha=1.0):
+    """Training-loop form of ``embedding_loss``: takes the instance labels (B,H,W) instead of
+    (target, weightmap, mask) and equals
+
+        target, mask = gen_affs_ours(labels[b], offsets, ignore, padding)       (utils/affinity_ours.py:17-39)
+        weightmap[b, k] = weight_binary_ratio(target[k], alpha=alpha)           (data/data_segmentation.py:205-228)
+        embedding_loss(embedding, target, weightmap, mask, criterion, offsets)  (:18-47)
+
+    i.e. what ``data_provider.py:204-225`` prepares on the host per sample.  For the canonical tables
+    ``multi_offset(shifts <= 12, neighbor=4)`` with ``WeightedMSE`` the three GT tensors never exist: one counting pass
+    over the labels, then the loss kernel derives target / mask / weight itself (172 instead of 258 bytes per pixel,
+    and no GT generation pass).  Everything else takes the two-step route.  Returns (loss, affs, all_loss)."""
+    _check_mode(mode)
+    embedding = ops.check_embedding("embedding", embedding, 4)
+    B, C, H, W = embedding.shape
+    if labels.dim() != 3 or tuple(labels.shape) != (B, H, W) or not labels.is_cuda:
+        raise ValueError(f"labels must be a CUDA tensor of shape {(B, H, W)}, got {tuple(labels.shape)}")
+    offs3 = ops.offsets3(offsets, 2)
+    K = offs3.shape[0]
+    if is_weighted_mse(criterion) and W % 4 == 0 and not labels.dtype.is_floating_point:
+        lab = labels.contiguous()
+        lab32 = lab if lab.dtype == torch.int32 else lab.to(torch.int32)
+        spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), np.ones(K, np.float32), affs_differentiable=True)
+        try:
+            wtab = ops.gt_pair_weights(lab32[:, None], offs3, 0, ignore, padding, alpha)
+            loss, affs, each = FusedAffinityLossLabels.apply(embedding, lab32, wtab, bool(ignore), spec)
+            return loss, affs, LossList(each)
+        except PeaError as ex:
+            if ex.code != -8:  # PEA_E_MODE: not a canonical table / shape -- two-step route below
+                raise
+    if alpha != 1.0:
+        raise NotImplementedError("alpha != 1 is implemented on the fused label-driven path only")
+    from .gt import make_targets_2d
+    target, mask, weight = make_targets_2d(labels, offsets, ignore, padding)
+    return embedding_loss(embedding, target, weight, mask, criterion, offsets, affs0_weight, mode)

@@ -759,6 +759,50 @@ def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, 
                 close_t(outs["canon"][2], outs[other][2], what=f"grad vs {other}")
 
 
+@pytest.mark.parametrize("B,H,W,shifts,ldtype,ignore", [
+    (2, 130, 160, [1, 3, 5, 9, 11], np.uint8, False),    # canonical table: GT derived inside the loss kernel
+    (1, 75, 100, [1, 3, 5, 9, 11], np.int32, True),      # partial tiles in x and y, ignore=True
+    (1, 64, 96, [1, 2, 4, 8, 12], np.uint8, False),
+    (1, 67, 96, [1, 3, 5, 9, 27], np.uint8, False),      # CVPPP table: two-step route behind the same call
+])
+def test_embedding_loss_labels_equals_gt_then_loss(P, O, B, H, W, shifts, ldtype, ignore):
+    """embedding_loss_labels(embedding, labels, ...) == gen_affs_ours + weight_binary_ratio per (sample, channel) +
+    embedding_loss: against this package's own two-step route and against the oracle's (the reference's data-provider
+    recipe, scripts_cvppp/data/data_provider.py:204-225), loss / affinities / gradient within 1e-5."""
+    offsets = O.multi_offset(shifts, neighbor=4)
+    rng = np.random.RandomState(B * 100 + H)
+    labs = np.stack([O.voronoi_labels((H, W), 9, 40 + b, background_frac=0.3, dtype=np.uint8) for b in range(B)]).astype(ldtype)
+    emb = rng.randn(B, 16, H, W).astype(np.float32)
+    emb[0, :, 3, 5] = 0.0
+    lab_d = torch.tensor(labs).cuda()
+    e = dev(emb, True)
+    l, a, al = P.embedding_loss_labels(e, lab_d, P.WeightedMSE(), offsets, ignore=ignore)
+    l.backward()
+    # two-step route of this package
+    tgt, msk, wgt = P.make_targets_2d(lab_d, offsets, ignore=ignore, padding=True)
+    e2 = dev(emb, True)
+    l2, a2, al2 = P.embedding_loss(e2, tgt, wgt, msk, P.WeightedMSE(), offsets)
+    l2.backward()
+    close_s(float(l.detach()), float(l2.detach()), what="loss vs two-step")
+    close_t(a.detach().cpu(), a2.detach().cpu(), what="affs vs two-step")
+    close_t(e.grad.cpu(), e2.grad.cpu(), what="grad vs two-step")
+    close_t(np.asarray(list(al)), np.asarray(list(al2)), what="all_loss vs two-step")
+    # oracle: the reference's host-side recipe
+    to, mo, wo = [], [], []
+    for b in range(B):
+        t_, m_ = O.gen_affs_ours(labs[b], offsets, ignore=ignore, padding=True)
+        to.append(t_)
+        mo.append(m_)
+        wo.append(np.stack([O.weight_binary_ratio(c) for c in t_]))
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao, _ = O.embedding_loss(eo, torch.tensor(np.stack(to)), torch.tensor(np.stack(wo)), torch.tensor(np.stack(mo)),
+                                 O.WeightedMSE(), offsets)
+    lo.backward()
+    close_s(float(l.detach()), lo, what="loss vs oracle")
+    close_t(a.detach().cpu(), ao, what="affs vs oracle")
+    close_t(e.grad.cpu(), eo.grad, what="grad vs oracle")
+
+
 # =========================================================================== forward-only tiled kernel + z-shards
 @pytest.mark.parametrize("B,D,H,W,seed", [(1, 18, 64, 96, 91), (2, 7, 37, 44, 92), (1, 5, 28, 28, 93)])
 def test_tiled3d_forward_matches_generic_and_oracle(P, O, B, D, H, W, seed):
