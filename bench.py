@@ -215,7 +215,7 @@ def our_step(P, w, e, tgt, wgt, msk, offsets, crit, partner=None):
 LAUNCHES_PER_STEP = 3  # fused3d_norm5_tm, finalize_loss, scale_inplace (profiles/r1_launches_bench_cfg3.csv)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused kernel at cfg3, from the committed
 # `ncu --set full` capture (profiles/r1_fused3d_tm_cfg3.txt); the algorithmic figure is 501.35 MB
-NCU_TRAFFIC_BYTES = {"cfg3": 304.79e6 + 166.37e6, "cfg2": 454.19e6 + 273.47e6}
+NCU_TRAFFIC_BYTES = {"cfg3": 304.79e6 + 166.37e6, "cfg2": 456.13e6 + 270.55e6}  # cfg2: profiles/r1_fused2d_canon_cfg2.txt
 
 
 def time_workload(P, w, steps, warmup, device, flush, dist_on):

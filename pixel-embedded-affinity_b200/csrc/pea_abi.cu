@@ -55,6 +55,37 @@ int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, 
                          const float* target, const float* weight, float* affs, float* partials, float* grad,
                          cudaStream_t st);
 
+#ifndef PEA_PDL
+#define PEA_PDL 1  // 0: plain stream-ordered launches of the two tail kernels (A/B)
+#endif
+// Programmatic dependent launch (sm_90+): the small tail kernels (loss finalize, gradient scale) are queued behind the
+// preceding kernel with the "programmatic stream serialization" attribute, so their launch latency overlaps the tail of
+// that kernel; they block in griddepcontrol.wait until it has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() {
+#if PEA_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_tail(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+#if PEA_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+#else
+    kern<<<grid, block, 0, st>>>(static_cast<KArgs>(args)...);
+    return cudaGetLastError();
+#endif
+}
+
 struct LossScale {
     float norm[PEA_MAX_OFFSETS];
     float coef[PEA_MAX_OFFSETS];
@@ -68,6 +99,7 @@ __global__ void __launch_bounds__(1024) finalize_loss_kernel(const float* __rest
                                                              LossScale sc, float* __restrict__ loss_out) {
     __shared__ double s_acc[1024];
     __shared__ float s_loss[PEA_MAX_OFFSETS];
+    pdl_wait();  // launched as a programmatic dependent of the kernel that writes the partials
     const int G = 1024 / K;
     const int k = threadIdx.x % K, g = threadIdx.x / K;
     double acc = 0.0;
@@ -103,6 +135,7 @@ __global__ void __launch_bounds__(1024) finalize_loss_kernel(const float* __rest
 
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ buf, int64_t n,
                                                             const float* __restrict__ scale) {
+    pdl_wait();
     const float s = __ldg(scale);
     if (s == 1.0f) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,8 +307,7 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         if ((rc = launch_canon2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts,
                                  grad_emb, st)))
             return rc;
-        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, canon2d_blocks(B, H, W), K, sc, loss_out);
-        return (int)cudaGetLastError();
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, canon2d_blocks(B, H, W), K, sc, loss_out);
     }
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC &&
         B <= 65535 &&
@@ -286,16 +318,14 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         if ((rc = launch_axis2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts,
                                 grad_emb, st)))
             return rc;
-        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, axis2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
-        return (int)cudaGetLastError();
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, axis2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
     }
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC) {
         float* parts = ws.rinvE;
         if ((rc = launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs,
                                  parts, grad_emb, st)))
             return rc;
-        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, tiled2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
-        return (int)cudaGetLastError();
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, tiled2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
     }
     const bool tiled_ok = tiled3_ok;
     if (tiled_ok && impl != PEA_IMPL_GENERIC) {
@@ -304,17 +334,15 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         rc = cross ? launch_cross3d_norm5(emb, partner, d, tab, target, weight, affs, parts, grad_emb, st)
                    : launch_fused3d_norm5(emb, d, tab, target, weight, affs, parts, grad_emb, st);
         if (rc) return rc;
-        finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, cross ? cross3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W),
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, cross ? cross3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W),
                                                  K, sc, loss_out);
-        return (int)cudaGetLastError();
     }
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
     rc = launch_fused_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP, cross,
                               target, weight, mask, mask_dtype, nullptr, affs, ws.partials, grad_emb, grad_partner, st);
     if (rc) return rc;
-    finalize_loss_kernel<<<1, 1024, 0, st>>>(ws.partials, generic_partial_blocks((int64_t)B * d.N), K, sc, loss_out);
-    return (int)cudaGetLastError();
+    return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, ws.partials, generic_partial_blocks((int64_t)B * d.N), K, sc, loss_out);
 }
 
 extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* labels, int B, int C, int H, int W,
@@ -345,8 +373,7 @@ extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* lab
     float* parts = ws.rinvE;
     if ((rc = launch_canon2d_labels(emb, labels, wtab, ignore, d, tab, border == PEA_BORDER_WRAP, affs, parts, grad_emb, st)))
         return rc;
-    finalize_loss_kernel<<<1, 1024, 0, st>>>(parts, canon2d_blocks(B, H, W), K, sc, loss_out);
-    return (int)cudaGetLastError();
+    return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, canon2d_blocks(B, H, W), K, sc, loss_out);
 }
 
 extern "C" int pea_affs_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
@@ -378,6 +405,5 @@ extern "C" int pea_scale_inplace(float* buf, int64_t n, const float* scale, void
     if (n <= 0) return PEA_E_SHAPE;
     int64_t g = (n / 4 + 255) / 256;
     const int grid = (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
-    scale_inplace_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, n, scale);
-    return (int)cudaGetLastError();
+    return (int)launch_tail(scale_inplace_kernel, grid, 256, static_cast<cudaStream_t>(stream), buf, n, scale);
 }
