@@ -803,6 +803,63 @@ def test_embedding_loss_labels_equals_gt_then_loss(P, O, B, H, W, shifts, ldtype
     close_t(e.grad.cpu(), eo.grad, what="grad vs oracle")
 
 
+@pytest.mark.parametrize("shifts,two_view,labels", [([1, 3, 5, 9, 11], False, False), ([1, 3, 5, 9, 11], True, False),
+                                                     ([1, 3, 5, 9, 11], False, True), ([1, 3, 5, 9, 27], False, False),
+                                                     ([1, 3, 5, 9, 27], True, False)])
+def test_2d_kernels_write_only_their_outputs(P, O, shifts, two_view, labels):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): affinities, gradient, loss vector and workspace
+    are carved out of larger poisoned buffers and handed to the C ABI directly; at a shape with partial tiles in x and
+    y (75 x 100) the persistent 2-D kernels must leave every byte outside their outputs untouched, and write every
+    element inside them."""
+    import ctypes
+    from pea_b200 import _ops as ops
+    from pea_b200._lib import lib, check
+    B, C, H, W = 2, 16, 75, 100
+    offsets = O.multi_offset(shifts, neighbor=4)
+    offs3 = ops.offsets3(offsets, 2)
+    K = offs3.shape[0]
+    g = torch.Generator().manual_seed(7)
+    emb = torch.randn((B, C, H, W), generator=g).cuda()
+    par = torch.randn((B, C, H, W), generator=g).cuda() if two_view else None
+    tgt = (torch.rand((B, K, H, W), generator=g) > 0.5).float().cuda()
+    wgt = (torch.rand((B, K, H, W), generator=g) + 0.1).cuda()
+    msk = (torch.rand((B, K, H, W), generator=g) > 0.2).to(torch.uint8).cuda()
+    lab = torch.tensor(np.stack([O.voronoi_labels((H, W), 7, 60 + b, dtype=np.uint8) for b in range(B)]).astype(np.int32)).cuda()
+    POISON, PAD = -12345.0, 4096
+
+    def guarded(n):
+        buf = torch.full((n + 2 * PAD,), POISON, dtype=torch.float32, device="cuda")
+        return buf, buf[PAD:PAD + n]
+
+    affs_buf, affs = guarded(B * K * H * W)
+    grad_buf, grad = guarded(B * C * H * W)
+    loss_buf, loss = guarded(1 + K)
+    nws = lib.pea_workspace_bytes(B, C, 1, H, W, K, int(two_view))
+    ws_buf, ws = guarded((nws + 3) // 4)
+    norm = (ctypes.c_float * K)(*([float(B * W)] * K))
+    coef = (ctypes.c_float * K)(*([1.0] * K))
+    offs = (ctypes.c_int32 * (3 * K))(*[int(v) for v in offs3.reshape(-1)])
+    st = torch.cuda.current_stream().cuda_stream
+    if labels:
+        wtab = ops.gt_pair_weights(lab[:, None], offs3, 0)
+        rc = lib.pea_affs_loss_labels_fwd_bwd(emb.data_ptr(), lab.data_ptr(), B, C, H, W, offs, K, ops.BORDER_WRAP, 0,
+                                              wtab.data_ptr(), norm, coef, affs.data_ptr(), loss.data_ptr(), grad.data_ptr(),
+                                              ws.data_ptr(), nws, st)
+        check("pea_affs_loss_labels_fwd_bwd", rc)
+    else:
+        rc = lib.pea_affs_loss_fwd_bwd(emb.data_ptr(), par.data_ptr() if two_view else None, B, C, 1, H, W, offs, K,
+                                       ops.BORDER_WRAP, ops.IMPL_AUTO, tgt.data_ptr(), wgt.data_ptr(), msk.data_ptr(), ops.MASK_U8,
+                                       norm, coef, affs.data_ptr(), loss.data_ptr(), grad.data_ptr(), None, ws.data_ptr(), nws, st)
+        check("pea_affs_loss_fwd_bwd", rc)
+    torch.cuda.synchronize()
+    for name, buf, n in (("affs", affs_buf, B * K * H * W), ("grad", grad_buf, B * C * H * W), ("loss", loss_buf, 1 + K),
+                         ("workspace", ws_buf, (nws + 3) // 4)):
+        assert bool((buf[:PAD] == POISON).all()) and bool((buf[PAD + n:] == POISON).all()), f"{name}: guard band overwritten"
+    for name, out in (("affs", affs), ("grad", grad), ("loss", loss)):
+        assert not bool((out == POISON).any()), f"{name}: elements left unwritten"
+        assert bool(torch.isfinite(out).all()), f"{name}: non-finite values"
+
+
 # =========================================================================== forward-only tiled kernel + z-shards
 @pytest.mark.parametrize("B,D,H,W,seed", [(1, 18, 64, 96, 91), (2, 7, 37, 44, 92), (1, 5, 28, 28, 93)])
 def test_tiled3d_forward_matches_generic_and_oracle(P, O, B, D, H, W, seed):
