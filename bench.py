@@ -463,6 +463,45 @@ def time_labels_pipeline(P, w, device, flush, iters=20):
     return out
 
 
+def time_inference_epilogue(P, device, shape=(100, 1024, 1024), iters=5):
+    """cfg4 on one GPU with what the reference's inference loop does next (scripts_ac3ac4/inference.py:160-165: three
+    border copies + F.relu): torch epilogue on the plain result vs relu / replicate_border folded into the call."""
+    D, H, W = shape
+    g = torch.Generator(device=device).manual_seed(5)
+    emb = torch.empty((1, C, D, H, W), device=device).normal_(generator=g)
+
+    def torch_epilogue():
+        pred = P.inf_embedding_loss_norm5(emb)
+        pred[:, 1, :, :1, :] = pred[:, 1, :, 1:2, :]
+        pred[:, 2, :, :, :1] = pred[:, 2, :, :, 1:2]
+        pred[:, 0, :1, :, :] = pred[:, 0, 1:2, :, :]
+        return torch.relu(pred)
+
+    def fused():
+        return P.inf_embedding_loss_norm5(emb, relu=True, replicate_border=True)
+
+    out = {}
+    for name, fn in (("torch_epilogue", torch_epilogue), ("fused", fused)):
+        for _ in range(2):
+            r = fn()
+        del r
+        torch.cuda.synchronize()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            r = fn()
+            del r
+        t.record()
+        torch.cuda.synchronize()
+        out[name + "_ms"] = s.elapsed_time(t) / iters
+    vox = int(np.prod(shape))
+    out.update({"workload": "cfg4 forward + border replicate + relu (inference.py:160-165), 1 GPU",
+                "value": 12 * vox / (out["fused_ms"] * 1e-3), "unit": "aff-voxels/s (forward only)"})
+    del emb
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline(w, seconds=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -547,6 +586,7 @@ def run_ours(args, rank, world, local_rank):
             for name in ("cfg2", "cfg3"):
                 also["gt_" + name] = time_gt(P, WORKLOADS[name], device)
                 also["gt_" + name]["roofline_frac"] = also["gt_" + name]["hbm_gbs"] / peak
+            also["cfg4_epilogue"] = time_inference_epilogue(P, device)
             also["cfg2_labels"] = time_labels_pipeline(P, WORKLOADS["cfg2"], device, flush)
             also["cfg2_labels"]["roofline_frac"] = also["cfg2_labels"]["hbm_gbs"] / peak
             torch.cuda.empty_cache()

@@ -64,6 +64,9 @@ extern "C" {
 #define PEA_IMPL_AUTO 0
 #define PEA_IMPL_GENERIC 1 /* table-driven gather kernel, any offsets */
 #define PEA_IMPL_TILED 2   /* shared-memory / register-tiled kernels for axis-aligned offset sets */
+/* Epilogue flag, or-ed into `impl` of pea_affs_fwd: store max(a, 0) -- the caller-side F.relu(pred) of
+ * scripts_ac3ac4/inference.py:165, scripts_cvppp/main.py:312 folded into the kernel's store. */
+#define PEA_EPI_RELU 0x100
 
 int pea_abi_version(void);
 const char* pea_strerror(int code);
@@ -155,6 +158,14 @@ size_t pea_gt_counts_bytes(int B, int K);
 int pea_gt_targets(const void* labels, int label_dtype, int B, int D, int H, int W,
                    const int32_t* offsets, int K, int semantics, int ignore, int padding, double alpha,
                    float* target, uint8_t* mask, float* weight, void* counts, size_t counts_bytes, void* stream);
+
+/* The border fix-up that follows the 3-D affinities in the reference's training / inference loops
+ * (scripts_ac3ac4/main.py:233-236, inference.py:161-163), in place:
+ *   affs[:, 0, :shift] = affs[:, 0, shift:2 shift];  affs[:, 1, :, :shift] = affs[:, 1, :, shift:2 shift];
+ *   affs[:, 2, :, :, :shift] = affs[:, 2, :, :, shift:2 shift]
+ * affs (B,K>=3,D,H,W) with `plane` elements between channel planes (0 = D*H*W); extents smaller than 2 shift on an
+ * axis leave that channel untouched.  One launch over the three thin slabs. */
+int pea_replicate_first(float* affs, int B, int K, int D, int H, int W, int64_t plane, int shift, void* stream);
 
 /* Label-driven fused 2-D loss (the step before the path -- the reference's Dataset.__getitem__,
  * scripts_cvppp/data/data_provider.py:204-225 -- folded into the path).  Two calls:

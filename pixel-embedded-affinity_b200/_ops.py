@@ -106,7 +106,10 @@ def _workspace(B, C, D, H, W, K, cross, device):
     return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
-def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None, halo=None):
+EPI_RELU = 0x100  # PEA_EPI_RELU: or-ed into the impl hint of pea_affs_fwd
+
+
+def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None, halo=None, relu=False):
     """(B,C,[D,]H,W) -> (B,K,[D - z_skip,]H,W) affinities.  emb/partner already validated.
 
     ``emb`` may be a z-range view ``buf[:, :, z0:z1]`` of a contiguous (B,C,Dtot,H,W) buffer and ``out`` a z-range
@@ -151,11 +154,12 @@ def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None, halo=No
     ws, n = _workspace(B, C, D, H, W, K, partner is not None, emb.device)
     keep, optr = _i32(offs3)
     with torch.cuda.device(emb.device):
-        rc = lib.pea_affs_fwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, int(z_skip), emb_plane,
-                              affs_plane, _ptr(halo), halo_n, halo_plane, _ptr(affs), _ptr(ws), n, _stream())
+        rc = lib.pea_affs_fwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl | (EPI_RELU if relu else 0),
+                              int(z_skip), emb_plane, affs_plane, _ptr(halo), halo_n, halo_plane, _ptr(affs), _ptr(ws), n,
+                              _stream())
     if rc == -8 and emb_plane and impl != IMPL_TILED and halo is None:
         # z-range view that the tiled kernel cannot take (shape / offsets): fall back to a contiguous copy
-        return affs_fwd(emb.contiguous(), partner, offs3, border, impl, z_skip, out)
+        return affs_fwd(emb.contiguous(), partner, offs3, border, impl, z_skip, out, relu=relu)
     check("pea_affs_fwd", rc)
     return affs
 
@@ -329,3 +333,15 @@ def affs_loss_labels_fwd_bwd(emb, labels_i32, offs3, border, ignore, wtab, loss_
                                               _stream())
     check("pea_affs_loss_labels_fwd_bwd", rc)
     return loss_out, affs, grad
+
+
+def replicate_first(affs, shift=1):
+    """In place: affs[:, 0, :s] = affs[:, 0, s:2s]; affs[:, 1, :, :s] = affs[:, 1, :, s:2s]; affs[:, 2, ..., :s] = ...[s:2s]
+    (scripts_ac3ac4/main.py:233-236) on a contiguous (B,K>=3,D,H,W) float32 CUDA tensor."""
+    if affs.dim() != 5 or not affs.is_cuda or affs.dtype != torch.float32 or not affs.is_contiguous():
+        raise ValueError("affs must be a contiguous (B,K,D,H,W) float32 CUDA tensor")
+    B, K, D, H, W = affs.shape
+    with torch.cuda.device(affs.device):
+        rc = lib.pea_replicate_first(_ptr(affs), B, K, D, H, W, 0, int(shift), _stream())
+    check("pea_replicate_first", rc)
+    return affs

@@ -9,7 +9,7 @@ namespace pea {
 int generic_partial_blocks(int64_t total);
 int launch_rinv(const float* emb, int C, const Dims& d, float* rinv, cudaStream_t st);
 int launch_fwd_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C, const Dims& d,
-                       const OffsetTable& tab, int wrap, int z_skip, int64_t affs_plane, float* affs, cudaStream_t st);
+                       const OffsetTable& tab, int wrap, int z_skip, int64_t affs_plane, float* affs, int relu, cudaStream_t st);
 int launch_fused_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C,
                          const Dims& d, const OffsetTable& tab, int wrap, int cross, const float* target,
                          const float* weight, const void* mask, int mask_dtype, const float* upstream, float* affs,
@@ -24,7 +24,7 @@ int cross3d_norm5_blocks(int B, int H, int W);
 bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
                           int64_t emb_plane);
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
-                       const float* halo, int halo_n, int64_t halo_plane, cudaStream_t st);
+                       const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
 
@@ -225,6 +225,8 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
                             int64_t affs_plane, const float* halo, int halo_slices, int64_t halo_plane, float* affs,
                             void* workspace, size_t ws_bytes, void* stream) {
     if (!emb || !offsets || !affs || !workspace) return PEA_E_NULL;
+    const int relu = (impl & PEA_EPI_RELU) ? 1 : 0;
+    impl &= ~PEA_EPI_RELU;
     if (impl != PEA_IMPL_AUTO && impl != PEA_IMPL_GENERIC && impl != PEA_IMPL_TILED) return PEA_E_MODE;
     Dims d;
     int rc = check_volume(B, C, D, H, W, K, d);
@@ -247,13 +249,14 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool contiguous = emb_plane == d.N;
     const bool plain = contiguous && z_skip == 0 && affs_plane == d.N;
-    const bool tiled2_ok = plain && tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, false);
+    const bool tiled2_ok = plain && !relu && tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, false);
     const bool tiled3_ok = tiled3d_fwd_eligible(C, W, tab, border, cross != 0, emb, emb_plane);
     if (impl == PEA_IMPL_TILED && !tiled2_ok && !tiled3_ok) return PEA_E_MODE;
     if (halo && (!tiled3_ok || impl == PEA_IMPL_GENERIC)) return PEA_E_MODE;  // only the tiled kernel reads an external halo
     if (impl != PEA_IMPL_GENERIC) {
         if (tiled3_ok)
-            return launch_fwd3d_norm5(emb, d, z_skip, emb_plane, affs_plane, affs, halo, halo ? halo_slices : 0, halo_plane, st);
+            return launch_fwd3d_norm5(emb, d, z_skip, emb_plane, affs_plane, affs, halo, halo ? halo_slices : 0, halo_plane, relu,
+                                      st);
         if (tiled2_ok)
             return launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, nullptr, nullptr, nullptr,
                                   PEA_MASK_NONE, affs, nullptr, nullptr, st);
@@ -262,7 +265,50 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
     return launch_fwd_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP,
-                              z_skip, affs_plane, affs, st);
+                              z_skip, affs_plane, affs, relu, st);
+}
+
+// affs[:, 0, :s] = affs[:, 0, s:2s] (z), affs[:, 1, :, :s] = affs[:, 1, :, s:2s] (y), affs[:, 2, :, :, :s] = ... (x)
+__global__ void __launch_bounds__(256) replicate_first_kernel(float* __restrict__ affs, int B, int K, int D, int H, int W,
+                                                              int64_t plane, int s) {
+    const int64_t HW = (int64_t)H * W;
+    const int64_t nz = D >= 2 * s ? (int64_t)s * HW : 0, ny = H >= 2 * s ? (int64_t)D * s * W : 0,
+                  nx = W >= 2 * s ? (int64_t)D * H * s : 0;
+    const int64_t per = nz + ny + nx, total = per * B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / per;
+        int64_t r = i - b * per;
+        float* base = affs + b * K * plane;
+        if (r < nz) {            // channel 0: slices [0, s) <- [s, 2s)
+            base[r] = base[r + (int64_t)s * HW];
+        } else if ((r -= nz) < ny) {  // channel 1: rows [0, s) <- [s, 2s)
+            const int64_t z = r / ((int64_t)s * W), q = r - z * s * W;
+            float* p = base + plane + z * HW + q;
+            p[0] = p[(int64_t)s * W];
+        } else {                 // channel 2: columns [0, s) <- [s, 2s)
+            r -= ny;
+            const int64_t zy = r / s, x = r - zy * s;
+            float* p = base + 2 * plane + zy * W + x;
+            p[0] = p[s];
+        }
+    }
+}
+
+extern "C" int pea_replicate_first(float* affs, int B, int K, int D, int H, int W, int64_t plane, int shift, void* stream) {
+    if (!affs) return PEA_E_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || shift <= 0) return PEA_E_SHAPE;
+    if (K < 3 || K > PEA_MAX_OFFSETS) return PEA_E_OFFSETS;
+    const int64_t N = (int64_t)D * H * W;
+    if (plane == 0) plane = N;
+    if (plane < N) return PEA_E_SHAPE;
+    const int64_t HW = (int64_t)H * W;
+    const int64_t per = (D >= 2 * shift ? shift * HW : 0) + (H >= 2 * shift ? (int64_t)D * shift * W : 0) +
+                        (W >= 2 * shift ? (int64_t)D * H * shift : 0);
+    if (per == 0) return PEA_OK;
+    int64_t g = (per * B + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    replicate_first_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(affs, B, K, D, H, W, plane, shift);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,

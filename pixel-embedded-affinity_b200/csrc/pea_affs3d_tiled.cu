@@ -920,6 +920,7 @@ struct ParamsF {
     const float* halo;
     int halo_n;
     int64_t halo_plane;
+    int relu;  // store max(a, 0): the caller-side F.relu(pred) folded into the kernel
 };
 
 template <int TY>
@@ -1064,7 +1065,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             const float* nb = (g < 3) ? &S.sY[0][ty + HY - s][tx] : &S.sAm[0][ty][tx];
             float a;
             inplane_pair<false>(nb, (g < 3) ? CHS_Y : CHS_A, e, dummyG, 0.f, 0.f, 0.f, a);
-            if (live) out[(int64_t)(3 * g + 1) * P.affs_plane] = (y >= s) ? a : 0.f;
+            if (live) out[(int64_t)(3 * g + 1) * P.affs_plane] = (y >= s) ? (P.relu ? fmaxf(a, 0.f) : a) : 0.f;
         }
         __syncwarp();
         if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(it + 1) - 1 && more) issueY(znext);
@@ -1075,7 +1076,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             const int s = shift_yx(g);
             float a;
             inplane_pair<false>(&S.sX[0][ty][tx + XPAD - s], CHS_X, e, dummyG, 0.f, 0.f, 0.f, a);
-            if (live) out[(int64_t)(3 * g + 2) * P.affs_plane] = (x >= s) ? a : 0.f;
+            if (live) out[(int64_t)(3 * g + 2) * P.affs_plane] = (x >= s) ? (P.relu ? fmaxf(a, 0.f) : a) : 0.f;
         }
         __syncwarp();
         if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(it + 1) - 1 && more) issueX(znext);
@@ -1092,7 +1093,8 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
                 d0 = fma2(re[0][i], re[j][i], d0);
                 d1 = fma2(re[0][i + 1], re[j][i + 1], d1);
             }
-            if (live) out[(int64_t)(3 * (j - 1)) * P.affs_plane] = (z + zprev >= j) ? hsum2(d0, d1) : 0.f;
+            const float az = hsum2(d0, d1);
+            if (live) out[(int64_t)(3 * (j - 1)) * P.affs_plane] = (z + zprev >= j) ? (P.relu ? fmaxf(az, 0.f) : az) : 0.f;
         }
 #pragma unroll
         for (int s = 4; s >= 1; --s)
@@ -1701,7 +1703,7 @@ bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool
 }
 
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
-                       const float* halo, int halo_n, int64_t halo_plane, cudaStream_t st) {
+                       const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st) {
 #ifndef PEA_TILE_Y3D_FWD
 #define PEA_TILE_Y3D_FWD 8
 #endif
@@ -1714,7 +1716,7 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
     t3::ParamsF P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W; P.z_skip = z_skip;
     P.emb_plane = emb_plane; P.affs_plane = affs_plane; P.emb = emb; P.affs = affs;
-    P.halo = halo; P.halo_n = halo_n; P.halo_plane = halo_plane;
+    P.halo = halo; P.halo_n = halo_n; P.halo_plane = halo_plane; P.relu = relu;
     const int grid = d.B * ((d.H + TY - 1) / TY) * ((d.W + t3::TX - 1) / t3::TX);
     const size_t smem = sizeof(t3::StageF<TY>) + 1024;
     auto kern = t3::fwd3d_norm5<TY>;

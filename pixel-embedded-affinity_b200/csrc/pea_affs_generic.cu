@@ -59,7 +59,7 @@ template <int C>
 __global__ void __launch_bounds__(kThreads)
 fwd_generic(const float* __restrict__ emb, const float* __restrict__ par, const float* __restrict__ rinvE,
             const float* __restrict__ rinvU, Dims d, OffsetTable tab, int wrap, int z_skip, int64_t affs_plane,
-            float* __restrict__ affs) {
+            float* __restrict__ affs, int relu) {
     const int64_t total = (int64_t)d.B * d.N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = i / d.N, p = i - b * d.N;
@@ -78,7 +78,7 @@ fwd_generic(const float* __restrict__ emb, const float* __restrict__ par, const 
                 load_unit<C>(par, rinvU, b, q, d.N, un);
                 a = dot<C>(e, un);
             }
-            affs[(b * tab.K + k) * affs_plane + pout] = a;
+            affs[(b * tab.K + k) * affs_plane + pout] = relu ? fmaxf(a, 0.f) : a;
         }
     }
 }
@@ -227,10 +227,11 @@ int launch_rinv(const float* emb, int C, const Dims& d, float* rinv, cudaStream_
 }
 
 int launch_fwd_generic(const float* emb, const float* par, const float* rinvE, const float* rinvU, int C, const Dims& d,
-                       const OffsetTable& tab, int wrap, int z_skip, int64_t affs_plane, float* affs, cudaStream_t st) {
+                       const OffsetTable& tab, int wrap, int z_skip, int64_t affs_plane, float* affs, int relu,
+                       cudaStream_t st) {
     const int grid = grid_for((int64_t)d.B * d.N);
     PEA_DISPATCH_C(C, fwd_generic<CC><<<grid, kThreads, 0, st>>>(emb, par, rinvE, rinvU, d, tab, wrap, z_skip, affs_plane,
-                                                                 affs));
+                                                                 affs, relu));
     return (int)cudaGetLastError();
 }
 

@@ -94,18 +94,29 @@ def ema_embedding_loss_norm1(embedding, ema_embedding, target, weightmap, criter
     return _loss3d(embedding, ema_embedding, target, weightmap, criterion, [shift] * 3, affs0_weight, 1)
 
 
-def _inf3d(embedding, shifts, z_skip=0, out=None, halo=None):
+def _inf3d(embedding, shifts, z_skip=0, out=None, halo=None, relu=False, replicate_border=False):
     embedding = ops.check_embedding("embedding", embedding, 5, make_contiguous=False)
     with torch.no_grad():
-        return ops.affs_fwd(embedding.detach(), None, offsets_from_shifts(shifts), ops.BORDER_ZERO, z_skip=z_skip, out=out,
-                            halo=halo)
+        affs = ops.affs_fwd(embedding.detach(), None, offsets_from_shifts(shifts), ops.BORDER_ZERO, z_skip=z_skip, out=out,
+                            halo=halo, relu=relu)
+        if replicate_border:
+            if not affs.is_contiguous():
+                raise ValueError("replicate_border needs a contiguous output (not a z-range view)")
+            ops.replicate_first(affs, 1)
+        return affs
 
 
-def inf_embedding_loss_norm5(embedding):
-    """:212-234 -- forward only, (B,12,D,H,W)."""
-    return _inf3d(embedding, SHIFTS_NORM5)
+def inf_embedding_loss_norm5(embedding, relu=False, replicate_border=False):
+    """:212-234 -- forward only, (B,12,D,H,W).
+
+    The two keyword arguments (default off: the reference's result) fold in what every caller does next
+    (scripts_ac3ac4/inference.py:160-165, main.py:232-237): ``replicate_border`` copies slice / row / column 1 of the
+    three shift-1 channels over slice / row / column 0 (where the affinity is undefined), ``relu`` clamps at zero --
+    the clamp rides on the kernel's store, the border copy is one small launch over three thin slabs, instead of
+    two more passes over the whole (B,12,D,H,W) result."""
+    return _inf3d(embedding, SHIFTS_NORM5, relu=relu, replicate_border=replicate_border)
 
 
-def inf_embedding_loss_norm1(embedding, shift=1):
-    """:54-67 -- forward only, (B,3,D,H,W)."""
-    return _inf3d(embedding, [shift] * 3)
+def inf_embedding_loss_norm1(embedding, shift=1, relu=False, replicate_border=False):
+    """:54-67 -- forward only, (B,3,D,H,W).  ``relu`` / ``replicate_border``: see ``inf_embedding_loss_norm5``."""
+    return _inf3d(embedding, [shift] * 3, relu=relu, replicate_border=replicate_border)

@@ -861,6 +861,26 @@ def test_2d_kernels_write_only_their_outputs(P, O, shifts, two_view, labels):
 
 
 # =========================================================================== forward-only tiled kernel + z-shards
+@pytest.mark.parametrize("B,D,H,W", [(1, 18, 64, 96), (2, 7, 37, 44), (1, 5, 30, 30)])
+def test_inference_epilogue_fused(P, O, B, D, H, W):
+    """relu / replicate_border of inf_embedding_loss_norm5 / norm1 == the reference callers' epilogue
+    (scripts_ac3ac4/inference.py:160-165) applied with torch to the plain result, bit for bit (tiled kernel at
+    W % 4 == 0, table-driven kernel otherwise)."""
+    g = torch.Generator().manual_seed(D * 100 + H)
+    emb = torch.randn((B, 16, D, H, W), generator=g).cuda()
+    for fn in (P.inf_embedding_loss_norm5, P.inf_embedding_loss_norm1):
+        plain = fn(emb)
+        ref = plain.clone()
+        ref[:, 1, :, :1, :] = ref[:, 1, :, 1:2, :]
+        ref[:, 2, :, :, :1] = ref[:, 2, :, :, 1:2]
+        ref[:, 0, :1, :, :] = ref[:, 0, 1:2, :, :]
+        ref = torch.relu(ref)
+        got = fn(emb, relu=True, replicate_border=True)
+        assert torch.equal(got, ref)
+        assert torch.equal(fn(emb, relu=True), torch.relu(plain))
+        assert (plain < 0).any()  # the clamp is exercised
+
+
 @pytest.mark.parametrize("B,D,H,W,seed", [(1, 18, 64, 96, 91), (2, 7, 37, 44, 92), (1, 5, 28, 28, 93)])
 def test_tiled3d_forward_matches_generic_and_oracle(P, O, B, D, H, W, seed):
     from pea_b200 import _ops as ops

@@ -14,3 +14,5 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 dev = torch.device("cuda", 0)
 r = bench.time_zshard(P, dev, 0, 1, steps)
 print(f"cfg4 forward: {r['ms_per_step']:.3f} ms  {r['hbm_gbs_aggregate']:.0f} GB/s = {r['hbm_gbs_aggregate'] / 6459.6 * 100:.1f}% of measured HBM peak")
+r = bench.time_inference_epilogue(P, dev)
+print(f"cfg4 forward + border replicate + relu: torch epilogue {r['torch_epilogue_ms']:.3f} ms, fused {r['fused_ms']:.3f} ms")
