@@ -176,13 +176,15 @@ int pea_replicate_first(float* affs, int B, int K, int D, int H, int W, int64_t 
  *                             target = gen_affs_ours(labels, offsets, ignore, padding)[0], mask = [1] (pairs across the
  *                             image edge dropped) and weight derived inside the kernel: results equal
  *                             pea_gt_targets followed by pea_affs_loss_fwd_bwd with a uint8 mask.
- * Only the canonical 2-D tables multi_offset(shifts <= 12, neighbor=4) with C = 16 are implemented: anything else
- * returns PEA_E_MODE and the caller takes the two-step route.  counts: device scratch of pea_gt_counts_bytes(B, K). */
+ * Implemented (C = 16): semantics 0 (gen_affs_ours) with the canonical 2-D tables multi_offset(shifts <= 12,
+ * neighbor=4), D = 1, either border; semantics 1 (seg_to_aff without replicate pad) with the 12-offset AC3/AC4 table,
+ * PEA_BORDER_ZERO.  Anything else returns PEA_E_MODE and the caller takes the two-step route.
+ * counts: device scratch of pea_gt_counts_bytes(B, K). */
 int pea_gt_pair_weights(const void* labels, int label_dtype, int B, int D, int H, int W,
                         const int32_t* offsets, int K, int semantics, int ignore, int padding, double alpha,
                         float* wtab, void* counts, size_t counts_bytes, void* stream);
-int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* labels, int B, int C, int H, int W,
-                                 const int32_t* offsets, int K, int border, int ignore, const float* wtab,
+int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* labels, int B, int C, int D, int H, int W,
+                                 const int32_t* offsets, int K, int border, int semantics, int ignore, const float* wtab,
                                  const float* loss_norm, const float* loss_coef,
                                  float* affs, float* loss_out, float* grad_emb,
                                  void* workspace, size_t ws_bytes, void* stream);

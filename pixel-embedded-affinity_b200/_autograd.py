@@ -112,22 +112,25 @@ class FusedAffinityLossLabels(torch.autograd.Function):
     the kernel (canonical 2-D tables; ``ops.affs_loss_labels_fwd_bwd`` raises PEA_E_MODE otherwise)."""
 
     @staticmethod
-    def forward(ctx, emb, labels_i32, wtab, ignore, spec):
+    def forward(ctx, emb, labels_i32, wtab, ignore, spec, semantics=0):
         need_e = ctx.needs_input_grad[0]
         loss_out, affs, grad = ops.affs_loss_labels_fwd_bwd(emb, labels_i32, spec.offs3, spec.border, ignore, wtab,
-                                                            spec.loss_norm, spec.loss_coef, want_affs=True, want_grad=need_e)
-        ctx.spec, ctx.ignore, ctx.grad_buf, ctx.need_e = spec, ignore, grad, need_e
+                                                            spec.loss_norm, spec.loss_coef, want_affs=True, want_grad=need_e,
+                                                            semantics=semantics)
+        ctx.spec, ctx.ignore, ctx.grad_buf, ctx.need_e, ctx.semantics = spec, ignore, grad, need_e, semantics
         if need_e:
             ctx.save_for_backward(emb, labels_i32, wtab)
         ctx.set_materialize_grads(False)
         loss, each = loss_out[0], loss_out[1:]
         ctx.mark_non_differentiable(each)
+        if not spec.affs_differentiable:
+            ctx.mark_non_differentiable(affs)
         return loss, affs, each
 
     @staticmethod
     def backward(ctx, g_loss, g_affs, g_each):
         if not ctx.need_e:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         emb, labels_i32, wtab = ctx.saved_tensors
         spec = ctx.spec
         ge = None
@@ -135,13 +138,14 @@ class FusedAffinityLossLabels(torch.autograd.Function):
             ge = ctx.grad_buf
             if ge is None:  # buffer already handed out by an earlier backward (retain_graph=True): recompute
                 _, _, ge = ops.affs_loss_labels_fwd_bwd(emb, labels_i32, spec.offs3, spec.border, ctx.ignore, wtab,
-                                                        spec.loss_norm, spec.loss_coef, want_affs=False, want_grad=True)
+                                                        spec.loss_norm, spec.loss_coef, want_affs=False, want_grad=True,
+                                                        semantics=ctx.semantics)
             ctx.grad_buf = None
             ops.scale_inplace(ge, g_loss.to(device=emb.device, dtype=torch.float32))
         if g_affs is not None:
             ae, _ = ops.affs_bwd(emb, None, spec.offs3, spec.border, g_affs.contiguous(), want_grad=True)
             ge = ae if ge is None else ge.add_(ae)
-        return ge, None, None, None, None
+        return ge, None, None, None, None, None
 
 
 class Affinities(torch.autograd.Function):

@@ -32,8 +32,8 @@ SIGNATURES = {
     "pea_gt_targets": (ci, [vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, ci, ctypes.c_double, vp, vp, vp, vp,
                             ctypes.c_size_t, vp]),
     "pea_gt_pair_weights": (ci, [vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, ci, ctypes.c_double, vp, vp, ctypes.c_size_t, vp]),
-    "pea_affs_loss_labels_fwd_bwd": (ci, [vp, vp, ci, ci, ci, ci, c_int32_p, ci, ci, ci, vp, c_float_p, c_float_p, vp, vp, vp, vp,
-                                          ctypes.c_size_t, vp]),
+    "pea_affs_loss_labels_fwd_bwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, ci, vp, c_float_p, c_float_p, vp, vp,
+                                          vp, vp, ctypes.c_size_t, vp]),
     "pea_replicate_first": (ci, [vp, ci, ci, ci, ci, ci, ctypes.c_int64, ci, vp]),
     "pea_wbr_stats_bytes": (ctypes.c_size_t, [ci]),
     "pea_weight_binary_ratio": (ci, [vp, ci, ctypes.c_int64, ctypes.c_double, vp, vp, ctypes.c_size_t, vp]),

@@ -314,8 +314,9 @@ def gt_pair_weights(labels4, offsets3_, semantics, ignore=False, padding=True, a
 
 
 def affs_loss_labels_fwd_bwd(emb, labels_i32, offs3, border, ignore, wtab, loss_norm, loss_coef, want_affs=True,
-                             want_grad=True):
-    """Label-driven fused 2-D loss (canonical tables only; PeaError with code PEA_E_MODE otherwise).
+                             want_grad=True, semantics=0):
+    """Label-driven fused loss: semantics 0 = gen_affs_ours targets (canonical 2-D tables), 1 = seg_to_aff targets (3-D
+    12-offset table); PeaError with code PEA_E_MODE for anything else.
     Returns (loss_out (1+K,), affs or None, grad_emb or None)."""
     B, C, D, H, W = _dims5(emb)
     K = offs3.shape[0]
@@ -323,14 +324,14 @@ def affs_loss_labels_fwd_bwd(emb, labels_i32, offs3, border, ignore, wtab, loss_
     affs = torch.empty((B, K) + tuple(emb.shape[2:]), dtype=torch.float32, device=dev) if want_affs else None
     grad = torch.empty_like(emb) if want_grad else None
     loss_out = torch.empty(1 + K, dtype=torch.float32, device=dev)
-    ws, n = _workspace(B, C, 1, H, W, K, False, dev)
+    ws, n = _workspace(B, C, D, H, W, K, False, dev)
     keep_o, optr = _i32(offs3)
     keep_n, nptr = _f32(loss_norm)
     keep_c, cptr = _f32(loss_coef)
     with torch.cuda.device(dev):
-        rc = lib.pea_affs_loss_labels_fwd_bwd(_ptr(emb), _ptr(labels_i32), B, C, H, W, optr, K, border, int(bool(ignore)),
-                                              _ptr(wtab), nptr, cptr, _ptr(affs), _ptr(loss_out), _ptr(grad), _ptr(ws), n,
-                                              _stream())
+        rc = lib.pea_affs_loss_labels_fwd_bwd(_ptr(emb), _ptr(labels_i32), B, C, D, H, W, optr, K, border, int(semantics),
+                                              int(bool(ignore)), _ptr(wtab), nptr, cptr, _ptr(affs), _ptr(loss_out),
+                                              _ptr(grad), _ptr(ws), n, _stream())
     check("pea_affs_loss_labels_fwd_bwd", rc)
     return loss_out, affs, grad
 

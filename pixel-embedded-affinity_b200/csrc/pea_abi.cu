@@ -27,6 +27,8 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
                        const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
+int launch_fused3d_norm5_labels(const float* emb, const int32_t* seg, const float* wtab, const Dims& d, const OffsetTable& tab,
+                                float* affs, float* partials, float* grad, cudaStream_t st);
 
 // pea_affs2d_tiled.cu
 bool tiled2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, int wrap, bool need_grad_partner);
@@ -391,15 +393,17 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, ws.partials, generic_partial_blocks((int64_t)B * d.N), K, sc, loss_out);
 }
 
-extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* labels, int B, int C, int H, int W,
-                                            const int32_t* offsets, int K, int border, int ignore, const float* wtab,
+extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* labels, int B, int C, int D, int H, int W,
+                                            const int32_t* offsets, int K, int border, int semantics, int ignore,
+                                            const float* wtab,
                                             const float* loss_norm, const float* loss_coef, float* affs, float* loss_out,
                                             float* grad_emb, void* workspace, size_t ws_bytes, void* stream) {
     if (!emb || !labels || !offsets || !wtab || !loss_norm || !loss_coef || !loss_out || !workspace) return PEA_E_NULL;
     Dims d;
-    int rc = check_volume(B, C, 1, H, W, K, d);
+    int rc = check_volume(B, C, D, H, W, K, d);
     if (rc) return rc;
     if (border != PEA_BORDER_WRAP && border != PEA_BORDER_ZERO) return PEA_E_MODE;
+    if (semantics != 0 && semantics != 1) return PEA_E_MODE;
     if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
     if ((reinterpret_cast<uintptr_t>(labels) | reinterpret_cast<uintptr_t>(wtab)) & 3) return PEA_E_ALIGN;
     Workspace ws;
@@ -414,9 +418,15 @@ extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* lab
         tab.gcoef[k] = (float)(2.0 * (double)loss_coef[k] / (double)loss_norm[k]);
     }
     // the label plane is staged by TMA like the embedding: 16-byte aligned base
-    if (!canon2d_eligible(C, 1, H, W, tab, emb, emb, emb, reinterpret_cast<const float*>(labels))) return PEA_E_MODE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* parts = ws.rinvE;
+    if (semantics == 1) {  // 3-D: seg_to_aff targets of the 12-offset table, zero border
+        const float* labf = reinterpret_cast<const float*>(labels);
+        if (!tiled3d_norm5_eligible(C, D, H, W, tab, border, PEA_MASK_NONE, false, emb, labf, labf)) return PEA_E_MODE;
+        if ((rc = launch_fused3d_norm5_labels(emb, labels, wtab, d, tab, affs, parts, grad_emb, st))) return rc;
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, fused3d_norm5_blocks(B, H, W), K, sc, loss_out);
+    }
+    if (D != 1 || !canon2d_eligible(C, 1, H, W, tab, emb, emb, emb, reinterpret_cast<const float*>(labels))) return PEA_E_MODE;
     if ((rc = launch_canon2d_labels(emb, labels, wtab, ignore, d, tab, border == PEA_BORDER_WRAP, affs, parts, grad_emb, st)))
         return rc;
     return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, canon2d_blocks(B, H, W), K, sc, loss_out);

@@ -50,6 +50,7 @@ struct Params {
     float* grad;      // may be null
     float* partials;  // [gridDim.x][12]
     float gcoef[12];
+    const float* wtab;  // label-driven flavour: [B][12][2] weight where the target is 1 / 0 (pea_gt_pair_weights)
 };
 
 // channel layout of the 12-offset set: k = 3*g + axis, shift of (group g, axis): z {1,2,3,4}, y/x {1,3,9,27}
@@ -557,7 +558,11 @@ struct alignas(128) StageM {
     float sFar[2][TY][TX];  // channel 10 (y shift 27), rows y0 + 27 ..: [target, weight]
 };
 
-template <int TY, bool GRAD>
+// LAB: target and weight are derived in the kernel from the int32 segmentation (seg_to_aff semantics: same positive id)
+// and the per-channel weight pairs of pea_gt_pair_weights -- mapT / mapW then describe the label volume with the
+// footprints of a y-column box (TY + 54 rows) and of the x-row box, staged in the space of the target / weight groups;
+// the z channels compare against a four-slice label ring in registers.
+template <int TY, bool GRAD, bool LAB = false>
 #ifdef PEA_K4_MAXNREG
 __global__ void __maxnreg__(PEA_K4_MAXNREG)
 #else
@@ -573,10 +578,17 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     __shared__ uint64_t barY, barX;
     __shared__ uint32_t cntY, cntX, s_tmem;
     __shared__ float s_red[12][TY];
+    __shared__ float s_w[12][2];  // LAB: weight where the channel's target is 1 / 0
 
     constexpr uint32_t kBytesTW = sizeof(S.sTW[0]);
-    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) + kBytesTW + (GRAD ? kBytesTW + sizeof(S.sFar) : 0);
-    constexpr uint32_t kBytesX = sizeof(S.sX) + kBytesTW + (GRAD ? kBytesTW : 0);
+    constexpr int LYR = TY + 2 * FAR;  // rows of the label y-column box, first row y0 - 27
+    constexpr uint32_t kBytesLY = LYR * TX * 4, kBytesLX = TY * XW * 4;
+    static_assert(kBytesLY <= 2 * kBytesTW && kBytesLX <= kBytesTW, "label boxes live in the target / weight groups' space");
+    constexpr uint32_t kBytesY = sizeof(S.sY) + sizeof(S.sAm) + sizeof(S.sAp) +
+                                 (LAB ? kBytesLY : kBytesTW + (GRAD ? kBytesTW + sizeof(S.sFar) : 0));
+    constexpr uint32_t kBytesX = sizeof(S.sX) + (LAB ? kBytesLX : kBytesTW + (GRAD ? kBytesTW : 0));
+    const int32_t* lY = reinterpret_cast<const int32_t*>(&S.sTW[0][0][0][0][0]);  // [LYR][TX]
+    const int32_t* lX = reinterpret_cast<const int32_t*>(&S.sTW[2][0][0][0][0]);  // [TY][XW], cols x0 - 28 ..
     constexpr int CHS_Y = (TY + 2 * HY) * TX, CHS_A = TY * TX, CHS_X = TY * XW;
     constexpr uint32_t kWarps = TY + PEA_K4_DUP;
 
@@ -602,8 +614,9 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     auto issueY = [&](int z) {
         mbar_arrive_expect_tx(&barY, kBytesY);
         tma_load_5d(&S.sY[0][0][0], &mapY, &barY, x0, y0 - HY, z, 0, b);
-        issueTW(0, 1, z, &barY);
-        if (GRAD) {  // rows below the tile for the pairs anchored at y + s (zero fill below the volume == pair dropped)
+        if (LAB) tma_load_5d(&S.sTW[0][0][0][0][0], &mapT, &barY, x0, y0 - FAR, z, 0, b);
+        else issueTW(0, 1, z, &barY);
+        if (GRAD && !LAB) {  // rows below the tile for the pairs anchored at y + s (zero fill below the volume == pair dropped)
             tma_load_5d(&S.sTW[3][0][0][0][0], &mapT, &barY, x0, y0 + TY, z, 1, b);
             tma_load_5d(&S.sTW[3][1][0][0][0], &mapW, &barY, x0, y0 + TY, z, 1, b);
             tma_load_5d(&S.sFar[0][0][0], &mapT1, &barY, x0, y0 + FAR, z, 10, b);
@@ -615,8 +628,9 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     auto issueX = [&](int z) {
         mbar_arrive_expect_tx(&barX, kBytesX);
         tma_load_5d(&S.sX[0][0][0], &mapX, &barX, x0 - XPAD, y0, z, 0, b);
-        issueTW(1, 2, z, &barX);
-        if (GRAD) {
+        if (LAB) tma_load_5d(&S.sTW[2][0][0][0][0], &mapW, &barX, x0 - XPAD, y0, z, 0, b);
+        else issueTW(1, 2, z, &barX);
+        if (GRAD && !LAB) {
             // the same four x channels of the NEXT 32 columns: target / weight of the pairs anchored at x + s beyond the
             // tile (TMA wants a 16-byte aligned start coordinate, so a box shifted by s itself is not an option)
             tma_load_5d(&S.sTW[2][0][0][0][0], &mapT, &barX, x0 + TX, y0, z, 2, b);
@@ -632,6 +646,7 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         issueY(0);
         issueX(0);
     }
+    if (LAB && threadIdx.x < 24) (&s_w[0][0])[threadIdx.x] = P.wtab[(int64_t)b * 24 + threadIdx.x];
     if (wid == 0) {  // one warp allocates the whole Tensor Memory of this SM (one CTA per SM anyway: shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols)
                      : "memory");
@@ -655,8 +670,11 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
 #pragma unroll
     for (int k = 0; k < 12; ++k) lossacc[k] = 0.f;
 
-    const float* tgt_b = P.target + (int64_t)b * 12 * N + pix;
-    const float* wgt_b = P.weight + (int64_t)b * 12 * N + pix;
+    const float* tgt_b = LAB ? nullptr : P.target + (int64_t)b * 12 * N + pix;
+    const float* wgt_b = LAB ? nullptr : P.weight + (int64_t)b * 12 * N + pix;
+    int32_t lz1 = 0, lz2 = 0, lz3 = 0, lz4 = 0, lp = 0;  // LAB: labels of this column at z-1 .. z-4, and at z
+    // seg_to_aff: both ends carry the same positive id; the weight map takes one of two values per channel
+    auto lab_t = [&](int32_t a, int32_t c) { return a > 0 && c > 0 && a == c; };
 #ifdef PEA_K4_NOSTORE
     float* affs_b = nullptr;
 #else
@@ -692,11 +710,13 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     // own target / weight of the four z channels (0, 3, 6, 9): needed only at the end of the slice, requested at its start
     float tz[4], wz[4];
     auto load_tz = [&](int z) {
+        if constexpr (!LAB) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t o = (int64_t)(3 * j) * N + (int64_t)z * HW;
             tz[j] = ldg_early(tgt_b + o, live);
             wz[j] = ldg_early(wgt_b + o, live);
+        }
         }
     };
 
@@ -750,7 +770,19 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             const int chs = (g < 3) ? CHS_Y : CHS_A;
             const bool vf = y >= s;  // out-of-volume voxels have zero weight (TMA zero fill)
             float a;
-            if (PEA_K4_LANEPACK && GRAD) {
+            if (LAB) {
+                const int32_t* lq = lY + (ty + FAR) * TX + tx;
+                if (g == 0) lp = lq[0];
+                const bool t_f = lab_t(lp, lq[-s * TX]), t_r = lab_t(lq[s * TX], lp);
+                const float w_f = (live && vf) ? s_w[k][t_f ? 0 : 1] : 0.f;
+                lossacc[PEA_K4_LK(k)] += inplane_pair<GRAD>(nb_m, chs, e, G, t_f ? 1.f : 0.f, w_f, P.gcoef[k], a);
+                if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
+                if (GRAD) {
+                    const float w_r = (y + s < H) ? s_w[k][t_r ? 0 : 1] : 0.f;  // anchor below the volume: pair dropped
+                    float a2;
+                    inplane_pair<true>(nb_p, chs, e, G, t_r ? 1.f : 0.f, w_r, P.gcoef[k], a2);
+                }
+            } else if (PEA_K4_LANEPACK && GRAD) {
                 const float* pr = (g == 3) ? &S.sFar[0][ty][tx]
                                            : (ty + s < TY ? sTy + (g * CHS_A + s * TX) : sTb + (g * CHS_A + (s - TY) * TX));
                 lossacc[PEA_K4_LK(k)] += inplane_pair2(nb_m, nb_p, chs, e, GL, sTy[g * CHS_A], vf ? sTy[kW + g * CHS_A] : 0.f, pr[0],
@@ -786,7 +818,19 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             const int k = 3 * g + 2;
             const bool vf = x >= s;
             float a;
-            if (PEA_K4_LANEPACK && GRAD) {
+            if (LAB) {
+                const int32_t* lq = lX + ty * XW + tx + XPAD;
+                const bool t_f = lab_t(lp, lq[-s]), t_r = lab_t(lq[s], lp);
+                const float w_f = (live && vf) ? s_w[k][t_f ? 0 : 1] : 0.f;
+                lossacc[PEA_K4_LK(k)] += inplane_pair<GRAD>(&S.sX[0][ty][tx + XPAD - s], CHS_X, e, G, t_f ? 1.f : 0.f, w_f,
+                                                            P.gcoef[k], a);
+                if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
+                if (GRAD) {
+                    const float w_r = (x + s < W) ? s_w[k][t_r ? 0 : 1] : 0.f;
+                    float a2;
+                    inplane_pair<true>(&S.sX[0][ty][tx + XPAD + s], CHS_X, e, G, t_r ? 1.f : 0.f, w_r, P.gcoef[k], a2);
+                }
+            } else if (PEA_K4_LANEPACK && GRAD) {
                 const float* pr = (tx + s < TX) ? sTx + (g * CHS_A + s) : sTn + (g * CHS_A + s - TX);
                 lossacc[PEA_K4_LK(k)] += inplane_pair2(&S.sX[0][ty][tx + XPAD - s], &S.sX[0][ty][tx + XPAD + s], CHS_X, e, GL,
                                             sTx[g * CHS_A], vf ? sTx[kW + g * CHS_A] : 0.f, pr[0], pr[kW], P.gcoef[k], a);
@@ -833,8 +877,16 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
                     d1 = fma2(e[i + 1], ej[i + 1], d1);
                 }
                 const float a = hsum2(d0, d1);
-                const float diff = a - tz[j - 1];
-                const float wv = wz[j - 1];  // 0 on dead lanes
+                float tzj, wv;
+                if (LAB) {
+                    const bool t = lab_t(lp, j == 1 ? lz1 : (j == 2 ? lz2 : (j == 3 ? lz3 : lz4)));
+                    tzj = t ? 1.f : 0.f;
+                    wv = live ? s_w[k][t ? 0 : 1] : 0.f;
+                } else {
+                    tzj = tz[j - 1];
+                    wv = wz[j - 1];  // 0 on dead lanes
+                }
+                const float diff = a - tzj;
                 lossacc[PEA_K4_LK(k)] += wv * diff * diff;
                 if (affs_b && live) affs_b[(int64_t)k * N + zoff] = a;
                 if (GRAD) {
@@ -863,6 +915,12 @@ fused3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
         rr3 = rr2;
         rr2 = rr1;
         rr1 = rp;
+        if (LAB) {
+            lz4 = lz3;
+            lz3 = lz2;
+            lz2 = lz1;
+            lz1 = lp;
+        }
     }
     // drain: slices D-4 .. D-1 (those >= 0) still hold their gradient in Tensor Memory; rr_j belongs to slice D - j
     if (GRAD) {
@@ -1619,7 +1677,7 @@ int launch_fused3d_norm5_rf(const float* emb, const Dims& d, const OffsetTable& 
     if ((rc = encode_volume_map(&mW, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 12))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
-    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
     const int grid = tiled3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::Stage<TY>) + 1024;
@@ -1673,7 +1731,7 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
     if ((rc = encode_volume_map(&mW1, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 1))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
-    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
     const int grid = fused3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::StageM<TY>) + 128;
@@ -1689,6 +1747,38 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
     }
     return (int)cudaGetLastError();
 #endif
+}
+
+// Label-driven flavour (SURVEY.md 8(f) item 1 for the 3-D path): target = seg_to_aff(seg, NHOOD_NORM5, pad='') and its
+// per-channel weight_binary_ratio are derived inside the loss kernel from the int32 segmentation.
+int launch_fused3d_norm5_labels(const float* emb, const int32_t* seg, const float* wtab, const Dims& d, const OffsetTable& tab,
+                                float* affs, float* partials, float* grad, cudaStream_t st) {
+    constexpr int TY = kTileYTm;
+    const float* lab = reinterpret_cast<const float*>(seg);  // 4-byte elements, copied bit for bit
+    CUtensorMap mY, mA, mX, mLy, mLx;
+    int rc;
+    if ((rc = encode_volume_map(&mY, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY + 2 * t3::HY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mA, emb, d.B, 16, d.D, d.H, d.W, t3::TX, TY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mX, emb, d.B, 16, d.D, d.H, d.W, t3::XW, TY, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mLy, lab, d.B, 1, d.D, d.H, d.W, t3::TX, TY + 2 * t3::FAR, 1, 1))) return rc;
+    if ((rc = encode_volume_map(&mLx, lab, d.B, 1, d.D, d.H, d.W, t3::XW, TY, 1, 1))) return rc;
+    t3::Params P;
+    P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
+    P.target = nullptr; P.weight = nullptr; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = wtab;
+    for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
+    const int grid = fused3d_norm5_blocks(d.B, d.H, d.W);
+    const size_t smem = sizeof(t3::StageM<TY>) + 128;
+    cudaError_t e;
+    if (grad) {
+        auto kern = t3::fused3d_norm5_tm<TY, true, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mLy, mLx, mLy, mLx, P);
+    } else {
+        auto kern = t3::fused3d_norm5_tm<TY, false, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<grid, TY * 32, smem, st>>>(mY, mA, mX, mLy, mLx, mLy, mLx, P);
+    }
+    return (int)cudaGetLastError();
 }
 
 bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
@@ -1748,7 +1838,7 @@ int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, 
     if ((rc = encode_volume_map(&mW, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 12))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
-    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
     const int grid = cross3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::StageX<TY>) + 1024;

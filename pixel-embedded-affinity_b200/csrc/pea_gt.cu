@@ -7,6 +7,11 @@
 
 namespace pea {
 
+#ifndef PEA_GT_UNROLL
+#define PEA_GT_UNROLL 4
+#endif
+constexpr int kGtUnroll = PEA_GT_UNROLL;  // offsets whose neighbour loads are in flight together in the fused passes
+
 struct GtTable {
     int K;
     int dz[PEA_MAX_OFFSETS];
@@ -214,7 +219,8 @@ gt_fused_x4(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int 
         L here[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) here[j] = s[p + j];
-        for (int k = 0; k < K; ++k) {
+#pragma unroll kGtUnroll
+        for (int k = 0; k < K; ++k) {  // unrolled: the neighbour loads of several offsets are in flight together
             const int dz = tab.dz[k], dy = tab.dy[k], dx = tab.dx[k];
             const int qz = z + dz, qy = y + dy;
             const bool row_in = (unsigned)qz < (unsigned)D && (unsigned)qy < (unsigned)H;

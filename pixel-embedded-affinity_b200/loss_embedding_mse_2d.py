@@ -122,7 +122,7 @@ def embedding_loss_labels(embedding, labels, criterion, offsets, affs0_weight=1,
         spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), np.ones(K, np.float32), affs_differentiable=True)
         try:
             wtab = ops.gt_pair_weights(lab32[:, None], offs3, 0, ignore, padding, alpha)
-            loss, affs, each = FusedAffinityLossLabels.apply(embedding, lab32, wtab, bool(ignore), spec)
+            loss, affs, each = FusedAffinityLossLabels.apply(embedding, lab32, wtab, bool(ignore), spec, 0)
             return loss, affs, LossList(each)
         except PeaError as ex:
             if ex.code != -8:  # PEA_E_MODE: not a canonical table / shape -- two-step route below

@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from . import _ops as ops
-from ._autograd import Affinities, FusedAffinityLoss, OpSpec
+from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, OpSpec
+from ._lib import PeaError
 from .loss import is_weighted_mse
 
 SHIFTS_NORM5 = [1, 1, 1, 2, 3, 3, 3, 9, 9, 4, 27, 27]  # :176
@@ -120,3 +121,37 @@ def inf_embedding_loss_norm5(embedding, relu=False, replicate_border=False):
 def inf_embedding_loss_norm1(embedding, shift=1, relu=False, replicate_border=False):
     """:54-67 -- forward only, (B,3,D,H,W).  ``relu`` / ``replicate_border``: see ``inf_embedding_loss_norm5``."""
     return _inf3d(embedding, [shift] * 3, relu=relu, replicate_border=replicate_border)
+
+
+def embedding_loss_norm5_labels(embedding, seg, criterion, affs0_weight=1):
+    """Training-loop form of ``embedding_loss_norm5``: takes the segmentation (B,D,H,W) instead
+    of (target, weightmap) and equals
+
+        target[b] = seg_to_aff(seg[b], nhood = the 12 offsets, pad='')              (data/data_affinity.py:53-102)
+        weightmap[b, k] = weight_binary_ratio(target[b, k])                         (data/data_segmentation.py:205-228)
+        embedding_loss_norm5(embedding, target, weightmap, criterion, affs0_weight) (:169-194)
+
+    i.e. what ``data_provider_labeled_deep.py:246-285`` prepares on the host per sample.  With ``WeightedMSE`` and
+    W % 4 == 0 the two (B,12,D,H,W) GT tensors never exist: one counting pass over the segmentation, then the fused
+    kernel derives target and weight from the int32 labels it stages next to the embedding.  Returns (loss, affs)."""
+    embedding = ops.check_embedding("embedding", embedding, 5)
+    B, C, D, H, W = embedding.shape
+    if seg.dim() != 4 or tuple(seg.shape) != (B, D, H, W) or not seg.is_cuda:
+        raise ValueError(f"seg must be a CUDA tensor of shape {(B, D, H, W)}, got {tuple(seg.shape)}")
+    if is_weighted_mse(criterion) and W % 4 == 0 and not seg.dtype.is_floating_point:
+        lab = seg.contiguous()
+        lab32 = lab if lab.dtype == torch.int32 else lab.to(torch.int32)
+        offs3 = offsets_from_shifts(SHIFTS_NORM5)
+        coef = np.ones(12, np.float32)
+        coef[:3] = affs0_weight
+        spec = OpSpec(offs3, ops.BORDER_ZERO, _norms_3d(embedding.shape, SHIFTS_NORM5), coef, affs_differentiable=False)
+        try:
+            wtab = ops.gt_pair_weights(lab32, offs3, 1)
+            loss, affs, _ = FusedAffinityLossLabels.apply(embedding, lab32, wtab, False, spec, 1)
+            return loss, affs
+        except PeaError as ex:
+            if ex.code != -8:  # PEA_E_MODE: shape the tiled kernel does not take -- two-step route below
+                raise
+    from .gt import make_targets_3d
+    target, weight = make_targets_3d(seg)
+    return embedding_loss_norm5(embedding, target, weight, criterion, affs0_weight)

@@ -860,6 +860,38 @@ def test_2d_kernels_write_only_their_outputs(P, O, shifts, two_view, labels):
         assert bool(torch.isfinite(out).all()), f"{name}: non-finite values"
 
 
+@pytest.mark.parametrize("B,D,H,W,seed", [(2, 7, 37, 44, 71), (1, 18, 64, 96, 72), (1, 5, 30, 28, 73), (1, 6, 30, 30, 74)])
+def test_embedding_loss_norm5_labels_equals_gt_then_loss(P, O, B, D, H, W, seed):
+    """embedding_loss_norm5_labels(embedding, seg, ...) == seg_to_aff(12 offsets, pad='') + weight_binary_ratio per
+    (sample, channel) + embedding_loss_norm5: against this package's two-step route and the oracle's (the reference's
+    data-provider recipe, data_provider_labeled_deep.py:246-285); partial tiles, D = 5 ring fill / drain, and a width
+    (30) that takes the two-step route behind the same call."""
+    rng = np.random.RandomState(seed)
+    segs = np.stack([O.voronoi_labels((D, H, W), 9, seed + b, background_frac=0.15, z_scale=4.0, dtype=np.uint16)
+                     for b in range(B)]).astype(np.int32)
+    emb = rng.randn(B, 16, D, H, W).astype(np.float32)
+    emb[0, :, 1, 3, 5] = 0.0
+    seg_d = torch.tensor(segs).cuda()
+    e = dev(emb, True)
+    l, a = P.embedding_loss_norm5_labels(e, seg_d, P.WeightedMSE(), affs0_weight=2)
+    l.backward()
+    tgt, wgt = P.make_targets_3d(seg_d)
+    e2 = dev(emb, True)
+    l2, a2 = P.embedding_loss_norm5(e2, tgt, wgt, P.WeightedMSE(), affs0_weight=2)
+    l2.backward()
+    close_s(float(l.detach()), float(l2.detach()), what="loss vs two-step")
+    close_t(a.cpu(), a2.cpu(), what="affs vs two-step")
+    close_t(e.grad.cpu(), e2.grad.cpu(), what="grad vs two-step")
+    to = np.stack([O.seg_to_aff_norm5(sg) for sg in segs])
+    wo = np.stack([np.stack([O.weight_binary_ratio(c) for c in t_]) for t_ in to])
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao = O.embedding_loss_norm5(eo, torch.tensor(to), torch.tensor(wo), O.WeightedMSE(), affs0_weight=2)
+    lo.backward()
+    close_s(float(l.detach()), lo, what="loss vs oracle")
+    close_t(a.cpu(), ao, what="affs vs oracle")
+    close_t(e.grad.cpu(), eo.grad, what="grad vs oracle")
+
+
 # =========================================================================== forward-only tiled kernel + z-shards
 @pytest.mark.parametrize("B,D,H,W", [(1, 18, 64, 96), (2, 7, 37, 44), (1, 5, 30, 30)])
 def test_inference_epilogue_fused(P, O, B, D, H, W):
