@@ -842,7 +842,7 @@ def test_2d_kernels_write_only_their_outputs(P, O, shifts, two_view, labels):
     st = torch.cuda.current_stream().cuda_stream
     if labels:
         wtab = ops.gt_pair_weights(lab[:, None], offs3, 0)
-        rc = lib.pea_affs_loss_labels_fwd_bwd(emb.data_ptr(), lab.data_ptr(), B, C, H, W, offs, K, ops.BORDER_WRAP, 0,
+        rc = lib.pea_affs_loss_labels_fwd_bwd(emb.data_ptr(), lab.data_ptr(), B, C, 1, H, W, offs, K, ops.BORDER_WRAP, 0, 0,
                                               wtab.data_ptr(), norm, coef, affs.data_ptr(), loss.data_ptr(), grad.data_ptr(),
                                               ws.data_ptr(), nws, st)
         check("pea_affs_loss_labels_fwd_bwd", rc)
