@@ -219,56 +219,41 @@ gt_fused_x4(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int 
         L here[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) here[j] = s[p + j];
-        // offsets in groups of kGtUnroll: first every neighbour load and compare of the group (independent, all in
-        // flight together), then the stores and the warp counts -- the warp reduction is a scheduling barrier for the
-        // loads, and one offset at a time the pass was latency-bound (a dependent L2 round trip per offset)
-        for (int k0 = 0; k0 < K; k0 += kGtUnroll) {
-            float a[kGtUnroll][4];
-            unsigned int inb[kGtUnroll];
+#pragma unroll kGtUnroll
+        for (int k = 0; k < K; ++k) {  // unrolled: the neighbour loads of several offsets are in flight together
+            const int dz = tab.dz[k], dy = tab.dy[k], dx = tab.dx[k];
+            const int qz = z + dz, qy = y + dy;
+            const bool row_in = (unsigned)qz < (unsigned)D && (unsigned)qy < (unsigned)H;
+            const int32_t nb = (int32_t)p + (dz * (int32_t)HW + dy * W + dx);
+            float a[4];
+            unsigned int inb = 0;
 #pragma unroll
-            for (int u = 0; u < kGtUnroll; ++u) {
-                const int k = (k0 + u < K) ? k0 + u : K - 1;  // tail: repeat the last offset, result unused
-                const int dz = tab.dz[k], dy = tab.dy[k], dx = tab.dx[k];
-                const int qz = z + dz, qy = y + dy;
-                const bool row_in = (unsigned)qz < (unsigned)D && (unsigned)qy < (unsigned)H;
-                const int32_t nb = (int32_t)p + (dz * (int32_t)HW + dy * W + dx);
-                inb[u] = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool in = row_in && (unsigned)(x + j + dx) < (unsigned)W;
-                    inb[u] |= in ? (1u << j) : 0u;
-                    if (!in) {
-                        a[u][j] = (MODE == 0 && padding) ? 1.f : 0.f;
-                    } else {
-                        const L there = __ldg(s + (nb + j));
-                        bool same = (here[j] == there);
-                        if (MODE == 0) { if (ignore) same = same && (here[j] != (L)0) && (there != (L)0); }
-                        else same = same && (here[j] > (L)0) && (there > (L)0);
-                        a[u][j] = same ? 1.f : 0.f;
-                    }
+            for (int j = 0; j < 4; ++j) {
+                const bool in = row_in && (unsigned)(x + j + dx) < (unsigned)W;
+                inb |= in ? (1u << j) : 0u;
+                if (!in) {
+                    a[j] = (MODE == 0 && padding) ? 1.f : 0.f;
+                } else {
+                    const L there = __ldg(s + (nb + j));
+                    bool same = (here[j] == there);
+                    if (MODE == 0) { if (ignore) same = same && (here[j] != (L)0) && (there != (L)0); }
+                    else same = same && (here[j] > (L)0) && (there > (L)0);
+                    a[j] = same ? 1.f : 0.f;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kGtUnroll; ++u) {
-                const int k = k0 + u;
-                if (k >= K) break;  // block-uniform
-                const uint32_t o = (uint32_t)k * N + p;
-                if (PASS == 1) {
-                    if (live && target) {  // target == nullptr: counts only (pea_gt_pair_weights)
-                        *reinterpret_cast<float4*>(out + o) = make_float4(a[u][0], a[u][1], a[u][2], a[u][3]);
-                        if (mout)
-                            *reinterpret_cast<uint32_t*>(mout + o) =
-                                (inb[u] & 1u) | ((inb[u] & 2u) << 7) | ((inb[u] & 4u) << 14) | ((inb[u] & 8u) << 21);
-                    }
-                    const unsigned int c =
-                        live ? (unsigned)((a[u][0] != 0.f) + (a[u][1] != 0.f) + (a[u][2] != 0.f) + (a[u][3] != 0.f)) : 0u;
-                    const unsigned int tot = __reduce_add_sync(0xffffffffu, c);
-                    if (lane == 0) s_cnt[warp][k] += tot;
-                } else if (live) {
-                    const float wp = s_pos[k], wn = s_neg[k];
-                    *reinterpret_cast<float4*>(out + o) = make_float4(a[u][0] != 0.f ? wp : wn, a[u][1] != 0.f ? wp : wn,
-                                                                      a[u][2] != 0.f ? wp : wn, a[u][3] != 0.f ? wp : wn);
+            const uint32_t o = (uint32_t)k * N + p;
+            if (PASS == 1) {
+                if (live && target) {  // target == nullptr: counts only (pea_gt_pair_weights)
+                    *reinterpret_cast<float4*>(out + o) = make_float4(a[0], a[1], a[2], a[3]);
+                    if (mout) *reinterpret_cast<uint32_t*>(mout + o) = (inb & 1u) | ((inb & 2u) << 7) | ((inb & 4u) << 14) | ((inb & 8u) << 21);
                 }
+                const unsigned int c = live ? (unsigned)((a[0] != 0.f) + (a[1] != 0.f) + (a[2] != 0.f) + (a[3] != 0.f)) : 0u;
+                const unsigned int tot = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0) s_cnt[warp][k] += tot;
+            } else if (live) {
+                const float wp = s_pos[k], wn = s_neg[k];
+                *reinterpret_cast<float4*>(out + o) = make_float4(a[0] != 0.f ? wp : wn, a[1] != 0.f ? wp : wn,
+                                                                  a[2] != 0.f ? wp : wn, a[3] != 0.f ? wp : wn);
             }
         }
     }
