@@ -55,6 +55,33 @@ def test_argument_rejection_without_touching_the_device():
     assert lib.pea_gt_affs2d(one, 99, 1, 8, 8, offs, 2, 0, 1, one, one, None) == -6
 
 
+def test_new_entry_points_reject_bad_arguments_without_touching_the_device():
+    """ABI v4 additions: label-driven loss, weight-pair table, border replicate."""
+    import pea_b200
+    lib = pea_b200._lib.lib
+    one = ctypes.c_void_p(16)
+    offs = (ctypes.c_int32 * 6)(0, -1, 0, 0, 0, -1)
+    nrm = (ctypes.c_float * 2)(1.0, 1.0)
+    # pea_affs_loss_labels_fwd_bwd(emb, labels, B, C, D, H, W, offsets, K, border, semantics, ignore, wtab, norm, coef, ...)
+    f = lib.pea_affs_loss_labels_fwd_bwd
+    assert f(None, one, 1, 16, 1, 64, 64, offs, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -1
+    assert f(one, one, 0, 16, 1, 64, 64, offs, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -2
+    assert f(one, one, 1, 16, 1, 64, 64, offs, 2, 0, 5, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -8   # semantics
+    assert f(one, one, 1, 16, 1, 64, 64, offs, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 0, None) == -5          # workspace
+    # a table that is not multi_offset(shifts <= 12, 4): the caller must take the two-step route
+    assert f(one, one, 1, 16, 1, 64, 64, offs, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -8
+    g = lib.pea_gt_pair_weights
+    assert g(None, 0, 1, 1, 8, 8, offs, 2, 0, 0, 1, 1.0, one, one, 64, None) == -1
+    assert g(one, 0, 1, 1, 8, 8, offs, 2, 3, 0, 1, 1.0, one, one, 64, None) == -8     # semantics
+    assert g(one, 0, 1, 1, 8, 8, offs, 2, 0, 0, 1, 1.0, one, one, 8, None) == -5      # counts scratch too small
+    assert g(one, 0, 1, 1, 8, 6, offs, 2, 0, 0, 1, 1.0, one, one, 64, None) == -2     # W % 4 != 0
+    r = lib.pea_replicate_first
+    assert r(None, 1, 3, 4, 8, 8, 0, 1, None) == -1
+    assert r(one, 1, 2, 4, 8, 8, 0, 1, None) == -4      # needs the three shift-1 channels
+    assert r(one, 1, 3, 4, 8, 8, 0, 0, None) == -2      # shift must be positive
+    assert r(one, 1, 3, 4, 8, 8, 10, 1, None) == -2     # plane smaller than D*H*W
+
+
 def test_offset_tables_match_reference_convention(golden):
     import pea_b200
     g = golden["gt"]
