@@ -44,6 +44,7 @@ int axis2d_blocks(int B, int H, int W, const OffsetTable& tab, int wrap);
 bool canon2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, const float* emb, const float* partner,
                       const float* target, const float* weight);
 int canon2d_blocks(int B, int H, int W);
+bool canon2d_mask_ok(const void* mask, int mask_dtype);
 int launch_canon2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap, const float* target,
                    const float* weight, const void* mask, int mask_dtype, float* affs, float* partials, float* grad,
                    cudaStream_t st);
@@ -350,7 +351,7 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     // fully unrolled persistent kernel.
     // PEA_NO_CANON (read per call, no state kept): test knob that sends these calls to the table-driven axis kernel.
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC && grad_partner == nullptr && getenv("PEA_NO_CANON") == nullptr &&
-        canon2d_eligible(C, D, H, W, tab, emb, partner ? partner : emb, target, weight)) {
+        canon2d_eligible(C, D, H, W, tab, emb, partner ? partner : emb, target, weight) && canon2d_mask_ok(mask, mask_dtype)) {
         float* parts = ws.rinvE;
         if ((rc = launch_canon2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts,
                                  grad_emb, st)))

@@ -21,6 +21,10 @@
 #include "pea_common.cuh"
 #include "pea_tma.cuh"
 
+#ifndef PEA_CANON_MASK_STAGE
+#define PEA_CANON_MASK_STAGE 0  // 1: uint8 masks staged in shared memory one tile ahead instead of per-thread byte loads
+#endif
+
 namespace pea {
 namespace c2 {
 
@@ -136,6 +140,13 @@ struct alignas(128) Stage {
     float sO[CROSS ? kC : 1][CROSS ? TY : 1][TX];  // CROSS: the anchor view's own tile
     int32_t lY[LAB ? Geo<CROSS>::YR : 1][TX];      // LAB: labels of the y-column box
     int32_t lX[LAB ? TY : 1][Geo<CROSS>::XW];      // LAB: labels of the x-row box
+    // uint8 masks of the target / weight groups' footprints, double-buffered over the tile walk (PEA_CANON_MASK_STAGE):
+    // TMA cannot carry them (row pitch W bytes is not a multiple of 16 at W = 696), so every thread loads a few aligned
+    // 32-bit words of the NEXT tile's masks and stores them before it releases the corresponding box
+    uint32_t mY[PEA_CANON_MASK_STAGE && !LAB ? 2 : 1][PEA_CANON_MASK_STAGE && !LAB ? NS : 1]
+              [PEA_CANON_MASK_STAGE && !LAB ? Geo<CROSS>::GY : 1][TX / 4];
+    uint32_t mX[PEA_CANON_MASK_STAGE && !LAB ? 2 : 1][PEA_CANON_MASK_STAGE && !LAB ? NS : 1][PEA_CANON_MASK_STAGE && !LAB ? TY : 1]
+              [Geo<CROSS>::GX / 4];
 };
 
 // One neighbour q of the own pixel p (raw values, channels CHS floats apart): a = <e^_p, e^_q>,
@@ -205,6 +216,9 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
     using G_ = Geo<CROSS>;
     constexpr int YR = G_::YR, XW = G_::XW, CHS_Y = G_::CHS_Y, CHS_X = G_::CHS_X, GY = G_::GY, GX = G_::GX;
     constexpr bool REV = GRAD && !CROSS;  // the pair anchored at p + s, whose partner is p, contributes to grad(p)
+    constexpr bool MST = PEA_CANON_MASK_STAGE && MASK == PEA_MASK_U8 && !LAB;  // masks staged in shared memory
+    constexpr int NWY = NS * GY * (TX / 4), NWX = NS * TY * (GX / 4);          // 32-bit words of the two mask groups
+    constexpr int RY = (NWY + NT - 1) / NT, RX = (NWX + NT - 1) / NT;          // words per thread
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     static_assert(!(LAB && (CROSS || MASK != PEA_MASK_NONE)), "label-driven flavour: one view, mask derived in the kernel");
     Stage<CROSS, LAB>& S = *reinterpret_cast<Stage<CROSS, LAB>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
@@ -258,6 +272,23 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < K; ++k) lossacc[k] = 0.f;
 
+    // word `idx` of a tile's y-channel (isx = false) or x-channel mask group: rows y0 .., columns x0 .. of channel
+    // 2 j (+ 1); outside the image the circular border wraps (whole words: W % 4 == 0), the zero border reads 0
+    auto mask_word = [&](bool isx, int idx, int b, int y0, int x0) -> uint32_t {
+        const int wpr = isx ? GX / 4 : TX / 4, rows = isx ? TY : GY;
+        const int j = idx / (rows * wpr), rem = idx - j * rows * wpr;
+        const int row = rem / wpr, wc = rem - row * wpr;
+        int gy = y0 + row, gx = x0 + 4 * wc;
+        if (wrap) {
+            gy = wrap3(gy, H);
+            gx = wrap3(gx, W);
+        } else if (gy >= H || gx >= W) {
+            return 0u;
+        }
+        const uint8_t* m = reinterpret_cast<const uint8_t*>(P.mask) + (int64_t)b * K * Nu;
+        return __ldg(reinterpret_cast<const uint32_t*>(m + ((uint32_t)(2 * j + (isx ? 1 : 0)) * Nu + (uint32_t)(gy * W + gx))));
+    };
+
     int t = blockIdx.x;
     if (threadIdx.x == 0) {
         mbar_init(&barY, 1);
@@ -268,6 +299,12 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         tile_origin(t, b, y0, x0);
         issueY(b, y0, x0);
         issueX(b, y0, x0);
+    }
+    if (MST && t < n_tiles) {  // the first tile's masks, synchronously
+        int b, y0, x0;
+        tile_origin(t, b, y0, x0);
+        for (int idx = threadIdx.x; idx < NWY; idx += NT) (&S.mY[0][0][0][0])[idx] = mask_word(false, idx, b, y0, x0);
+        for (int idx = threadIdx.x; idx < NWX; idx += NT) (&S.mX[0][0][0][0])[idx] = mask_word(true, idx, b, y0, x0);
     }
     __syncthreads();
     uint32_t phY = 0, phX = 0, it = 0;
@@ -339,7 +376,21 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 }
             }
         };
-        fetch_masks(false, mky);
+        uint32_t nextY[MST ? RY : 1], nextX[MST ? RX : 1];
+        const int mb = (int)(it & 1u);  // this tile's mask buffer; the next tile's is mb ^ 1
+        if (MST) {
+            // the next tile's y group is requested now and stored before the y boxes are released (the release /
+            // acquire chain of the box refill makes it visible); this tile's masks are read after the barrier wait
+            if (has_next) {
+#pragma unroll
+                for (int r = 0; r < RY; ++r) {
+                    const int idx = threadIdx.x + r * NT;
+                    nextY[r] = idx < NWY ? mask_word(false, idx, bn, y0n, x0n) : 0u;
+                }
+            }
+        } else {
+            fetch_masks(false, mky);
+        }
 
         mbar_wait(&barY, phY & 1u);
         if (patch) {
@@ -371,6 +422,14 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             __syncthreads();  // patched y boxes complete
         }
 
+        if (MST) {  // after the wait on barY: the stores of the tile before are visible
+            const uint8_t* my8 = reinterpret_cast<const uint8_t*>(&S.mY[MST ? mb : 0][0][0][0]) + ty * TX + tx;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                mky[j][0] = my8[j * GY * TX];
+                if (REV) mky[j][1] = my8[j * GY * TX + P.shift[j] * TX];
+            }
+        }
         const float* ownY = &S.sY[0][ty + PM][tx];
         const float* ownX = &S.sX[0][ty][tx + PM];
         float* affs_b = P.affs ? P.affs + sample + pix : nullptr;
@@ -395,7 +454,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 G[i] = 0ull;
             }
         }
-        fetch_masks(true, mkx);  // needed after the y part: a third of a tile ahead
+        if (!MST) fetch_masks(true, mkx);  // needed after the y part: a third of a tile ahead
 
         // ---------------- y part: channel 2j pairs p with (y - s, x); the pair anchored at (y + s, x) has p as partner
         {
@@ -435,6 +494,18 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 }
             }
         }
+        if (MST && has_next) {
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                const int idx = threadIdx.x + r * NT;
+                if (idx < NWY) (&S.mY[MST ? mb ^ 1 : 0][0][0][0])[idx] = nextY[r];
+            }
+#pragma unroll
+            for (int r = 0; r < RX; ++r) {
+                const int idx = threadIdx.x + r * NT;
+                nextX[r] = idx < NWX ? mask_word(true, idx, bn, y0n, x0n) : 0u;
+            }
+        }
         __syncwarp();
         if (tx == 0 && arrive_count(&cntY) == goal && has_next) issueY(bn, y0n, x0n);
 
@@ -470,6 +541,14 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
             }
             __syncthreads();  // patched x boxes complete
         }
+        if (MST) {
+            const uint8_t* mx8 = reinterpret_cast<const uint8_t*>(&S.mX[MST ? mb : 0][0][0][0]) + ty * GX + tx;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                mkx[j][0] = mx8[j * TY * GX];
+                if (REV) mkx[j][1] = mx8[j * TY * GX + P.shift[j]];
+            }
+        }
         {
             const float* tq = &S.tX[0][ty][tx];
             const float* wq = &S.wX[0][ty][tx];
@@ -502,6 +581,13 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                     float a2;
                     pair<CHS_X, true>(ownX + s, e, G, t_r, w_r, P.gcoef[2 * j + 1], a2);
                 }
+            }
+        }
+        if (MST && has_next) {
+#pragma unroll
+            for (int r = 0; r < RX; ++r) {
+                const int idx = threadIdx.x + r * NT;
+                if (idx < NWX) (&S.mX[MST ? mb ^ 1 : 0][0][0][0])[idx] = nextX[r];
             }
         }
         __syncwarp();
@@ -571,6 +657,11 @@ bool canon2d_eligible(int C, int D, int H, int W, const OffsetTable& tab, const 
     // the hand patch of edge tiles maps coordinates through wrap3 (-n <= v < 4n); TMA needs a 16-byte row pitch
     if (W % 4 != 0 || H < 32 || W < 64) return false;
     return (int64_t)16 * H * W < ((int64_t)1 << 31);
+}
+
+// staged uint8 masks are read as aligned 32-bit words
+bool canon2d_mask_ok(const void* mask, int mask_dtype) {
+    return !(PEA_CANON_MASK_STAGE && mask_dtype == PEA_MASK_U8 && (reinterpret_cast<uintptr_t>(mask) & 3));
 }
 
 static int canon_grid(int n_tiles) {
