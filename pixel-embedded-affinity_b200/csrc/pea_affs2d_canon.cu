@@ -1,7 +1,12 @@
 // Fused 2-D kernel for the CANONICAL offset tables multi_offset([s0..s4], neighbor=4) with shifts <= 12 -- channel 2j
 // is the y shift [-s_j, 0], channel 2j + 1 the x shift [0, -s_j] (scripts_cvppp/utils/affinity_ours.py:4-15; the
-// BBBC039V1 table [1, 3, 5, 9, 11] of bbbc039v1.yaml:65-71) -- one view, embedding_loss
-// (scripts_cvppp/loss/loss_embedding_mse.py:18-47): embedding -> 10 affinities -> masked weighted MSE -> gradient.
+// BBBC039V1 table [1, 3, 5, 9, 11] of bbbc039v1.yaml:65-71): embedding -> 10 affinities -> masked weighted MSE ->
+// gradient, in three flavours of one template:
+//   SELF   embedding_loss      (scripts_cvppp/loss/loss_embedding_mse.py:18-47), described below;
+//   CROSS  ema_embedding_loss  (:79-95) with the second view constant: only the pair anchored at p exists -- upper / left
+//          halo only, tile-sized target / weight groups, the anchor view's own tile in a box of its own;
+//   LAB    embedding_loss from instance labels (the data provider's gen_affs_ours + weight_binary_ratio folded in,
+//          SURVEY.md 8(f) item 1): the int32 label plane is staged instead of the target / weight groups.
 //
 // Design (DESIGN.md "K2c"): the 3-D kernel's in-plane recipe on a persistent 2-D tile walk.
 //   * a CTA of 16 warps owns 16 x 32 pixels; it walks tiles t = blockIdx.x, + gridDim.x, ...; per tile the RAW
@@ -16,7 +21,8 @@
 //     multiple of 16 bytes at W = 696, so TMA cannot carry it -- is fetched per thread, one part of the tile ahead;
 //   * circular border (torch.roll): TMA zero-fills what lies outside the image; on the tiles whose boxes cross the image
 //     edge (17 % at 520 x 696) exactly those elements are then patched by hand through the wrap rule.
-// The one-tile-per-CTA table-driven kernel (pea_affs2d_axis.cu) executes ~2400 instructions per pixel, this one ~1500.
+// The table-driven kernel (pea_affs2d_axis.cu) executes ~2400 instructions per pixel, this one ~2000 (ncu: 0.373 ms one
+// tile per CTA, 0.356 ms persistent, 0.280 ms here at B = 8, 520 x 696).
 #include <cstdlib>
 #include "pea_common.cuh"
 #include "pea_tma.cuh"
