@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PEA_ABI_VERSION 4
+#define PEA_ABI_VERSION 5
 #define PEA_MAX_OFFSETS 64
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -104,13 +104,16 @@ int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, in
  * loss_out (device, 1 + K floats) receives [loss, loss_0 .. loss_{K-1}].
  * grad_emb (B,C,D,H,W) receives d loss / d emb for an upstream gradient of 1; grad_partner likewise for
  * the partner embedding; either may be NULL (not computed).  affs may be NULL (not stored).
- * mask may be NULL with mask_dtype = PEA_MASK_NONE. */
+ * mask may be NULL with mask_dtype = PEA_MASK_NONE.
+ * ticket (optional, may be NULL): one device uint32 that is ZERO on entry and is left zero.  With it the kernels that
+ * support it reduce the per-CTA loss partials themselves (last CTA to arrive, fixed order: reproducible) instead of a
+ * second launch; one call in flight per ticket word (the Python layer keeps one per stream). */
 int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
                           const int32_t* offsets, int K, int border, int impl,
                           const float* target, const float* weight, const void* mask, int mask_dtype,
                           const float* loss_norm, const float* loss_coef,
                           float* affs, float* loss_out, float* grad_emb, float* grad_partner,
-                          void* workspace, size_t ws_bytes, void* stream);
+                          void* workspace, size_t ws_bytes, uint32_t* ticket, void* stream);
 
 /* Backward of pea_affs_fwd for an arbitrary upstream gradient (criterion other than WeightedMSE, or a
  * caller that back-propagates through the returned 2-D affs, scripts_cvppp/loss/loss_embedding_mse.py:46).

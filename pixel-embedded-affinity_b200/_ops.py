@@ -106,6 +106,32 @@ def _workspace(B, C, D, H, W, K, cross, device):
     return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
+_TICKETS = {}       # (device index, stream handle) -> one-element int32 view
+_TICKET_POOL = {}   # device index -> [int32 zeros (256,), slots handed out]
+
+
+def _ticket(device):
+    """One zero-initialised device word per (device, stream): the fused kernels that finalize the loss themselves count
+    their CTAs on it and leave it zero (include/pea_b200.h, `ticket`).  Slots come out of a per-device pool created on
+    the first call, so nothing is allocated per call and a captured CUDA graph keeps pointing at live memory.  Returns
+    None (=> separate finalize launch) if the very first call on a device happens inside a graph capture."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(device).cuda_stream)
+    t = _TICKETS.get(key)
+    if t is None:
+        pool = _TICKET_POOL.get(idx)
+        if pool is None:
+            if torch.cuda.is_current_stream_capturing():
+                return None
+            pool = _TICKET_POOL[idx] = [torch.zeros(256, dtype=torch.int32, device=device), 0]
+            torch.cuda.current_stream(device).synchronize()  # zero-filled before any other stream counts on a slot
+        if pool[1] >= pool[0].numel():
+            return None
+        t = _TICKETS[key] = pool[0][pool[1]:pool[1] + 1]
+        pool[1] += 1
+    return t
+
+
 EPI_RELU = 0x100  # PEA_EPI_RELU: or-ed into the impl hint of pea_affs_fwd
 
 
@@ -190,7 +216,7 @@ def affs_loss_fwd_bwd(emb, partner, offs3, border, target, weight, mask, loss_no
     with torch.cuda.device(dev):
         rc = lib.pea_affs_loss_fwd_bwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, _ptr(target),
                                        _ptr(weight), _ptr(mask), mdt, nptr, cptr, _ptr(affs), _ptr(loss_out), _ptr(grad),
-                                       _ptr(gpar), _ptr(ws), n, _stream())
+                                       _ptr(gpar), _ptr(ws), n, _ptr(_ticket(dev)), _stream())
     check("pea_affs_loss_fwd_bwd", rc)
     return loss_out, affs, grad, gpar
 

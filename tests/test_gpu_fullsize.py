@@ -11,9 +11,10 @@ RTOL = 1e-5   # fp32 tolerance of BASELINE.json's north_star, relative to the la
 
 
 def close(a, b, what, rtol=RTOL):
-    scale = float(b.abs().max())
-    err = float((a - b).abs().max())
-    assert err <= rtol * max(scale, 1e-30), f"{what}: |delta| {err:.3e} vs scale {scale:.3e}"
+    scale = max(float(b.abs().max()), 1e-30)
+    delta = (a - b).abs().double()
+    excess = float((delta - (rtol * b.abs().double() + 0.1 * rtol * scale)).max())
+    assert excess <= 0.0, f"{what}: |delta| {float(delta.max()):.3e} exceeds rtol {rtol:g} + atol {0.1 * rtol:g} * {scale:.3e} by {excess:.3e}"
 
 
 @pytest.fixture(scope="module")

@@ -2,8 +2,10 @@
 reference and (2) the CPU oracle on the same seeded inputs.
 
 Tolerances (BASELINE.json north_star): ground-truth affinities, masks and weights bit-exact; affinities, loss and
-embedding gradients within 1e-5 relative in fp32.  "Relative" for a tensor is measured against its largest
-magnitude (inf-norm): |ours - ref|_inf <= 1e-5 * |ref|_inf; scalar losses use plain relative error.
+embedding gradients within 1e-5 relative in fp32, written as SURVEY.md 7.4-6 prescribes, element by element:
+    |ours - ref| <= rtol * |ref| + (rtol / 10) * max|ref|        rtol = 1e-5, i.e. atol = 1e-6 * scale
+(small-magnitude elements are held to a tenth of what a pure inf-norm test would allow them); scalar losses use plain
+relative error.
 """
 import numpy as np
 import pytest
@@ -23,9 +25,14 @@ def close_t(ours, ref, rtol=RTOL, what=""):
     ours = ours.detach().cpu().numpy() if isinstance(ours, torch.Tensor) else np.asarray(ours)
     ref = ref.detach().cpu().numpy() if isinstance(ref, torch.Tensor) else np.asarray(ref)
     assert ours.shape == ref.shape, (what, ours.shape, ref.shape)
+    if ours.size == 0:
+        return
     scale = max(float(np.abs(ref).max()), 1e-30)
-    err = float(np.abs(ours.astype(np.float64) - ref.astype(np.float64)).max())
-    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} > {rtol:g} * {scale:.3e}"
+    ref64 = ref.astype(np.float64)
+    delta = np.abs(ours.astype(np.float64) - ref64)
+    excess = float((delta - (rtol * np.abs(ref64) + 0.1 * rtol * scale)).max())
+    assert excess <= 0.0, (f"{what}: |delta| exceeds {rtol:g} * |ref| + {0.1 * rtol:g} * {scale:.3e} by {excess:.3e} "
+                           f"(max |delta| {float(delta.max()):.3e})")
 
 
 def close_s(ours, ref, rtol=RTOL, what=""):
@@ -263,21 +270,44 @@ def test_oracle_2d(P, O, B, C, H, W, shifts, nb, seed):
     close_t(e.grad, 3.0 * eo.grad, what="ema grad, scaled upstream")
 
 
+def _criteria(P):
+    """(name, oracle-side callable, drop-in criterion) for every non-fused criterion the reference ships
+    (scripts_*/loss/loss.py:126-152).  The BCE flavours need predictions in [0, 1]: callers feed embeddings with
+    non-negative components, whose cosine affinities are."""
+    F = torch.nn.functional
+    return (("MSELoss", lambda p, t, w: F.mse_loss(p, t), P.MSELoss()),
+            ("BCELoss", lambda p, t, w: F.binary_cross_entropy(p, t), P.BCELoss()),
+            ("WeightedBCE", lambda p, t, w: F.binary_cross_entropy(p, t, w), P.WeightedBCE()))
+
+
 def test_non_fused_criterion_2d(P, O):
-    """Criteria other than WeightedMSE run the CUDA affinity op + the criterion in PyTorch, like the reference loop."""
+    """Criteria other than WeightedMSE run the CUDA affinity op + the criterion in PyTorch, like the reference loop;
+    the gradient comes back through pea_affs_bwd (K5)."""
     offsets = O.multi_offset([1, 3], neighbor=4)
     emb, ema, tgt, wgt, msk = _inputs_2d(O, 2, 16, 20, 24, offsets, 7)
-    for crit_o, crit_p in ((torch.nn.MSELoss(), P.MSELoss()),):
+    emb, ema = np.abs(emb) + 0.05, np.abs(ema) + 0.05
+    for name, crit_o, crit_p in _criteria(P):
         eo = torch.tensor(emb, requires_grad=True)
-        lo, ao, allo = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk),
-                                        lambda p, t, w: crit_o(p, t), offsets)
+        lo, ao, allo = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), crit_o, offsets)
         lo.backward()
         e = dev(emb, True)
         l, a, al = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), crit_p, offsets)
         l.backward()
-        close_s(l, lo, what="MSELoss loss")
-        close_t(e.grad, eo.grad, what="MSELoss grad")
-        close_t(np.asarray(list(al)), np.asarray(allo), what="MSELoss all_loss")
+        close_s(l, lo, what=f"{name} loss")
+        close_t(a, ao, what=f"{name} affs")
+        close_t(e.grad, eo.grad, what=f"{name} grad")
+        close_t(np.asarray(list(al)), np.asarray(allo), what=f"{name} all_loss")
+        # two views, gradient to both
+        eo, uo = torch.tensor(emb, requires_grad=True), torch.tensor(ema, requires_grad=True)
+        lo, ao = O.ema_embedding_loss(eo, uo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), crit_o, offsets,
+                                      affs0_weight=2)
+        lo.backward()
+        e, u = dev(emb, True), dev(ema, True)
+        l, a = P.ema_embedding_loss(e, u, dev(tgt), dev(wgt), dev(msk), crit_p, offsets, affs0_weight=2)
+        l.backward()
+        close_s(l, lo, what=f"{name} ema loss")
+        close_t(e.grad, eo.grad, what=f"{name} ema grad")
+        close_t(u.grad, uo.grad, what=f"{name} ema grad wrt partner")
 
 
 def _inputs_3d(O, B, C, D, H, W, K, seed, replicate=False):
@@ -291,6 +321,38 @@ def _inputs_3d(O, B, C, D, H, W, K, seed, replicate=False):
         tgt[b] = O.seg_to_aff_norm5(lab) if K == 12 else O.seg_to_aff(lab, pad='replicate' if replicate else '')
         wgt[b] = np.stack([O.weight_binary_ratio(c) for c in tgt[b]])
     return emb, ema, tgt, wgt
+
+
+def test_non_fused_criterion_3d(P, O):
+    """3-D route for criteria other than WeightedMSE (scripts_ac3ac4/loss/loss_embedding_mse.py:159-163): CUDA affinity
+    op (tiled forward kernel for the 12-offset set, table-driven otherwise), per-channel cropped criterion calls in
+    PyTorch, gradient through pea_affs_bwd."""
+    for (B, Cc, D, H, W, K, seed) in ((1, 16, 6, 30, 32, 12, 21), (2, 16, 5, 14, 18, 3, 22)):
+        emb, ema, tgt, wgt = _inputs_3d(O, B, Cc, D, H, W, K, seed)
+        emb, ema = np.abs(emb) + 0.05, np.abs(ema) + 0.05
+        fo, fp = (O.embedding_loss_norm5, P.embedding_loss_norm5) if K == 12 else (O.embedding_loss_norm1, P.embedding_loss_norm1)
+        xo, xp = ((O.ema_embedding_loss_norm5, P.ema_embedding_loss_norm5) if K == 12
+                  else (O.ema_embedding_loss_norm1, P.ema_embedding_loss_norm1))
+        for name, crit_o, crit_p in _criteria(P):
+            eo = torch.tensor(emb, requires_grad=True)
+            lo, ao = fo(eo, torch.tensor(tgt), torch.tensor(wgt), crit_o, affs0_weight=1.5)
+            lo.backward()
+            e = dev(emb, True)
+            l, a = fp(e, dev(tgt), dev(wgt), crit_p, affs0_weight=1.5)
+            l.backward()
+            assert not a.requires_grad
+            close_s(l, lo, what=f"K={K} {name} loss")
+            close_t(a, ao, what=f"K={K} {name} affs")
+            close_t(e.grad, eo.grad, what=f"K={K} {name} grad")
+            eo, uo = torch.tensor(emb, requires_grad=True), torch.tensor(ema, requires_grad=True)
+            lo, ao = xo(eo, uo, torch.tensor(tgt), torch.tensor(wgt), crit_o, affs0_weight=1.5)
+            lo.backward()
+            e, u = dev(emb, True), dev(ema, True)
+            l, a = xp(e, u, dev(tgt), dev(wgt), crit_p, affs0_weight=1.5)
+            l.backward()
+            close_s(l, lo, what=f"K={K} {name} ema loss")
+            close_t(e.grad, eo.grad, what=f"K={K} {name} ema grad")
+            close_t(u.grad, uo.grad, what=f"K={K} {name} ema grad wrt partner")
 
 
 @pytest.mark.parametrize("B,C,D,H,W,seed", [(2, 16, 7, 31, 45, 11), (1, 16, 18, 40, 36, 12), (1, 8, 5, 28, 28, 13)])
@@ -849,7 +911,7 @@ def test_2d_kernels_write_only_their_outputs(P, O, shifts, two_view, labels):
     else:
         rc = lib.pea_affs_loss_fwd_bwd(emb.data_ptr(), par.data_ptr() if two_view else None, B, C, 1, H, W, offs, K,
                                        ops.BORDER_WRAP, ops.IMPL_AUTO, tgt.data_ptr(), wgt.data_ptr(), msk.data_ptr(), ops.MASK_U8,
-                                       norm, coef, affs.data_ptr(), loss.data_ptr(), grad.data_ptr(), None, ws.data_ptr(), nws, st)
+                                       norm, coef, affs.data_ptr(), loss.data_ptr(), grad.data_ptr(), None, ws.data_ptr(), nws, None, st)
         check("pea_affs_loss_fwd_bwd", rc)
     torch.cuda.synchronize()
     for name, buf, n in (("affs", affs_buf, B * K * H * W), ("grad", grad_buf, B * C * H * W), ("loss", loss_buf, 1 + K),
