@@ -74,6 +74,32 @@ def make_labels(w, seed):
     return np.stack(out)
 
 
+def config_dict(w, name):
+    """The SAME dict in both arms (the driver compares them)."""
+    return {"workload": w["descr"], "name": name, "batch": w["B"],
+            "l2": "flushed between timed steps (256 MiB memset, untimed); step working set also exceeds L2",
+            "timing": "ours: CUDA events around a CUDA-graph replay of the public-API fwd+bwd, max over ranks; "
+                      "reference arm: wall clock around the reference's CPU fwd+bwd on the host cores"}
+
+
+def cpu_impl():
+    """(namespace with the reference's loss functions and criterion, kind).  The UNMODIFIED reference files staged under
+    baseline/_ref by build() when they travelled with the snapshot (kind "reference"), else the oracle port."""
+    from oracle import ref_loader
+    if ref_loader.available():
+        try:
+            import types
+            ref = ref_loader.load()
+            ns = types.SimpleNamespace(embedding_loss=ref.loss2d.embedding_loss, embedding_loss_norm5=ref.loss3d.embedding_loss_norm5,
+                                       WeightedMSE=ref.crit.WeightedMSE, gen_affs_ours=ref.aff2d.gen_affs_ours,
+                                       seg_to_aff=ref.aff3d.seg_to_aff, weight_binary_ratio=ref.seg.weight_binary_ratio)
+            return ns, "reference"
+        except Exception as ex:  # noqa: BLE001
+            sys.stderr.write(f"reference files unusable ({type(ex).__name__}: {ex}); timing the oracle port\n")
+    from oracle import pea_oracle as O
+    return O, "port"
+
+
 def host_inputs_oracle(w, seed, B=None):
     """Everything on the host through the oracle (reference arm / cpu_baseline)."""
     from oracle import pea_oracle as O
@@ -94,14 +120,30 @@ def host_inputs_oracle(w, seed, B=None):
     return emb, torch.tensor(tgt), torch.tensor(wgt), (torch.tensor(msk) if msk is not None else None), offsets
 
 
-def oracle_step(w, emb, tgt, wgt, msk, offsets):
-    from oracle import pea_oracle as O
+class host_only:
+    """While the reference's CPU path is being timed, `Tensor.cuda()` is a no-op: its WeightedMSE moves the normaliser
+    with `.cuda()` (scripts_cvppp/loss/loss.py:116), which on a GPU box would put the loss scalar on the device."""
+
+    def __enter__(self):
+        self.saved = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self.saved
+
+
+def oracle_step(w, emb, tgt, wgt, msk, offsets, impl=None, full=False):
+    """One fwd+bwd of the reference's CPU implementation (reference files or the port, see cpu_impl)."""
+    O = impl or cpu_impl()[0]
     e = emb.detach().requires_grad_(True)
-    if w["nd"] == 2:
-        loss, _, _ = O.embedding_loss(e, tgt, wgt, msk, O.WeightedMSE(), offsets)
-    else:
-        loss, _ = O.embedding_loss_norm5(e, tgt, wgt, O.WeightedMSE())
-    loss.backward()
+    with host_only():
+        if w["nd"] == 2:
+            loss, affs, _ = O.embedding_loss(e, tgt, wgt, msk, O.WeightedMSE(), offsets)
+        else:
+            loss, affs = O.embedding_loss_norm5(e, tgt, wgt, O.WeightedMSE())
+        loss.backward()
+    if full:
+        return float(loss.detach()), affs.detach(), e.grad
     return float(loss.detach())
 
 
@@ -152,12 +194,13 @@ def run_reference(args, rank):
     w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    impl, kind = cpu_impl()
     alg_bytes, K = algorithmic_bytes_per_step(w)
     # bounded sample: shrink the batch until K steps fit in the budget
     B = w["B"]
     emb, tgt, wgt, msk, offsets = host_inputs_oracle(w, 0, B)
     t0 = time.perf_counter()
-    oracle_step(w, emb, tgt, wgt, msk, offsets)
+    oracle_step(w, emb, tgt, wgt, msk, offsets, impl)
     t1 = time.perf_counter() - t0
     budget = 240.0
     while B > 1 and t1 * (B / w["B"]) * (args.steps + args.warmup) > budget:
@@ -165,19 +208,20 @@ def run_reference(args, rank):
     if B != w["B"]:
         emb, tgt, wgt, msk, offsets = host_inputs_oracle(w, 0, B)
     for _ in range(max(args.warmup - 1, 0)):
-        oracle_step(w, emb, tgt, wgt, msk, offsets)
+        oracle_step(w, emb, tgt, wgt, msk, offsets, impl)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(w, emb, tgt, wgt, msk, offsets)
+        oracle_step(w, emb, tgt, wgt, msk, offsets, impl)
     dt = time.perf_counter() - t0
     vox = B * K * int(np.prod(w["spatial"]))
     value = vox * args.steps / dt
-    sample = f"{args.steps} fwd+bwd calls of the oracle port (torch CPU) at B={B} of the workload's B={w['B']}"
+    what = "the reference's own files (baseline/_ref, unmodified)" if kind == "reference" else "the oracle port"
+    sample = f"{args.steps} fwd+bwd calls of {what} (torch CPU, {cores} threads) at B={B} of the workload's B={w['B']}"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["descr"], "name": args.workload, "sample_batch": B},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_dict(w, args.workload),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -551,19 +595,102 @@ def time_inference_epilogue(P, device, shape=(100, 1024, 1024), iters=5):
 def cpu_baseline(w, seconds=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    impl, kind = cpu_impl()
     emb, tgt, wgt, msk, offsets = host_inputs_oracle(w, 0)
-    oracle_step(w, emb, tgt, wgt, msk, offsets)  # warm-up
+    oracle_step(w, emb, tgt, wgt, msk, offsets, impl)  # warm-up
     n, t0 = 0, time.perf_counter()
     while True:
-        oracle_step(w, emb, tgt, wgt, msk, offsets)
+        oracle_step(w, emb, tgt, wgt, msk, offsets, impl)
         n += 1
         dt = time.perf_counter() - t0
         if dt > seconds or n >= 20:
             break
     _, K = algorithmic_bytes_per_step(w)
     vox = w["B"] * K * int(np.prod(w["spatial"]))
-    return {"value": vox * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} full-batch fwd+bwd calls of the oracle port (torch CPU, {cores} threads), {dt:.1f} s"}
+    what = "the reference's own files (baseline/_ref, unmodified)" if kind == "reference" else "the oracle port"
+    return {"value": vox * n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n} full-batch fwd+bwd calls of {what} (torch CPU, {cores} threads), {dt:.1f} s"}
+
+
+def cpu_gt_baseline(w, seconds=6.0):
+    """the reference's GT functions (a10-a12) are single-threaded NumPy / SciPy, called per sample inside
+    DataLoader workers: time ONE sample on one core, and quote the x num_workers equivalent (cvppp.yaml:49 /
+    bbbc039v1.yaml:49 use 2-8 workers)."""
+    impl, kind = cpu_impl()
+    lab = make_labels(dict(w, B=1), 0)[0]
+    K = 12 if w["nd"] == 3 else 2 * len(w["shifts"])
+    if w["nd"] == 2:
+        from oracle import pea_oracle as O
+        offsets = O.multi_offset(w["shifts"], 4)
+
+        def one():
+            t, m = impl.gen_affs_ours(lab, offsets, ignore=False, padding=True)
+            return [impl.weight_binary_ratio(c) for c in t]
+    else:
+        from oracle import pea_oracle as O
+        nhoods = [O.mknhood3d(1)] + [np.asarray([[-a, 0, 0], [0, -b, 0], [0, 0, -c]]) for a, b, c in ((2, 3, 3), (3, 9, 9), (4, 27, 27))]
+
+        def one():
+            t = np.concatenate([impl.seg_to_aff(lab, nh, pad='') for nh in nhoods], axis=0)
+            return [impl.weight_binary_ratio(c) for c in t]
+    one()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        one()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds or n >= 50:
+            break
+    per = dt / n
+    vox = K * int(np.prod(w["spatial"]))
+    return {"ms_per_sample": per * 1e3, "value": vox / per, "unit": UNIT + " (GT only, one sample, one core)",
+            "value_x8_workers": 8 * vox / per, "cores": 1, "kind": kind,
+            "sample": f"{n} samples of gen_affs_ours/seg_to_aff + weight_binary_ratio x {K} channels, {dt:.1f} s"}
+
+
+def parity_vs_cpu(P, w, device):
+    """The GPU path against the reference's CPU path on the SAME seeded batch (the cpu_baseline leg's inputs): loss,
+    affinities, gradient.  Tolerance of tests/: |d| <= 1e-5 |ref| + 1e-6 max|ref| element by element."""
+    impl, kind = cpu_impl()
+    emb, tgt, wgt, msk, offsets = host_inputs_oracle(w, 0)
+    lo, ao, go = oracle_step(w, emb, tgt, wgt, msk, offsets, impl, full=True)
+    e = emb.to(device).requires_grad_(True)
+    crit = P.WeightedMSE()
+    if w["nd"] == 2:
+        loss, affs, _ = P.embedding_loss(e, tgt.to(device), wgt.to(device), msk.to(device), crit, offsets)
+    else:
+        loss, affs = P.embedding_loss_norm5(e, tgt.to(device), wgt.to(device), crit)
+    loss.backward()
+    out = {"against": kind, "loss_gpu": float(loss), "loss_cpu": lo, "loss_rel": abs(float(loss) - lo) / max(abs(lo), 1e-30)}
+    worst = out["loss_rel"] / 1e-5
+    for name, a, b in (("affs", affs.detach().cpu(), ao), ("grad", e.grad.cpu(), go)):
+        scale = float(b.abs().max())
+        d = (a.double() - b.double()).abs()
+        out[name + "_max_abs_over_scale"] = float(d.max()) / max(scale, 1e-30)
+        worst = max(worst, float((d / (1e-5 * b.abs().double() + 1e-6 * scale)).max()))
+    out["parity_max_rel"] = max(out["loss_rel"], out["affs_max_abs_over_scale"], out["grad_max_abs_over_scale"])
+    out["tolerance_used"] = worst   # <= 1 means inside rtol 1e-5 + atol 1e-6 * scale everywhere
+    out["ok"] = bool(worst <= 1.0)
+    return out
+
+
+def count_launches(fn):
+    """Kernels launched by one call of fn (torch.profiler / CUPTI), outside any timed region."""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = [ev.name for ev in prof.events() if getattr(ev, "device_type", None) is not None
+                 and "cuda" in str(ev.device_type).lower() and not ev.name.lower().startswith("memcpy")
+                 and not ev.name.lower().startswith("memset")]
+        ours = [n for n in names if "pea::" in n]
+        return len(ours), sorted(set(n.split("(")[0][-60:] for n in ours)), len(names)
+    except Exception as ex:  # noqa: BLE001
+        sys.stderr.write(f"launch count via profiler unavailable ({type(ex).__name__}: {ex})\n")
+        return None, [], None
 
 
 def measured_peak():
@@ -616,6 +743,14 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = measured_peak()
         ms_step = total_ms / args.steps
+        lab0, emb0, tgt0, wgt0, msk0, offs0 = device_inputs(P, w, 0, device)
+        e0 = emb0.clone().requires_grad_(True)
+
+        def one_step():
+            our_step(P, w, e0, tgt0, wgt0, msk0, offs0, P.WeightedMSE())
+            e0.grad = None
+        n_ours, k_names, n_all = count_launches(one_step)
+        del lab0, emb0, tgt0, wgt0, msk0, e0
         achieved = alg_bytes / (statistics.mean(res["per_ms"]) * 1e-3) / 1e9
         also = {}
         if world == 1 and not args.quick:
@@ -641,10 +776,8 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": w["descr"], "name": args.workload, "per_gpu_batch": w["B"],
-                       "parallelism": f"dp{world} (independent batches, no data-path collective)",
-                       "l2": "flushed between timed steps (256 MiB memset, untimed); step working set also exceeds L2",
-                       "timing": "CUDA events around a CUDA-graph replay of the public-API fwd+bwd, max over ranks"},
+            "config": config_dict(w, args.workload),
+            "parallelism": f"dp{world}: every rank runs the workload's batch (independent batches, no data-path collective)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic if args.traffic is not None else NCU_TRAFFIC_BYTES.get(args.workload),
                          "peak_source": peak_src,
@@ -659,12 +792,20 @@ def run_ours(args, rank, world, local_rank):
                               "h2d_bytes_per_step": lapi_bytes, "d2h_bytes_per_step": 4,
                               "what": "embedding + int32 labels from pinned host each step through the label-driven loss "
                                       "(embedding_loss_labels / embedding_loss_norm5_labels), loss read back"},
-            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "gpu_launches": (n_ours if n_ours is not None else LAUNCHES_PER_STEP) * args.steps,
+            "gpu_launches_per_step": {"pea_kernels": n_ours, "all_kernels": n_all, "names": k_names,
+                                      "how": "torch.profiler (CUPTI) over one public-API fwd+bwd outside the timed region"
+                                             if n_ours is not None else "static table (profiler unavailable)"},
             "clocks": clocks,
             "loss": res["loss"],
         }
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(w)
+            line["cpu_baseline"]["gt"] = cpu_gt_baseline(w)
+            line["parity"] = parity_vs_cpu(P, w, device)
+            line["parity_max_rel"] = line["parity"]["parity_max_rel"]
+            if not line["parity"]["ok"]:
+                sys.stderr.write(f"PARITY FAILURE against the CPU {line['parity']['against']}: {line['parity']}\n")
         else:
             line["cpu_baseline"] = None
         if zres is not None:

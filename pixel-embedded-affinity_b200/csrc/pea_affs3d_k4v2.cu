@@ -179,7 +179,7 @@ __device__ __forceinline__ float pair1(const float* __restrict__ nb, int chs, co
 }
 
 #ifndef PEA_K4V2_PAIR
-#define PEA_K4V2_PAIR 2  // in-plane pair evaluation: 0 channel-packed (round 1), 1 lane-packed, 2 lane-packed + scalar update
+#define PEA_K4V2_PAIR 0  // in-plane pair evaluation: 0 channel-packed (round 1), 1 lane-packed, 2 lane-packed + scalar update
 #endif
 
 __device__ __forceinline__ float ld_cg(const float* p) {
@@ -520,17 +520,30 @@ fused3d_norm5_v2(const __grid_constant__ CUtensorMap mapY, const __grid_constant
     if (P.ticket == nullptr) return;  // the caller runs the separate finalize kernel
 
     // ---------------- in-kernel finalize by the last CTA to arrive
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (ty == 0) {  // the partials were written by lanes 0..11 of this warp: fence, then one ticket per CTA
+        __threadfence();
+        __syncwarp();
+        if (tx == 0) s_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     {
-        // warp k owns channel k: lane-strided rows in double, then a fixed shuffle tree => run-to-run reproducible
-        const int k = ty;
+        // warp k owns channel k: every lane keeps four independent loads in flight, rows lane, lane + 32, ...; double
+        // accumulation in a fixed order, then a fixed shuffle tree => run-to-run reproducible
+        const int k = ty, n = (int)gridDim.x;
+        const float* src = P.partials + k;
         double acc = 0.0;
-        for (int i = tx; i < (int)gridDim.x; i += 32) acc += (double)ld_cg(P.partials + (int64_t)i * 12 + k);
+        int i = tx;
+        for (; i + 96 < n; i += 128) {
+            const float v0 = ld_cg(src + (int64_t)i * 12), v1 = ld_cg(src + (int64_t)(i + 32) * 12);
+            const float v2 = ld_cg(src + (int64_t)(i + 64) * 12), v3 = ld_cg(src + (int64_t)(i + 96) * 12);
+            acc += (double)v0;
+            acc += (double)v1;
+            acc += (double)v2;
+            acc += (double)v3;
+        }
+        for (; i < n; i += 32) acc += (double)ld_cg(src + (int64_t)i * 12);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (tx == 0) s_loss[k] = (float)acc / P.norm[k];
@@ -552,7 +565,7 @@ fused3d_norm5_v2(const __grid_constant__ CUtensorMap mapY, const __grid_constant
 
 // ---- host side -------------------------------------------------------------------------------------------------
 #ifndef PEA_K4V2_BALANCE
-#define PEA_K4V2_BALANCE 1  // 0: ceil(H / 12) tiles of 12 rows per strip (A/B)
+#define PEA_K4V2_BALANCE 0  // 0: ceil(H / 12) tiles of 12 rows per strip (A/B)
 #endif
 namespace {
 constexpr int kTY = 12;

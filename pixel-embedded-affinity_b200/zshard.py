@@ -128,16 +128,41 @@ class PeerZShard:
             self._side = torch.cuda.Stream(device=self.buf.device)
         return self._stage, self._side
 
+    # ---- the two-barrier contract of a slab that is rewritten every step -----------------------------------------
+    #   write own  ->  publish()  ->  kernel (reads prev_tail in place)  ->  release()  ->  next write of own
+    # publish() orders every producer's writes before the neighbours' reads; release() orders every rank's reads of its
+    # neighbour's tail before that neighbour's NEXT write.  Without the second barrier rank r-1 may overwrite its slab
+    # while rank r's kernel is still reading the last four slices over NVLink (a cross-GPU write-after-read race that
+    # corrupts slab-boundary affinities silently).  ``affinities()`` issues both.
     def publish(self):
         """Order the producer's writes of ``own`` before the neighbours' reads (device-side barrier on the current
         stream; no host synchronisation)."""
         if self.world > 1:
             self.handle.barrier(channel=0)
 
+    def release(self):
+        """Order this step's reads of the neighbours' slab tails (the kernels enqueued since ``publish()``) before anyone's
+        next write of ``own`` (device-side barrier on the current stream, second channel)."""
+        if self.world > 1:
+            self.handle.barrier(channel=1)
+
+    def affinities(self, out=None, overlapped=False, compute=None):
+        """publish() -> 12-channel affinities of this rank's slab (halo read from the peer in place) -> release().
+        After it returns (stream-ordered) ``own`` may be rewritten for the next volume."""
+        self.publish()
+        if overlapped:
+            out = overlapped_halo_affinities(self, out=out, compute=compute)
+        else:
+            out = fused_halo_affinities(self.own, self.prev_tail, out=out, compute=compute)
+        self.release()
+        return out
+
 
 def fused_halo_affinities(emb_own, prev_tail, out=None, compute=None):
     """12-channel affinities of a slab in ONE launch: ``prev_tail`` (B,C,<=4,H,W; None for the first slab) is read in
-    place -- typically from the peer GPU.  Bit-identical to the same slices of the whole-volume result."""
+    place -- typically from the peer GPU.  Bit-identical to the same slices of the whole-volume result.
+    With peer memory the caller owns the ordering: ``PeerZShard.publish()`` before, ``PeerZShard.release()`` after
+    (or call ``PeerZShard.affinities()``, which does both)."""
     compute = compute or _cuda_compute
     B, C, depth, H, W = emb_own.shape
     if out is None:

@@ -81,3 +81,36 @@ def test_fused_halo_host_logic_with_oracle_compute():
         tail = vol[:, :, z0 - HALO:z0] if r else None
         parts.append(fused_halo_affinities(vol[:, :, z0:z1], tail, compute=compute))
     assert torch.allclose(torch.cat(parts, dim=2), ref, rtol=0, atol=5e-7)
+
+
+def test_peer_zshard_two_barrier_contract():
+    """PeerZShard.affinities() = publish (channel 0) -> kernel -> release (channel 1): the second barrier keeps a
+    neighbour's in-flight reads of this slab's tail apart from the next write of the slab (a cross-GPU write-after-read
+    race otherwise).  Symmetric memory needs GPUs; here the handle is a recorder and the kernel the oracle."""
+    from pea_b200.zshard import PeerZShard, HALO
+    log = []
+
+    class Handle:
+        def barrier(self, channel=0):
+            log.append(("barrier", channel))
+
+    torch.manual_seed(2)
+    vol = torch.randn(1, 16, 9, 30, 32)
+    sh = object.__new__(PeerZShard)
+    sh.rank, sh.world, sh.handle = 1, 2, Handle()
+    sh.z0, sh.z1, sh.depth, sh.halo = 5, 9, 4, HALO
+    sh.own, sh.prev_tail = vol[:, :, 5:9], vol[:, :, 1:5]
+
+    def compute(emb_view, z_skip, out_view, halo=None):
+        log.append(("kernel", None))
+        full = torch.cat([halo, emb_view], dim=2)
+        out_view.copy_(O.inf_embedding_loss_norm5(full)[:, :, halo.shape[2]:])
+
+    out = sh.affinities(compute=compute)
+    assert log == [("barrier", 0), ("kernel", None), ("barrier", 1)]
+    np.testing.assert_allclose(out.numpy(), O.inf_embedding_loss_norm5(vol)[:, :, 5:9].numpy(), rtol=0, atol=2e-7)
+    log.clear()
+    sh.world = 1   # a single rank never synchronises
+    sh.prev_tail = None
+    sh.affinities(compute=lambda e, z, o, h=None: log.append(("kernel", None)))
+    assert log == [("kernel", None)]

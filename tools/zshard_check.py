@@ -35,14 +35,15 @@ except Exception as ex:  # noqa: BLE001
     ps = None
     print(f"rank {rank}: symmetric memory unavailable ({type(ex).__name__}: {ex})", flush=True)
 if ps is not None:
-    ps.own.copy_(vol[:, :, ps.z0:ps.z1])
-    for it in range(3):
-        ps.publish()
-        out = fused_halo_affinities(ps.own, ps.prev_tail)
-        assert torch.equal(out, whole[:, :, ps.z0:ps.z1]), f"rank {rank} iteration {it}: fused-halo slab differs"
-        out2 = overlapped_halo_affinities(ps)
-        assert torch.equal(out2, whole[:, :, ps.z0:ps.z1]), f"rank {rank} iteration {it}: overlapped-halo slab differs"
-        ps.publish()   # nobody overwrites a slab while a neighbour may still be reading it
+    # the slab is REWRITTEN every iteration (a real inference loop): publish / release inside affinities() must keep a
+    # neighbour's in-flight reads of the old tail apart from the next write
+    for it in range(6):
+        g2 = torch.Generator(device="cpu").manual_seed(100 + it)
+        vol_it = torch.randn((1, 16, D, H, W), generator=g2).to(dev)
+        whole_it = P.inf_embedding_loss_norm5(vol_it)
+        ps.own.copy_(vol_it[:, :, ps.z0:ps.z1])
+        out = ps.affinities(overlapped=(it % 2 == 1))
+        assert torch.equal(out, whole_it[:, :, ps.z0:ps.z1]), f"rank {rank} iteration {it}: peer-halo slab differs"
     print(f"zshard_check fused-halo OK rank {rank}/{world}", flush=True)
 torch.cuda.synchronize()
 dist.barrier()
