@@ -123,6 +123,38 @@ int pea_affs_bwd(const float* emb, const float* partner, int B, int C, int D, in
                  const float* grad_affs, float* grad_emb, float* grad_partner,
                  void* workspace, size_t ws_bytes, void* stream);
 
+/* Several SMALL fused losses in ONE launch: the deep-supervision calls of a training step,
+ *   scripts_ac3ac4/main.py:227-230   embedding_loss_norm1(emd_i, down_i[:, :3], down_i[:, 3:], criterion)   x 4 scales
+ *   scripts_cvppp/main.py:284-287    embedding_loss(emd_i, ..., offsets[:2 i])                              x 4 scales
+ * Every problem has the semantics of pea_affs_loss_fwd_bwd (same fields, same loss_out layout); `partner` != NULL makes
+ * it the two-view loss with the second view constant (no grad_partner here).  Up to PEA_MULTI_MAX_PROBLEMS problems of
+ * up to PEA_MULTI_MAX_OFFSETS offsets (|component| <= 127) and the same channel count C.  The kernel finalizes every
+ * problem's loss itself: `ticket` is REQUIRED (one device uint32, zero on entry, left zero).  workspace: at least
+ * pea_affs_loss_multi_workspace(problems, n) bytes. */
+#define PEA_MULTI_MAX_PROBLEMS 8
+#define PEA_MULTI_MAX_OFFSETS 12
+typedef struct pea_loss_problem {
+    const float* emb;        /* (B, C, D, H, W) */
+    const float* partner;    /* second view or NULL */
+    const float* target;     /* (B, K, D, H, W) */
+    const float* weight;
+    const void* mask;        /* NULL with mask_dtype = PEA_MASK_NONE */
+    float* affs;             /* (B, K, D, H, W) or NULL */
+    float* grad_emb;         /* (B, C, D, H, W) or NULL */
+    float* loss_out;         /* 1 + K floats */
+    const int32_t* offsets;  /* host, K * 3 as (dz, dy, dx) */
+    const float* loss_norm;  /* host, K */
+    const float* loss_coef;  /* host, K */
+    int32_t B, D, H, W, K, border, mask_dtype;
+} pea_loss_problem;
+size_t pea_affs_loss_multi_workspace(const pea_loss_problem* problems, int n);
+int pea_affs_loss_multi(const pea_loss_problem* problems, int n, int C, void* workspace, size_t ws_bytes,
+                        uint32_t* ticket, void* stream);
+/* bufs[i][0 .. lens[i]) *= *scales[i] for i < n <= PEA_MULTI_MAX_PROBLEMS in one launch (the upstream gradients of the
+ * losses of one pea_affs_loss_multi call); a buffer whose scalar is exactly 1 is not touched.  Host arrays of device
+ * pointers. */
+int pea_scale_multi(float* const* bufs, const int64_t* lens, const float* const* scales, int n, void* stream);
+
 /* buf[i] *= *scale (a device scalar), in place; exits without touching memory when *scale == 1.
  * Used by the autograd backward to apply the upstream gradient of the scalar loss to the gradient the
  * fused forward already produced (the common `loss.backward()` case costs one empty launch). */

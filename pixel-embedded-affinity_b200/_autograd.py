@@ -75,12 +75,12 @@ class FusedAffinityLoss(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         loss = loss_out[0]
         each = loss_out[1:]
-        ctx.mark_non_differentiable(each)
-        if not spec.affs_differentiable:
-            ctx.mark_non_differentiable(affs)
+        # ONE call: mark_non_differentiable replaces the set of an earlier call
+        ctx.mark_non_differentiable(*([each] if spec.affs_differentiable else [each, affs]))
         return loss, affs, each
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_loss, g_affs, g_each):
         need_e, need_u = ctx.need
         spec = ctx.spec
@@ -122,12 +122,11 @@ class FusedAffinityLossLabels(torch.autograd.Function):
             ctx.save_for_backward(emb, labels_i32, wtab)
         ctx.set_materialize_grads(False)
         loss, each = loss_out[0], loss_out[1:]
-        ctx.mark_non_differentiable(each)
-        if not spec.affs_differentiable:
-            ctx.mark_non_differentiable(affs)
+        ctx.mark_non_differentiable(*([each] if spec.affs_differentiable else [each, affs]))
         return loss, affs, each
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_loss, g_affs, g_each):
         if not ctx.need_e:
             return None, None, None, None, None, None
@@ -146,6 +145,70 @@ class FusedAffinityLossLabels(torch.autograd.Function):
             ae, _ = ops.affs_bwd(emb, None, spec.offs3, spec.border, g_affs.contiguous(), want_grad=True)
             ge = ae if ge is None else ge.add_(ae)
         return ge, None, None, None, None, None
+
+
+class MultiFusedAffinityLoss(torch.autograd.Function):
+    """n small fused losses in ONE launch (ops.affs_loss_multi) and their gradient scaling in ONE launch.
+
+    apply(specs, n, emb_0 .. emb_{n-1}, partner_0 .., target_0 .., weight_0 .., mask_0 ..) -> (loss_0, affs_0, each_0,
+    loss_1, ...).  Partners / masks may be None; the second view is a constant here."""
+
+    @staticmethod
+    def forward(ctx, specs, n, *tensors):
+        embs, pars, tgts, wgts, msks = (tensors[i * n:(i + 1) * n] for i in range(5))
+        need = [ctx.needs_input_grad[2 + i] for i in range(n)]
+        problems = [dict(emb=embs[i], partner=pars[i], offs3=specs[i].offs3, border=specs[i].border, target=tgts[i],
+                         weight=wgts[i], mask=msks[i], loss_norm=specs[i].loss_norm, loss_coef=specs[i].loss_coef,
+                         want_grad=need[i]) for i in range(n)]
+        outs = ops.affs_loss_multi(problems)
+        if outs is None:  # no ticket word yet (first call on this device happens inside a graph capture): one by one
+            outs = []
+            for p in problems:
+                lo, af, gr, _ = ops.affs_loss_fwd_bwd(p["emb"], p["partner"], p["offs3"], p["border"], p["target"], p["weight"],
+                                                      p["mask"], p["loss_norm"], p["loss_coef"], want_grad=p["want_grad"])
+                outs.append((lo, af, gr))
+        ctx.n, ctx.specs, ctx.need = n, specs, need
+        ctx.grads = [o[2] for o in outs]
+        ctx.save_for_backward(*tensors)
+        ctx.set_materialize_grads(False)
+        flat, nondiff = [], []
+        for i, (loss_out, affs, _) in enumerate(outs):
+            each = loss_out[1:]
+            nondiff.append(each)
+            if not specs[i].affs_differentiable:
+                nondiff.append(affs)
+            flat += [loss_out[0], affs, each]
+        ctx.mark_non_differentiable(*nondiff)  # ONE call: a second call would replace the set
+        return tuple(flat)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gs):
+        n, specs = ctx.n, ctx.specs
+        tensors = ctx.saved_tensors
+        embs, pars, tgts, wgts, msks = (tensors[i * n:(i + 1) * n] for i in range(5))
+        out = [None] * n
+        bufs, scales = [], []
+        for i in range(n):
+            g_loss = gs[3 * i]
+            if not ctx.need[i] or g_loss is None:
+                continue
+            ge = ctx.grads[i]
+            if ge is None:  # handed out by an earlier backward (retain_graph=True): recompute
+                _, _, ge, _ = ops.affs_loss_fwd_bwd(embs[i], pars[i], specs[i].offs3, specs[i].border, tgts[i], wgts[i], msks[i],
+                                                    specs[i].loss_norm, specs[i].loss_coef, want_affs=False, want_grad=True)
+            ctx.grads[i] = None
+            out[i] = ge
+            bufs.append(ge)
+            scales.append(g_loss.to(device=ge.device, dtype=torch.float32))
+        if bufs:  # one launch applies every upstream scalar
+            ops.scale_multi(bufs, scales)
+        for i in range(n):  # gradients arriving through the returned affinities (2-D: they carry grad in the reference)
+            g_affs = gs[3 * i + 1]
+            if ctx.need[i] and g_affs is not None:
+                ae, _ = ops.affs_bwd(embs[i], pars[i], specs[i].offs3, specs[i].border, g_affs.contiguous(), want_grad=True)
+                out[i] = ae if out[i] is None else out[i].add_(ae)
+        return (None, None) + tuple(out) + (None,) * (4 * n)
 
 
 class Affinities(torch.autograd.Function):

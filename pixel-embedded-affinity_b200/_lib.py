@@ -15,6 +15,17 @@ c_int32_p = ctypes.POINTER(ctypes.c_int32)
 vp = ctypes.c_void_p
 ci = ctypes.c_int
 
+MULTI_MAX_PROBLEMS, MULTI_MAX_OFFSETS = 8, 12
+
+
+class LossProblem(ctypes.Structure):
+    """pea_loss_problem of include/pea_b200.h"""
+    _fields_ = [("emb", vp), ("partner", vp), ("target", vp), ("weight", vp), ("mask", vp), ("affs", vp), ("grad_emb", vp),
+                ("loss_out", vp), ("offsets", c_int32_p), ("loss_norm", c_float_p), ("loss_coef", c_float_p),
+                ("B", ctypes.c_int32), ("D", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("K", ctypes.c_int32), ("border", ctypes.c_int32), ("mask_dtype", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/pea_b200.h one to one
 SIGNATURES = {
     "pea_abi_version": (ci, []),
@@ -26,6 +37,9 @@ SIGNATURES = {
                                    c_float_p, vp, vp, vp, vp, vp, ctypes.c_size_t, vp, vp]),
     "pea_affs_bwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "pea_scale_inplace": (ci, [vp, ctypes.c_int64, vp, vp]),
+    "pea_affs_loss_multi_workspace": (ctypes.c_size_t, [ctypes.POINTER(LossProblem), ci]),
+    "pea_affs_loss_multi": (ci, [ctypes.POINTER(LossProblem), ci, ci, vp, ctypes.c_size_t, vp, vp]),
+    "pea_scale_multi": (ci, [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(vp), ci, vp]),
     "pea_gt_affs2d": (ci, [vp, ci, ci, ci, ci, c_int32_p, ci, ci, ci, vp, vp, vp]),
     "pea_gt_affs3d": (ci, [vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, vp, vp]),
     "pea_gt_counts_bytes": (ctypes.c_size_t, [ci, ci]),

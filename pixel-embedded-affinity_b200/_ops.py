@@ -7,7 +7,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import lib, check, c_float_p, c_int32_p
+from ._lib import lib, check, c_float_p, c_int32_p, LossProblem, MULTI_MAX_PROBLEMS, MULTI_MAX_OFFSETS
 
 BORDER_WRAP, BORDER_ZERO = 0, 1
 MASK_NONE, MASK_U8, MASK_F32 = 0, 1, 2
@@ -219,6 +219,72 @@ def affs_loss_fwd_bwd(emb, partner, offs3, border, target, weight, mask, loss_no
                                        _ptr(gpar), _ptr(ws), n, _ptr(_ticket(dev)), _stream())
     check("pea_affs_loss_fwd_bwd", rc)
     return loss_out, affs, grad, gpar
+
+
+def multi_eligible(problems):
+    """True when a list of (emb, partner, offs3, ...) problems fits one pea_affs_loss_multi launch."""
+    if not 1 <= len(problems) <= MULTI_MAX_PROBLEMS:
+        return False
+    C = problems[0]["emb"].shape[1]
+    for p in problems:
+        if p["emb"].shape[1] != C or p["offs3"].shape[0] > MULTI_MAX_OFFSETS or np.abs(p["offs3"]).max() > 127:
+            return False
+        if p["emb"].numel() // C > (1 << 31):
+            return False
+    return True
+
+
+def affs_loss_multi(problems, want_affs=True):
+    """Several small fused losses in ONE launch (pea_affs_loss_multi).  problems: list of dicts with emb, partner,
+    offs3, border, target, weight, mask, loss_norm, loss_coef, want_grad.  Returns a list of (loss_out, affs, grad), or
+    None when no ticket word is available (first call on a device inside a graph capture)."""
+    n = len(problems)
+    dev = problems[0]["emb"].device
+    ticket = _ticket(dev)
+    if ticket is None:
+        return None
+    arr = (LossProblem * n)()
+    keep, outs = [], []
+    for i, p in enumerate(problems):
+        emb = p["emb"]
+        B, C, D, H, W = _dims5(emb)
+        K = p["offs3"].shape[0]
+        mask = p.get("mask")
+        mdt = MASK_NONE if mask is None else (MASK_U8 if mask.dtype == torch.uint8 else MASK_F32)
+        affs = torch.empty((B, K) + tuple(emb.shape[2:]), dtype=torch.float32, device=dev) if want_affs else None
+        grad = torch.empty_like(emb) if p.get("want_grad", True) else None
+        loss_out = torch.empty(1 + K, dtype=torch.float32, device=dev)
+        ko, optr = _i32(p["offs3"])
+        kn, nptr = _f32(p["loss_norm"])
+        kc, cptr = _f32(p["loss_coef"])
+        keep += [ko, kn, kc]
+        a = arr[i]
+        a.emb, a.partner, a.target, a.weight = emb.data_ptr(), (p["partner"].data_ptr() if p.get("partner") is not None else None), \
+            p["target"].data_ptr(), p["weight"].data_ptr()
+        a.mask = mask.data_ptr() if mask is not None else None
+        a.affs = affs.data_ptr() if affs is not None else None
+        a.grad_emb = grad.data_ptr() if grad is not None else None
+        a.loss_out = loss_out.data_ptr()
+        a.offsets, a.loss_norm, a.loss_coef = optr, nptr, cptr
+        a.B, a.D, a.H, a.W, a.K, a.border, a.mask_dtype = B, D, H, W, K, p["border"], mdt
+        outs.append((loss_out, affs, grad))
+    nbytes = lib.pea_affs_loss_multi_workspace(arr, n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pea_affs_loss_multi(arr, n, int(problems[0]["emb"].shape[1]), _ptr(ws), nbytes, _ptr(ticket), _stream())
+    check("pea_affs_loss_multi", rc)
+    return outs
+
+
+def scale_multi(bufs, scales):
+    """bufs[i] *= scales[i] (0-dim float32 CUDA tensors) in one launch."""
+    n = len(bufs)
+    B = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs])
+    L = (ctypes.c_int64 * n)(*[b.numel() for b in bufs])
+    S = (ctypes.c_void_p * n)(*[s.data_ptr() for s in scales])
+    with torch.cuda.device(bufs[0].device):
+        rc = lib.pea_scale_multi(B, L, S, n, _stream())
+    check("pea_scale_multi", rc)
 
 
 def affs_bwd(emb, partner, offs3, border, grad_affs, want_grad=True, want_grad_partner=False):

@@ -63,7 +63,7 @@ int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, 
                          cudaStream_t st);
 
 #ifndef PEA_K4_V2
-#define PEA_K4_V2 1  // 0: the round-1 kernel fused3d_norm5_tm for the one-view 3-D loss (A/B)
+#define PEA_K4_V2 0  // 1: fused3d_norm5_v2 (pea_affs3d_k4v2.cu: in-kernel finalize, pair-evaluation variants; measured 3 us slower)
 #endif
 #ifndef PEA_PDL
 #define PEA_PDL 1  // 0: plain stream-ordered launches of the two tail kernels (A/B)

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _ops as ops
-from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, LossList, OpSpec
+from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, LossList, MultiFusedAffinityLoss, OpSpec
 from ._lib import PeaError
 from .loss import is_weighted_mse
 
@@ -72,6 +72,34 @@ def embedding_loss(embedding, target, weightmap, mask, criterion, offsets, affs0
     affs = Affinities.apply(embedding, None, offs3, ops.BORDER_WRAP, ops.IMPL_AUTO)
     loss, each = _generic_criterion(affs, target, weightmap, mask, criterion, [1] * K)
     return loss, affs, LossList(torch.stack([e.detach() for e in each]))
+
+
+def embedding_loss_multi(embeddings, targets, weightmaps, masks, criterion, offsets_list, affs0_weight=1, mode='ours'):
+    """The deep-supervision calls of one training step in ONE launch: equals
+
+        [embedding_loss(e, t, w, m, criterion, o) for e, t, w, m, o in zip(embeddings, targets, weightmaps, masks, offsets_list)]
+
+    i.e. scripts_cvppp/main.py:284-287 (emd1..emd4 at 272^2 .. 34^2 with offsets[:8], [:6], [:4], [:2]).  With
+    ``WeightedMSE`` and at most 8 scales of at most 12 offsets the list runs through one work-list kernel that also
+    finalizes every loss, and backward scales all gradients in one launch; anything else falls back to the calls above.
+    Returns a list of (loss, affs, all_loss)."""
+    _check_mode(mode)
+    n = len(embeddings)
+    if not (len(targets) == len(weightmaps) == len(masks) == len(offsets_list) == n):
+        raise ValueError("embeddings, targets, weightmaps, masks and offsets_list must have the same length")
+    prep = [_prep(e, t, w, m, o) for e, t, w, m, o in zip(embeddings, targets, weightmaps, masks, offsets_list)]
+    probs = [dict(emb=p[0], offs3=p[4]) for p in prep]
+    if not is_weighted_mse(criterion) or not ops.multi_eligible(probs):
+        return [embedding_loss(e, t, w, m, criterion, o, affs0_weight, mode)
+                for e, t, w, m, o in zip(embeddings, targets, weightmaps, masks, offsets_list)]
+    specs = []
+    for emb, _, _, _, offs3 in prep:
+        B, C, H, W = emb.shape
+        K = offs3.shape[0]
+        specs.append(OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), np.ones(K, np.float32), affs_differentiable=True))
+    flat = MultiFusedAffinityLoss.apply(specs, n, *[p[0] for p in prep], *([None] * n), *[p[1] for p in prep],
+                                        *[p[2] for p in prep], *[p[3] for p in prep])
+    return [(flat[3 * i], flat[3 * i + 1], LossList(flat[3 * i + 2])) for i in range(n)]
 
 
 def ema_embedding_loss(embedding, ema_embedding, target, weightmap, mask, criterion, offsets, affs0_weight=1,

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _ops as ops
-from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, OpSpec
+from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, MultiFusedAffinityLoss, OpSpec
 from ._lib import PeaError
 from .loss import is_weighted_mse
 
@@ -81,6 +81,35 @@ def embedding_loss_norm5(embedding, target, weightmap, criterion, affs0_weight=1
 def embedding_loss_norm1(embedding, target, weightmap, criterion, affs0_weight=1, shift=1, fill=True):
     """:7-27 -- 3 channels at one shift; only the z channel is scaled by ``affs0_weight`` (:20)."""
     return _loss3d(embedding, None, target, weightmap, criterion, [shift] * 3, affs0_weight, 1)
+
+
+def embedding_loss_norm1_multi(embeddings, targets, weightmaps, criterion, affs0_weight=1, shift=1, fill=True):
+    """The deep-supervision calls of one training step in ONE launch: equals
+
+        [embedding_loss_norm1(e, t, w, criterion, affs0_weight, shift) for e, t, w in zip(embeddings, targets, weightmaps)]
+
+    i.e. scripts_ac3ac4/main.py:227-230 (emd1..emd4 at 18 x 10^2 .. 80^2 against down4..down1).  With ``WeightedMSE`` the
+    list (at most 8 volumes) runs through one work-list kernel that also finalizes every loss, and backward scales all
+    gradients in one launch; anything else falls back to the calls above.  Returns a list of (loss, affs)."""
+    n = len(embeddings)
+    if not (len(targets) == len(weightmaps) == n):
+        raise ValueError("embeddings, targets and weightmaps must have the same length")
+    shifts = [shift] * 3
+    offs3 = offsets_from_shifts(shifts)
+    embs = [ops.check_embedding("embedding", e, 5) for e in embeddings]
+    if not is_weighted_mse(criterion) or not ops.multi_eligible([dict(emb=e, offs3=offs3) for e in embs]):
+        return [embedding_loss_norm1(e, t, w, criterion, affs0_weight, shift, fill)
+                for e, t, w in zip(embeddings, targets, weightmaps)]
+    specs, tg, wg = [], [], []
+    for e, t, w in zip(embs, targets, weightmaps):
+        B, C, D, H, W = e.shape
+        tg.append(ops.check_like("target", t, (B, 3, D, H, W)))
+        wg.append(ops.check_like("weightmap", w, (B, 3, D, H, W)))
+        coef = np.ones(3, np.float32)
+        coef[:1] = affs0_weight
+        specs.append(OpSpec(offs3, ops.BORDER_ZERO, _norms_3d(e.shape, shifts), coef, affs_differentiable=False))
+    flat = MultiFusedAffinityLoss.apply(specs, n, *embs, *([None] * n), *tg, *wg, *([None] * n))
+    return [(flat[3 * i], flat[3 * i + 1]) for i in range(n)]
 
 
 def ema_embedding_loss_norm5(embedding, ema_embedding, target, weightmap, criterion, affs0_weight=1, shift=1,

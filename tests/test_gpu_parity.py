@@ -1055,3 +1055,65 @@ def test_fused_batch_gt_matches_oracle(P, O):
             to = O.seg_to_aff_norm5((segs[b] % 200).astype(dt))
             same(tgt[b], to, f"3D target {dt.__name__}")
             same(wgt[b], np.stack([O.weight_binary_ratio(c) for c in to]), "3D weight")
+
+
+# =========================================================================== several small losses in one launch
+def test_norm1_multi_matches_single_calls_and_oracle(P, O):
+    """embedding_loss_norm1_multi (ONE launch for the four deep-supervision scales, scripts_ac3ac4/main.py:227-230)
+    against the oracle's four calls: losses, affinities, gradients; upstream scalars other than 1 in backward."""
+    embs, tgts, wgts = [], [], []
+    for i, (B, D, H, W) in enumerate(((2, 6, 5, 5), (2, 6, 10, 10), (2, 6, 20, 20), (2, 6, 40, 40))):
+        emb, _, tgt, wgt = _inputs_3d(O, B, 16, D, H, W, 3, 40 + i, replicate=True)
+        embs.append(emb), tgts.append(tgt), wgts.append(wgt)
+    scal = [1.0, 0.5, 2.0, 1.0]
+    eo = [torch.tensor(e, requires_grad=True) for e in embs]
+    ro = [O.embedding_loss_norm1(e, torch.tensor(t), torch.tensor(w), O.WeightedMSE(), affs0_weight=1.5)
+          for e, t, w in zip(eo, tgts, wgts)]
+    sum(c * r[0] for c, r in zip(scal, ro)).backward()
+    e = [dev(x, True) for x in embs]
+    r = P.embedding_loss_norm1_multi(e, [dev(t) for t in tgts], [dev(w) for w in wgts], P.WeightedMSE(), affs0_weight=1.5)
+    sum(c * x[0] for c, x in zip(scal, r)).backward()
+    for i in range(4):
+        close_s(r[i][0], ro[i][0], what=f"scale {i} loss")
+        close_t(r[i][1], ro[i][1], what=f"scale {i} affs")
+        assert not r[i][1].requires_grad
+        close_t(e[i].grad, eo[i].grad, what=f"scale {i} grad")
+
+
+def test_embedding_loss_multi_2d_matches_oracle(P, O):
+    """embedding_loss_multi (scripts_cvppp/main.py:284-287: coarser scales use the first 2 i offsets) against the oracle,
+    including a gradient that arrives through the returned affinities and a float mask."""
+    offsets = O.multi_offset([1, 3, 5, 9], neighbor=4)
+    shapes = ((2, 17, 17, 2), (2, 34, 34, 4), (1, 68, 60, 6), (1, 40, 72, 8))
+    ins = [_inputs_2d(O, B, 16, H, W, offsets[:K], 50 + i) for i, (B, H, W, K) in enumerate(shapes)]
+    eo = [torch.tensor(x[0], requires_grad=True) for x in ins]
+    ro = [O.embedding_loss(e, torch.tensor(x[2]), torch.tensor(x[3]), torch.tensor(x[4]), O.WeightedMSE(), offsets[:K])
+          for e, x, (_, _, _, K) in zip(eo, ins, shapes)]
+    up = torch.tensor(np.random.RandomState(3).randn(*ins[1][2].shape).astype(np.float32))
+    (sum(r[0] for r in ro) + (ro[1][1] * up).sum()).backward()
+    e = [dev(x[0], True) for x in ins]
+    masks = [dev(x[4]) if i != 2 else dev(x[4]).float() for i, x in enumerate(ins)]
+    r = P.embedding_loss_multi(e, [dev(x[2]) for x in ins], [dev(x[3]) for x in ins], masks, P.WeightedMSE(),
+                               [offsets[:K] for (_, _, _, K) in shapes])
+    (sum(x[0] for x in r) + (r[1][1] * up.cuda()).sum()).backward()
+    for i in range(4):
+        close_s(r[i][0], ro[i][0], what=f"scale {i} loss")
+        close_t(r[i][1], ro[i][1], what=f"scale {i} affs")
+        close_t(np.asarray(list(r[i][2])), np.asarray(ro[i][2]), what=f"scale {i} all_loss")
+        close_t(e[i].grad, eo[i].grad, what=f"scale {i} grad")
+    # graph capture + replay gives the same numbers (the ticket word is left zero by every launch)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        P.embedding_loss_multi(e, [dev(x[2]) for x in ins], [dev(x[3]) for x in ins], masks, P.WeightedMSE(),
+                               [offsets[:K] for (_, _, _, K) in shapes])
+    torch.cuda.current_stream().wait_stream(side)
+    tg, wg = [dev(x[2]) for x in ins], [dev(x[3]) for x in ins]
+    with torch.cuda.graph(g):
+        r2 = P.embedding_loss_multi([x.detach() for x in e], tg, wg, masks, P.WeightedMSE(), [offsets[:K] for (_, _, _, K) in shapes])
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert float(r2[i][0]) == float(r[i][0]), f"scale {i}: graph replay differs"

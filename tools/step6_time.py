@@ -36,10 +36,16 @@ downs = [tw(3, h) for h in scales]
 crit = P.WeightedMSE()
 
 
+MULTI = os.environ.get("PEA_STEP6_MULTI", "1") == "1"
+
+
 def step():
     l0, pred = P.embedding_loss_norm5(emb, tgt, wgt, crit, affs0_weight=1)
     l1, _ = P.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit, affs0_weight=1)
-    ls = [P.embedding_loss_norm1(e, t, w, crit, affs0_weight=1)[0] for e, (t, w) in zip(emds, downs)]
+    if MULTI:
+        ls = [r[0] for r in P.embedding_loss_norm1_multi(emds, [d[0] for d in downs], [d[1] for d in downs], crit, affs0_weight=1)]
+    else:
+        ls = [P.embedding_loss_norm1(e, t, w, crit, affs0_weight=1)[0] for e, (t, w) in zip(emds, downs)]
     loss = l0 + l1 + ls[0] + ls[1] + ls[2] + ls[3]
     loss.backward()
     emb.grad = None
@@ -76,7 +82,7 @@ for _ in range(iters):
     torch.cuda.synchronize()
     per.append(s.elapsed_time(t) * 1e3)
 per.sort()
-print(f"step6 (3-D, B={B}): eager {eager:.1f} us/step   graph replay median {per[len(per) // 2]:.1f} us  min {per[0]:.1f} us   loss {float(loss):.6f}")
+print(f"step6 (3-D, B={B}, multi={MULTI}): eager {eager:.1f} us/step   graph replay median {per[len(per) // 2]:.1f} us  min {per[0]:.1f} us   loss {float(loss):.6f}")
 if os.environ.get("PEA_STEP6_PROFILE"):
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
