@@ -424,13 +424,12 @@ def time_zshard(P, device, rank, world, steps, shape=(100, 1024, 1024)):
 
     def step():
         if transport == "peer":
-            sh.publish()                       # producer's slab visible to the next rank
-            if os.environ.get("PEA_ZSHARD_OVERLAP", "0") == "1":
-                overlapped_halo_affinities(sh, out=out)
-            else:
-                fused_halo_affinities(sh.own, sh.prev_tail, out=out)
+            # publish() -> kernel (halo read from the peer in place) -> release(): the contract of a slab that is rewritten
+            sh.affinities(out=out, overlapped=os.environ.get("PEA_ZSHARD_OVERLAP", "0") == "1")
         else:
             sharded_affinities(sh, out=out)
+
+    halo_check = zshard_halo_check(P, device, rank, world, transport) if dist_on else "single GPU"
 
     for _ in range(2):
         step()
@@ -452,12 +451,216 @@ def time_zshard(P, device, rank, world, steps, shape=(100, 1024, 1024)):
     res = {"workload": f"cfg4 AC3/AC4 full volume 100x1024x1024 forward-only, z-sharded over {world} GPU(s)",
            "ms_per_step": ms, "value": 12 * vox / (ms * 1e-3), "unit": "aff-voxels/s (forward only)",
            "scaling": "strong", "hbm_gbs_aggregate": 112 * vox / (ms * 1e-3) / 1e9,
-           "halo_transport": transport,
+           "halo_transport": transport, "halo_check": halo_check,
            "halo_bytes_per_boundary": HALO_BYTES(shape) if world > 1 else 0,
            "slab_depths": [b - a for a, b in __import__("pea_b200").zshard.shard_ranges(D, world)]}
     del sh, out
     torch.cuda.empty_cache()
     return res
+
+
+def zshard_halo_check(P, device, rank, world, transport, shape=(32, 256, 256), iters=3):
+    """The REAL multi-GPU path against a single-GPU run, bit for bit, before anything is timed: every rank builds the same
+    seeded reduced volume, computes the whole volume locally, rewrites its slab every iteration (so a missing
+    release() barrier or a stale halo shows up) and compares its slab of the sharded result."""
+    from pea_b200.zshard import ZShard, PeerZShard, sharded_affinities
+    D, H, W = shape
+    try:
+        sh = PeerZShard(1, C, D, H, W, rank, world, device) if transport == "peer" else ZShard(1, C, D, H, W, rank, world, device)
+        ok = torch.ones(1, device=device)
+        for it in range(iters):
+            g = torch.Generator(device="cpu").manual_seed(4321 + it)
+            vol = torch.randn((1, C, D, H, W), generator=g).to(device)
+            whole = P.inf_embedding_loss_norm5(vol)
+            sh.own.copy_(vol[:, :, sh.z0:sh.z1])
+            out = sh.affinities() if transport == "peer" else sharded_affinities(sh)
+            if not torch.equal(out, whole[:, :, sh.z0:sh.z1]):
+                ok[0] = 0.0
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        del sh
+        torch.cuda.empty_cache()
+        return "ok" if float(ok) == 1.0 else "FAILED: a slab differs from the single-GPU result"
+    except Exception as ex:  # noqa: BLE001
+        return f"not run ({type(ex).__name__}: {ex})"
+
+
+def time_step6(P, device, flush, iters=20):
+    """The six loss calls of one AC3/AC4 training step (scripts_ac3ac4/main.py:218-231) -- norm5 + two-view norm5 at
+    B x 18 x 160 x 160, norm1 at the four deep-supervision scales -- as six separate public-API calls vs the multi-scale
+    launch for the four small ones; parity of the summed loss against the CPU reference/port."""
+    B, D = 2, 18   # ac3ac4.yaml batch_size
+    g = torch.Generator(device="cpu").manual_seed(6)
+    emb = torch.randn((B, C, D, 160, 160), generator=g).to(device).requires_grad_(True)
+    ema = torch.randn((B, C, D, 160, 160), generator=g).to(device)
+
+    def tw(K, h):
+        t = (torch.rand((B, K, D, h, h), generator=g) > 0.5).float().to(device)
+        w = (torch.rand((B, K, D, h, h), generator=g) * 2 + 0.1).to(device)
+        return t, w
+    tgt, wgt = tw(12, 160)
+    scales = [10, 20, 40, 80]
+    emds = [torch.randn((B, C, D, h, h), generator=g).to(device).requires_grad_(True) for h in scales]
+    downs = [tw(3, h) for h in scales]
+    crit = P.WeightedMSE()
+
+    def step(multi):
+        l0, _ = P.embedding_loss_norm5(emb, tgt, wgt, crit, affs0_weight=1)
+        l1, _ = P.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit, affs0_weight=1)
+        if multi:
+            ls = [r[0] for r in P.embedding_loss_norm1_multi(emds, [d[0] for d in downs], [d[1] for d in downs], crit)]
+        else:
+            ls = [P.embedding_loss_norm1(e, t, w, crit)[0] for e, (t, w) in zip(emds, downs)]
+        loss = l0 + l1 + ls[0] + ls[1] + ls[2] + ls[3]
+        loss.backward()
+        emb.grad = None
+        for e in emds:
+            e.grad = None
+        return loss
+
+    out = {}
+    for name, multi in (("six_calls", False), ("multi", True)):
+        n_ours, _, n_all = count_launches(lambda: step(multi))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step(multi)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            step(multi)
+        torch.cuda.synchronize()
+        out[name + "_eager_ms"] = (time.perf_counter() - t0) / iters * 1e3
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = step(multi)
+        per = []
+        for _ in range(iters):
+            flush.zero_()
+            s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            graph.replay()
+            t_.record()
+            torch.cuda.synchronize()
+            per.append(s_.elapsed_time(t_))
+        out[name + "_graph_ms"] = statistics.median(per)
+        out[name + "_loss"] = float(loss.detach())
+        out[name + "_launches"] = {"pea_kernels": n_ours, "all_kernels": n_all}
+        del graph
+    # parity of the summed loss against the CPU implementation's six calls
+    try:
+        impl, kind = cpu_impl()
+        from oracle import pea_oracle as O
+        with host_only():
+            e0 = emb.detach().cpu()
+            lo = impl.embedding_loss_norm5(e0, tgt.cpu(), wgt.cpu(), impl.WeightedMSE())[0]
+            n5x = O.ema_embedding_loss_norm5 if kind == "port" else __import__("oracle.ref_loader", fromlist=["x"]).load().loss3d.ema_embedding_loss_norm5
+            n1 = O.embedding_loss_norm1 if kind == "port" else __import__("oracle.ref_loader", fromlist=["x"]).load().loss3d.embedding_loss_norm1
+            lo = lo + n5x(e0, ema.cpu(), tgt.cpu(), wgt.cpu(), impl.WeightedMSE())[0]
+            for e, (t, w) in zip(emds, downs):
+                lo = lo + n1(e.detach().cpu(), t.cpu(), w.cpu(), impl.WeightedMSE())[0]
+        out["loss_cpu_" + kind] = float(lo)
+        out["parity_rel"] = abs(out["multi_loss"] - float(lo)) / abs(float(lo))
+    except Exception as ex:  # noqa: BLE001
+        out["parity_rel"] = f"not run ({type(ex).__name__}: {ex})"
+    out["workload"] = f"six loss calls of one AC3/AC4 training step, B={B}: norm5 + two-view norm5 at 18x160x160, norm1 at 18x{{10,20,40,80}}^2"
+    return out
+
+
+def time_cfg5(P, device, rank, world, kind3d=True, steps=5):
+    """BASELINE config 5: one data-parallel training step with the REFERENCE's backbone (UNet_PNI_embedding_deep,
+    scripts_ac3ac4/model/model_superhuman.py:443-492, built as scripts_ac3ac4/main.py:122-133 does with ac3ac4.yaml's
+    filters), wrapped in DistributedDataParallel (NCCL gradient all-reduce over NVLink) + the six PEA loss calls + Adam.
+    Reported: step time with this package's loss functions and with the reference's own loss functions running as
+    eager torch ops on the GPU (context), and the loss functions' share of the step."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "reference model files not staged (baseline/_ref)"}
+    ref = ref_loader.load(models=True)
+    B, D = 2, 18
+    torch.manual_seed(1234)
+    model = ref.unet3d.UNet_PNI_embedding_deep(in_planes=1, out_planes=12, filters=[28, 36, 48, 64, 80], upsample_mode='bilinear',
+                                                decode_ratio=1, merge_mode='add', pad_mode='zero', bn_mode='async',
+                                                relu_mode='elu', init_mode='kaiming_normal', emd=16).to(device)
+    nparams = sum(p.numel() for p in model.parameters())
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, amsgrad=True)
+    g = torch.Generator(device="cpu").manual_seed(77 + rank)
+    x = torch.rand((B, 1, D, 160, 160), generator=g).to(device)
+    x2 = torch.rand((B, 1, D, 160, 160), generator=g).to(device)
+
+    def tw(K, h):
+        t = (torch.rand((B, K, D, h, h), generator=g) > 0.5).float().to(device)
+        w = (torch.rand((B, K, D, h, h), generator=g) * 2 + 0.1).to(device)
+        return t, w
+    tgt, wgt = tw(12, 160)
+    downs = [tw(3, h) for h in (10, 20, 40, 80)]
+    crit_p, crit_r = P.WeightedMSE(), ref.crit.WeightedMSE()
+    L3 = ref.loss3d
+
+    def losses(ours, emds, emb, ema):
+        if ours:
+            l0, _ = P.embedding_loss_norm5(emb, tgt, wgt, crit_p)
+            l1, _ = P.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit_p)
+            ls = [r[0] for r in P.embedding_loss_norm1_multi(emds, [d[0] for d in downs], [d[1] for d in downs], crit_p)]
+        else:
+            l0, _ = L3.embedding_loss_norm5(emb, tgt, wgt, crit_r)
+            l1, _ = L3.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit_r)
+            ls = [L3.embedding_loss_norm1(e, t, w, crit_r)[0] for e, (t, w) in zip(emds, downs)]
+        return l0 + l1 + ls[0] + ls[1] + ls[2] + ls[3]
+
+    def train_step(ours):
+        opt.zero_grad(set_to_none=True)
+        e1, e2, e3, e4, emb = model(x)
+        with torch.no_grad():
+            ema = model(x2)[-1]
+        loss = losses(ours, [e1, e2, e3, e4], emb, ema.detach())
+        loss.backward()
+        opt.step()
+        return loss
+
+    out = {"model": "UNet_PNI_embedding_deep (reference file, unmodified)", "params": nparams, "per_gpu_batch": B,
+           "input": f"({B},1,18,160,160) per GPU", "collective": "DDP NCCL all-reduce of the backbone gradients" if world > 1 else "none (1 GPU)"}
+    for name, ours in (("ours", True), ("reference_loss_on_gpu", False)):
+        for _ in range(2):
+            train_step(ours)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(steps):
+            loss = train_step(ours)
+        t_.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s_.elapsed_time(t_) / steps], device=device, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        out[name + "_step_ms"] = float(ms)
+        out[name + "_loss"] = float(loss.detach())
+    # the loss functions alone (fwd + bwd to the embeddings), same tensors, CUDA events
+    with torch.no_grad():
+        outs = model(x)
+    leaf = [o.detach().requires_grad_(True) for o in outs]
+    ema = model(x2)[-1].detach()
+    for name, ours in (("ours", True), ("reference_loss_on_gpu", False)):
+        for _ in range(2):
+            losses(ours, leaf[:4], leaf[4], ema).backward()
+        torch.cuda.synchronize()
+        s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(steps):
+            losses(ours, leaf[:4], leaf[4], ema).backward()
+        t_.record()
+        torch.cuda.synchronize()
+        out[name + "_loss_part_ms"] = s_.elapsed_time(t_) / steps
+    out["samples_per_s"] = world * B / (out["ours_step_ms"] * 1e-3)
+    out["loss_share_of_step"] = out["ours_loss_part_ms"] / out["ours_step_ms"]
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
 
 
 def HALO_BYTES(shape):
@@ -736,10 +939,14 @@ def run_ours(args, rank, world, local_rank):
         lab_ms, lab_bytes = time_e2e_labels_only(P, w, e2e_steps, device, res["inputs"])
         lapi_ms, lapi_bytes = time_e2e_label_api(P, w, e2e_steps, device, res["inputs"])
     res["inputs"] = None
-    zres = None
+    zres = c5 = None
     if not args.quick:
         torch.cuda.empty_cache()
         zres = time_zshard(P, device, rank, world, 5)
+        try:
+            c5 = time_cfg5(P, device, rank, world)
+        except Exception as ex:  # noqa: BLE001
+            c5 = {"unavailable": f"{type(ex).__name__}: {ex}"}
     if rank == 0:
         peak, peak_src = measured_peak()
         ms_step = total_ms / args.steps
@@ -771,6 +978,7 @@ def run_ours(args, rank, world, local_rank):
             also["cfg4_epilogue"] = time_inference_epilogue(P, device)
             also["cfg2_labels"] = time_labels_pipeline(P, WORKLOADS["cfg2"], device, flush)
             also["cfg2_labels"]["roofline_frac"] = also["cfg2_labels"]["hbm_gbs"] / peak
+            also["step6"] = time_step6(P, device, flush)
             torch.cuda.empty_cache()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -811,6 +1019,8 @@ def run_ours(args, rank, world, local_rank):
         if zres is not None:
             zres["roofline_frac_per_gpu"] = zres["hbm_gbs_aggregate"] / world / peak
             also["cfg4"] = zres
+        if c5 is not None:
+            also["cfg5_3d"] = c5
         if also:
             line["also"] = also
         emit(line)

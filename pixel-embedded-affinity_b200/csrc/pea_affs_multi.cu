@@ -72,6 +72,7 @@ template <int C>
 __global__ void __launch_bounds__(kThreads, 2) multi_fused(const __grid_constant__ Batch bt) {
     __shared__ float s_part[kWarps][kMaxProblems][kMaxK];
     __shared__ float s_loss[kMaxProblems][kMaxK];
+    __shared__ double s_acc[kWarps][kMaxProblems * kMaxK];
     __shared__ uint32_t s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kWarps * kMaxProblems * kMaxK; i += kThreads) (&s_part[0][0][0])[i] = 0.f;
@@ -190,9 +191,30 @@ __global__ void __launch_bounds__(kThreads, 2) multi_fused(const __grid_constant
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // rows of partials are dealt out to the warps (row = warp, warp + 8, ...), a lane owns slot lane + 32 j; eight loads
+    // in flight per lane; double accumulation in a fixed order, then the eight warp sums in warp order: reproducible
+    for (int base = 0; base < slots; base += 32) {
+        const int i = base + lane;
+        double acc = 0.0;
+        if (i < slots) {
+            const float* src = bt.partials + i;
+            int c = warp;
+            for (; c + 7 * kWarps < (int)gridDim.x; c += 8 * kWarps) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ld_cg(src + (int64_t)(c + u * kWarps) * slots);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += (double)v[u];
+            }
+            for (; c < (int)gridDim.x; c += kWarps) acc += (double)ld_cg(src + (int64_t)c * slots);
+            s_acc[warp][i] = acc;
+        }
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < slots; i += kThreads) {
         double acc = 0.0;
-        for (int c = 0; c < (int)gridDim.x; ++c) acc += (double)ld_cg(bt.partials + (int64_t)c * slots + i);
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) acc += s_acc[w][i];
         const int pi = i / kMaxK, k = i - pi * kMaxK;
         s_loss[pi][k] = (k < bt.p[pi].K) ? (float)acc / bt.p[pi].norm[k] : 0.f;
     }
@@ -279,7 +301,10 @@ extern "C" int pea_affs_loss_multi(const pea_loss_problem* problems, int n, int 
     }
     bt.total_chunks = (int)chunks;
     int64_t g = (chunks + multi::kWarps - 1) / multi::kWarps;
-    const int grid = (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int cap = nsm > 0 && nsm <= 592 ? 2 * nsm : 296;  // two resident CTAs per SM walk the chunk list
+    const int grid = (int)(g < 1 ? 1 : (g > cap ? cap : g));
     if ((size_t)grid * (size_t)n * PEA_MULTI_MAX_OFFSETS * sizeof(float) > ws_bytes) return PEA_E_WORKSPACE;
     // (2^31 voxels per problem bound above keeps every in-kernel voxel index inside int32)
     bt.partials = static_cast<float*>(workspace);

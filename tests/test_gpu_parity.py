@@ -1117,3 +1117,30 @@ def test_embedding_loss_multi_2d_matches_oracle(P, O):
     torch.cuda.synchronize()
     for i in range(4):
         assert float(r2[i][0]) == float(r[i][0]), f"scale {i}: graph replay differs"
+
+
+def test_label_pyramid_matches_oracle_recipe(P, O):
+    """make_targets_pyramid_2d / _3d: all five scales' ground truth from ONE label upload, bit for bit what the
+    reference's loaders build per sample (data_provider.py:198-239, data_provider_labeled_deep.py:224-285)."""
+    offsets = O.multi_offset([1, 3, 5, 9, 27], neighbor=4)
+    labs = np.stack([O.voronoi_labels((64, 96), 9, 70 + b) for b in range(2)])
+    (t, m, w), downs = P.make_targets_pyramid_2d(torch.tensor(labs).cuda(), offsets, nb_half=2)
+    for b in range(2):
+        to, mo = O.gen_affs_ours(labs[b], offsets, ignore=False, padding=True)
+        same(t[b], to, "full target"), same(m[b], mo, "full mask")
+        same(w[b], np.stack([O.weight_binary_ratio(c) for c in to]), "full weight")
+        for i, (f, c) in enumerate(zip((2, 4, 8, 16), (4, 3, 2, 1))):
+            K = 2 * c
+            td, md = O.gen_affs_ours(labs[b][::f, ::f], offsets[:K], ignore=False, padding=True)
+            wd = np.stack([O.weight_binary_ratio(ch) for ch in td])
+            same(downs[i][b], np.concatenate([td, wd, md.astype(np.float32)], axis=0), f"down{i + 1}")
+    segs = np.stack([O.voronoi_labels((6, 32, 48), 10, 80 + b, z_scale=4.0, dtype=np.uint16) for b in range(2)])
+    (t, w), downs = P.make_targets_pyramid_3d(torch.tensor(segs.astype(np.int32)).cuda())
+    for b in range(2):
+        to = O.seg_to_aff_norm5(segs[b])
+        same(t[b], to, "3D full target")
+        same(w[b], np.stack([O.weight_binary_ratio(c) for c in to]), "3D full weight")
+        for i, f in enumerate((2, 4, 8, 16)):
+            td = O.seg_to_aff(segs[b][:, ::f, ::f], pad='replicate')
+            wd = np.stack([O.weight_binary_ratio(ch) for ch in td])
+            same(downs[i][b], np.concatenate([td, wd], axis=0), f"3D down{i + 1}")

@@ -4,6 +4,7 @@ The fixtures in tests/golden/*.npz were produced by tests/golden/make_golden.py,
 unmodified reference from /root/reference.  Everything here is CPU-only.
 """
 import numpy as np
+import pytest
 import torch
 
 from oracle import pea_oracle as O
@@ -184,3 +185,21 @@ def test_weight_binary_ratio(golden):
         same(w, cout)
     same(np.stack([O.weight_binary_ratio(c) for c in g["gt3d_aff12"]]), g["gt3d_w12"])
     same(np.stack([O.weight_binary_ratio(c) for c in g["gt2d_aff_i0_p1"]]), g["gt2d_w"])
+
+
+def test_pyramid_downsampling_is_strided_sampling():
+    """The reference's label pyramid (cv2.resize INTER_NEAREST by 1/2 .. 1/16, scripts_cvppp/data/data_provider.py:199-202;
+    the (H,W,D)-transposed 3-D call, scripts_ac3ac4/data/data_provider_labeled_deep.py:224-232) equals label[::f, ::f]
+    for extents divisible by f -- what pea_b200.make_targets_pyramid_* does on the device."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(0)
+    for (H, W) in ((544, 544), (160, 160), (704, 704), (256, 256)):
+        lab = rng.randint(0, 50, (H, W)).astype(np.float32)
+        for f in (2, 4, 8, 16):
+            d = cv2.resize(lab, (0, 0), fx=1 / f, fy=1 / f, interpolation=cv2.INTER_NEAREST)
+            assert np.array_equal(d, lab[::f, ::f]), (H, W, f)
+    lb = rng.randint(0, 50, (18, 160, 160)).astype(np.uint16)
+    t = np.transpose(lb, (1, 2, 0))
+    for f in (2, 4, 8, 16):
+        d = np.transpose(cv2.resize(t, (0, 0), fx=1 / f, fy=1 / f, interpolation=cv2.INTER_NEAREST), (2, 0, 1))
+        assert np.array_equal(d, lb[:, ::f, ::f]), f
