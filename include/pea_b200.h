@@ -155,6 +155,30 @@ int pea_affs_loss_multi(const pea_loss_problem* problems, int n, int C, void* wo
  * pointers. */
 int pea_scale_multi(float* const* bufs, const int64_t* lens, const float* const* scales, int n, void* stream);
 
+/* Full-volume inference epilogue: Gaussian-weighted accumulation of overlapping patches,
+ *   replaces  Provider_valid.add_vol / get_results     scripts_ac3ac4/data/provider_valid.py:306-348
+ *             `1 - output_affs` for the Mutex Watershed scripts_ac3ac4/inference.py:196
+ * pea_blend_add:    acc[k, z0+z, y0+y, x0+x] += patch[k,z,y,x] * weight[z,y,x]   (product rounded, then added: NumPy's
+ *                   two roundings),  wmap[z0+z, y0+y, x0+x] += weight[z,y,x].   patch (K,d,h,w), weight (d,h,w),
+ *                   acc (K,D,H,W), wmap (D,H,W).  Patches are added one call at a time (stream order), like the loop.
+ * pea_blend_finish: out[k] = acc[k] / wmap cropped by (pad_z, pad_y, pad_x) on both sides of every axis
+ *                   (valid_padding, :330-340), or 1 - that when one_minus != 0.  out (K, D-2pz, H-2py, W-2px). */
+int pea_blend_add(const float* patch, const float* weight, int K, int d, int h, int w, float* acc, float* wmap,
+                  int D, int H, int W, int z0, int y0, int x0, void* stream);
+int pea_blend_finish(const float* acc, const float* wmap, int K, int D, int H, int W, int pad_z, int pad_y, int pad_x,
+                     int one_minus, float* out, void* stream);
+
+/* Undo the per-sample flip / transpose augmentation of the second view before the two-view loss, one pass, rules read on
+ * the device (no host synchronisation)  
+ *   replaces  convert_consistency_flip   scripts_cvppp/data/data_consistency.py:34-45 (+ :19-31)
+ *                                        scripts_ac3ac4/utils/consistency_aug.py:217-228 (+ :58-77)
+ * in / out (B, C, D, H, W) float32, out != in; rules: DEVICE int32 [B][4] as (z reflection, x reflection, y reflection,
+ * xy transpose); 2-D callers pass D = 1 and rz = 0.  H must equal W for samples whose transpose bit is set (the
+ * reference stacks the samples back into one tensor, so it needs that too).
+ * out[b,c,z,y,x] = in[b,c,z',y',x'], or in[b,c,z',x',y'] under the transpose, with z' = D-1-z, y' = H-1-y, x' = W-1-x
+ * where the corresponding reflection bit is set. */
+int pea_consistency_flip(const float* in, const int32_t* rules, int B, int C, int D, int H, int W, float* out, void* stream);
+
 /* buf[i] *= *scale (a device scalar), in place; exits without touching memory when *scale == 1.
  * Used by the autograd backward to apply the upstream gradient of the scalar loss to the gradient the
  * fused forward already produced (the common `loss.backward()` case costs one empty launch). */

@@ -397,6 +397,73 @@ def closed_form_grad_3d(embedding, target, weightmap, shifts, weighted_upto, par
 # ----------------------------------------------------------------------------------------
 # seeded synthetic inputs shared by tests / bench
 # ----------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------------------------
+# undoing the second view's flip augmentation: scripts_cvppp/data/data_consistency.py:19-45 (2-D, rule of size 3) and
+# scripts_ac3ac4/utils/consistency_aug.py:58-77, 217-228 (3-D, rule of size 4)
+def simple_augment_reverse(data, rule):
+    """data (C,H,W) with rule (x reflection, y reflection, xy transpose), or (C,D,H,W) with rule (z reflection,
+    x reflection, y reflection, xy transpose): transpose first, then the reflections, as the reference orders them."""
+    if data.dim() == 3:
+        assert np.size(rule) == 3
+        if rule[2]:
+            data = data.permute(0, 2, 1)
+        if rule[1]:
+            data = torch.flip(data, [1])
+        if rule[0]:
+            data = torch.flip(data, [2])
+        return data
+    assert np.size(rule) == 4 and data.dim() == 4
+    if rule[3]:
+        data = data.permute(0, 1, 3, 2)
+    if rule[2]:
+        data = torch.flip(data, [2])
+    if rule[1]:
+        data = torch.flip(data, [3])
+    if rule[0]:
+        data = torch.flip(data, [1])
+    return data
+
+
+def convert_consistency_flip(gt, rules):
+    """data_consistency.py:34-45 / consistency_aug.py:217-228."""
+    gt = gt.detach().clone()
+    rules = np.asarray(rules.data.cpu().numpy() if isinstance(rules, torch.Tensor) else rules).astype(np.uint8)
+    return torch.stack([simple_augment_reverse(gt[k], rules[k]) for k in range(gt.shape[0])], dim=0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# full-volume inference epilogue: scripts_ac3ac4/data/provider_valid.py:294-340 (get_weight, add_vol, get_results)
+def blend_get_weight(out_size, sigma=0.2, mu=0.0):
+    """provider_valid.py:294-304 (the num_z >= 18 branch): (1, d, h, w) float32."""
+    zz, yy, xx = np.meshgrid(np.linspace(-1, 1, out_size[0], dtype=np.float32),
+                             np.linspace(-1, 1, out_size[1], dtype=np.float32),
+                             np.linspace(-1, 1, out_size[2], dtype=np.float32), indexing='ij')
+    dd = np.sqrt(zz * zz + yy * yy + xx * xx)
+    weight = 1e-6 + np.exp(-((dd - mu) ** 2 / (2.0 * sigma ** 2)))
+    return weight[np.newaxis, ...]
+
+
+def blend_add_vol(out_affs, weight_map, affs_vol, weight_vol, pos):
+    """provider_valid.py:306-316 ('superhuman' branch), in place; pos = origin along the three volume axes."""
+    a, b, c = pos
+    d, h, w = affs_vol.shape[1:]
+    out_affs[:, a:a + d, b:b + h, c:c + w] += affs_vol * weight_vol
+    weight_map[:, a:a + d, b:b + h, c:c + w] += weight_vol
+
+
+def blend_get_results(out_affs, weight_map, valid_padding=(0, 0, 0)):
+    """provider_valid.py:323-340."""
+    out = out_affs / weight_map
+    pz, py, px = valid_padding
+    if pz:
+        out = out[:, pz:-pz]
+    if py:
+        out = out[:, :, py:-py]
+    if px:
+        out = out[:, :, :, px:-px]
+    return out
+
+
 def voronoi_labels(shape, n_seeds, seed, background_frac=0.3, z_scale=1.0, dtype=np.uint8):
     """Seeded Voronoi instance map with a background (0) region; ids >= 1."""
     rng = np.random.RandomState(seed)

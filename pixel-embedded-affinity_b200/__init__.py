@@ -15,6 +15,8 @@ from .loss_embedding_mse_3d import (embedding_loss_norm1, embedding_loss_norm5, 
 from .affinity_ours import gen_offsets, multi_offset, gen_affs_ours
 from .data_affinity import mknhood3d, seg_to_aff
 from .data_segmentation import weight_binary_ratio
+from .data_consistency import convert_consistency_flip
+from .provider_valid import VolumeBlender
 from .gt import make_targets_2d, make_targets_3d, make_targets_pyramid_2d, make_targets_pyramid_3d
 
 __version__ = "0.1.0"

@@ -37,6 +37,9 @@ SIGNATURES = {
                                    c_float_p, vp, vp, vp, vp, vp, ctypes.c_size_t, vp, vp]),
     "pea_affs_bwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "pea_scale_inplace": (ci, [vp, ctypes.c_int64, vp, vp]),
+    "pea_consistency_flip": (ci, [vp, vp, ci, ci, ci, ci, ci, vp, vp]),
+    "pea_blend_add": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "pea_blend_finish": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp]),
     "pea_affs_loss_multi_workspace": (ctypes.c_size_t, [ctypes.POINTER(LossProblem), ci]),
     "pea_affs_loss_multi": (ci, [ctypes.POINTER(LossProblem), ci, ci, vp, ctypes.c_size_t, vp, vp]),
     "pea_scale_multi": (ci, [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(vp), ci, vp]),

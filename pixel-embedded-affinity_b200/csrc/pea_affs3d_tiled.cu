@@ -862,6 +862,23 @@ struct ParamsF {
     int relu;  // store max(a, 0): the caller-side F.relu(pred) folded into the kernel
 };
 
+#ifndef PEA_K3_ORDER
+#define PEA_K3_ORDER 0  // tile -> CTA order of the forward kernel: 0 row-major, 1 column-major, 2 blocks of PEA_K3_BLK columns
+#endif
+#ifndef PEA_K3_BLK
+#define PEA_K3_BLK 4
+#endif
+#ifndef PEA_K3_STCS
+#define PEA_K3_STCS 0   // 1: affinities leave with st.global.cs (evict-first): write-once data does not displace the halos in L2
+#endif
+__device__ __forceinline__ void st_out(float* p, float v) {
+#if PEA_K3_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 template <int TY>
 __global__ void __launch_bounds__(TY * 32, (TY <= 8) ? 2 : 1)
 fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
@@ -879,10 +896,24 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
     const int D = P.D, H = P.H, W = P.W, zs = P.z_skip;
     const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
     int bid = blockIdx.x;
+#if PEA_K3_ORDER == 1      // column-major: vertically adjacent tiles (the y halo and the y-27 arm) are launched back to back
+    const int tiy = bid % tiles_y;
+    bid /= tiles_y;
+    const int tix = bid % tiles_x;
+    const int b = bid / tiles_x;
+#elif PEA_K3_ORDER == 2    // blocks of PEA_K3_BLK tile columns, column-major inside a block
+    const int per_b = tiles_x * tiles_y;
+    const int b = bid / per_b;
+    bid -= b * per_b;
+    const int blk = bid / (PEA_K3_BLK * tiles_y), r = bid - blk * (PEA_K3_BLK * tiles_y);
+    const int wblk = min(PEA_K3_BLK, tiles_x - blk * PEA_K3_BLK);  // the last block may be narrower
+    const int tiy = r / wblk, tix = blk * PEA_K3_BLK + r % wblk;
+#else
     const int tix = bid % tiles_x;
     bid /= tiles_x;
     const int tiy = bid % tiles_y;
     const int b = bid / tiles_y;
+#endif
     const int x0 = tix * TX, y0 = tiy * TY;
     const int x = x0 + tx, y = y0 + ty;
     const bool live = (x < W) && (y < H);
@@ -1004,7 +1035,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             const float* nb = (g < 3) ? &S.sY[0][ty + HY - s][tx] : &S.sAm[0][ty][tx];
             float a;
             inplane_pair<false>(nb, (g < 3) ? CHS_Y : CHS_A, e, dummyG, 0.f, 0.f, 0.f, a);
-            if (live) out[(int64_t)(3 * g + 1) * P.affs_plane] = (y >= s) ? (P.relu ? fmaxf(a, 0.f) : a) : 0.f;
+            if (live) st_out(out + (int64_t)(3 * g + 1) * P.affs_plane, (y >= s) ? (P.relu ? fmaxf(a, 0.f) : a) : 0.f);
         }
         __syncwarp();
         if (tx == 0 && arrive_count(&cntY) == kWarps * (uint32_t)(it + 1) - 1 && more) issueY(znext);
@@ -1015,7 +1046,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             const int s = shift_yx(g);
             float a;
             inplane_pair<false>(&S.sX[0][ty][tx + XPAD - s], CHS_X, e, dummyG, 0.f, 0.f, 0.f, a);
-            if (live) out[(int64_t)(3 * g + 2) * P.affs_plane] = (x >= s) ? (P.relu ? fmaxf(a, 0.f) : a) : 0.f;
+            if (live) st_out(out + (int64_t)(3 * g + 2) * P.affs_plane, (x >= s) ? (P.relu ? fmaxf(a, 0.f) : a) : 0.f);
         }
         __syncwarp();
         if (tx == 0 && arrive_count(&cntX) == kWarps * (uint32_t)(it + 1) - 1 && more) issueX(znext);
@@ -1033,7 +1064,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
                 d1 = fma2(re[0][i + 1], re[j][i + 1], d1);
             }
             const float az = hsum2(d0, d1);
-            if (live) out[(int64_t)(3 * (j - 1)) * P.affs_plane] = (z + zprev >= j) ? (P.relu ? fmaxf(az, 0.f) : az) : 0.f;
+            if (live) st_out(out + (int64_t)(3 * (j - 1)) * P.affs_plane, (z + zprev >= j) ? (P.relu ? fmaxf(az, 0.f) : az) : 0.f);
         }
 #pragma unroll
         for (int s = 4; s >= 1; --s)

@@ -31,4 +31,4 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
-    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("loss2d", "loss3d", "gt")}
+    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("loss2d", "loss3d", "gt", "flip")}

@@ -225,6 +225,25 @@ def make_gt(ref):
     np.savez_compressed(os.path.join(OUT, "gt.npz"), **out)
 
 
+def make_flip():
+    """convert_consistency_flip of both script trees on every rule combination (square extents: the reference stacks
+    the per-sample results, which a transposed non-square sample would break)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT), ".."))
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    rng = np.random.RandomState(77)
+    out = {}
+    rules2 = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)], dtype=np.int64)
+    g2 = rng.randn(len(rules2), 3, 6, 6).astype(np.float32)
+    out["in2d"], out["rules2d"] = g2, rules2
+    out["out2d"] = np32(ref.flip2d.convert_consistency_flip(torch.tensor(g2), torch.tensor(rules2)))
+    rules3 = np.array([[a, b, c, d] for a in (0, 1) for b in (0, 1) for c in (0, 1) for d in (0, 1)], dtype=np.int64)
+    g3 = rng.randn(len(rules3), 2, 3, 5, 5).astype(np.float32)
+    out["in3d"], out["rules3d"] = g3, rules3
+    out["out3d"] = np32(ref.flip3d.convert_consistency_flip(torch.tensor(g3), torch.tensor(rules3)))
+    np.savez_compressed(os.path.join(OUT, "flip.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(1)  # fixed reduction order for the stored reference outputs
@@ -234,3 +253,4 @@ if __name__ == "__main__":
     make_gt(ref)
     for f in ("loss2d.npz", "loss3d.npz", "gt.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+    make_flip()

@@ -1,5 +1,6 @@
-"""The driver-facing contract of bench.py that can be checked without a GPU: the reference arm (oracle port on the host
-cores) prints exactly one JSON line with the agreed keys."""
+"""The driver-facing contract of bench.py that can be checked without a GPU: the reference arm (the reference's own files
+staged under baseline/_ref when present, else the oracle port, on the host cores) prints exactly one JSON line with the
+agreed keys."""
 import json
 import os
 import subprocess
@@ -17,7 +18,10 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "affinity_voxels_per_s_fwd_bwd" and d["unit"] == "aff-voxels/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert set(d["config"]) == {"workload", "name", "batch", "l2", "timing"}   # the same dict in both arms
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("CVPPP-shaped 2D")
 

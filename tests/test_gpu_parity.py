@@ -1144,3 +1144,64 @@ def test_label_pyramid_matches_oracle_recipe(P, O):
             td = O.seg_to_aff(segs[b][:, ::f, ::f], pad='replicate')
             wd = np.stack([O.weight_binary_ratio(ch) for ch in td])
             same(downs[i][b], np.concatenate([td, wd], axis=0), f"3D down{i + 1}")
+
+
+def test_volume_blender_matches_provider_valid(P, O):
+    """Device-side add_vol / get_results (scripts_ac3ac4/data/provider_valid.py:294-340) and the Mutex Watershed's
+    `1 - affs` (inference.py:196): overlapping patches straight from the inference kernel, bit for bit NumPy's result."""
+    from pea_b200.provider_valid import VolumeBlender, get_weight
+    K, vol, patch = 12, (10, 72, 88), (6, 40, 48)
+    same(get_weight(patch), O.blend_get_weight(patch), "window")
+    rng = np.random.RandomState(5)
+    emb = rng.randn(1, 16, *vol).astype(np.float32)
+    bl = VolumeBlender(K, vol, patch, "cuda")
+    acc, wm = np.zeros((K,) + vol, np.float32), np.zeros((1,) + vol, np.float32)
+    wv = O.blend_get_weight(patch)
+    e = dev(emb)
+    for z0 in (0, 4):
+        for y0 in (0, 16, 32):
+            for x0 in (0, 20, 40):
+                sub = e[:, :, z0:z0 + patch[0], y0:y0 + patch[1], x0:x0 + patch[2]].contiguous()
+                pred = P.inf_embedding_loss_norm5(sub, relu=True, replicate_border=True)
+                bl.add_vol(pred, (z0, y0, x0))
+                O.blend_add_vol(acc, wm, pred[0].cpu().numpy(), wv, (z0, y0, x0))
+    same(bl.out_affs, acc, "accumulated affinities")
+    same(bl.weight_map, wm, "accumulated window")
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref = O.blend_get_results(acc, wm, (1, 4, 4))
+    same(bl.get_results((1, 4, 4)), ref, "get_results")
+    same(bl.get_results((1, 4, 4), one_minus=True), (np.float32(1) - ref).astype(np.float32), "1 - affs")
+
+
+def test_consistency_flip_golden_and_oracle(P, O, golden):
+    """convert_consistency_flip in one device pass: the reference's goldens (every rule combination), then the oracle on
+    larger / non-multiple-of-32 / non-square (no transpose) extents, and the flip followed by the two-view loss."""
+    g = golden["flip"]
+    for nd in ("2d", "3d"):
+        out = P.convert_consistency_flip(dev(g["in" + nd]), torch.tensor(g["rules" + nd]).cuda())
+        same(out, g["out" + nd], "golden " + nd)
+        assert not out.requires_grad
+    rng = np.random.RandomState(9)
+    for shape, nr in (((8, 16, 70, 70), 3), ((16, 4, 3, 45, 45), 4), ((4, 16, 5, 33, 64), 4), ((4, 3, 37, 50), 3)):
+        x = rng.randn(*shape).astype(np.float32)
+        rules = rng.randint(0, 2, (shape[0], nr))
+        if shape[-1] != shape[-2]:
+            rules[:, -1] = 0
+        same(P.convert_consistency_flip(dev(x), torch.tensor(rules).cuda()),
+             O.convert_consistency_flip(torch.tensor(x), torch.tensor(rules)).numpy(), f"oracle {shape}")
+    with pytest.raises(ValueError):
+        P.convert_consistency_flip(dev(rng.randn(2, 3, 8, 12).astype(np.float32)), torch.tensor([[0, 0, 1], [0, 0, 0]]).cuda())
+    # flip -> two-view loss, as scripts_ac3ac4/main.py:213-222 chains them
+    emb, ema, tgt, wgt = _inputs_3d(O, 2, 16, 6, 32, 32, 12, 31)
+    rules = torch.tensor([[1, 0, 1, 1], [0, 1, 0, 0]])
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao = O.ema_embedding_loss_norm5(eo, O.convert_consistency_flip(torch.tensor(ema), rules), torch.tensor(tgt), torch.tensor(wgt),
+                                        O.WeightedMSE(), affs0_weight=2)
+    lo.backward()
+    e = dev(emb, True)
+    l, a = P.ema_embedding_loss_norm5(e, P.convert_consistency_flip(dev(ema), rules.cuda()), dev(tgt), dev(wgt), P.WeightedMSE(),
+                                      affs0_weight=2)
+    l.backward()
+    close_s(l, lo, what="flip + ema loss")
+    close_t(a, ao, what="flip + ema affs")
+    close_t(e.grad, eo.grad, what="flip + ema grad")

@@ -203,3 +203,14 @@ def test_pyramid_downsampling_is_strided_sampling():
     for f in (2, 4, 8, 16):
         d = np.transpose(cv2.resize(t, (0, 0), fx=1 / f, fy=1 / f, interpolation=cv2.INTER_NEAREST), (2, 0, 1))
         assert np.array_equal(d, lb[:, ::f, ::f]), f
+
+
+def test_oracle_consistency_flip_matches_reference_golden(golden):
+    """oracle.convert_consistency_flip against the real reference's outputs for every rule combination
+    (scripts_cvppp/data/data_consistency.py:34-45, scripts_ac3ac4/utils/consistency_aug.py:217-228)."""
+    import torch
+    from oracle import pea_oracle as O
+    g = golden["flip"]
+    for nd in ("2d", "3d"):
+        out = O.convert_consistency_flip(torch.tensor(g["in" + nd]), torch.tensor(g["rules" + nd]))
+        assert np.array_equal(out.numpy(), g["out" + nd]), nd
