@@ -585,7 +585,9 @@ def time_cfg5(P, device, rank, world, kind3d=True, steps=5):
                                                 relu_mode='elu', init_mode='kaiming_normal', emd=16).to(device)
     nparams = sum(p.numel() for p in model.parameters())
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
+        # broadcast_buffers=False: the step runs the model twice (second view), and a buffer broadcast in the second
+        # forward would modify BatchNorm buffers the first forward's graph still needs
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], broadcast_buffers=False)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, amsgrad=True)
     g = torch.Generator(device="cpu").manual_seed(77 + rank)
     x = torch.rand((B, 1, D, 160, 160), generator=g).to(device)
@@ -613,10 +615,10 @@ def time_cfg5(P, device, rank, world, kind3d=True, steps=5):
 
     def train_step(ours):
         opt.zero_grad(set_to_none=True)
+        with torch.no_grad():          # second view first: its forward must not touch state the graph below depends on
+            ema = model(x2)[-1].detach().clone()
         e1, e2, e3, e4, emb = model(x)
-        with torch.no_grad():
-            ema = model(x2)[-1]
-        loss = losses(ours, [e1, e2, e3, e4], emb, ema.detach())
+        loss = losses(ours, [e1, e2, e3, e4], emb, ema)
         loss.backward()
         opt.step()
         return loss

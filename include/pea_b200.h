@@ -71,6 +71,16 @@ extern "C" {
 int pea_abi_version(void);
 const char* pea_strerror(int code);
 
+/* TEST-ONLY: dispatch knobs of the parity tests (process-wide, 0 = production behaviour; the only mutable state in the
+ * library, written by nothing but this call).  PEA_KNOB_NO_CANON != 0: the canonical 2-D tables take the table-driven
+ * axis kernel; PEA_KNOB_MAX_CTAS = n > 0: persistent 2-D kernels launch at most n CTAs (every CTA walks many tiles);
+ * PEA_KNOB_TUNE_TY2D = 8 / 12 / 16: pins the tile height of the generic 2-D tiled kernel. */
+#define PEA_KNOB_NO_CANON 0
+#define PEA_KNOB_MAX_CTAS 1
+#define PEA_KNOB_TUNE_TY2D 2
+#define PEA_KNOB_COUNT 3
+int pea_debug_configure(int knob, int value);
+
 /* Bytes of device workspace the affinity entry points need for a problem of this size.
  * `cross` != 0 when a partner (second-view) embedding is passed. */
 size_t pea_workspace_bytes(int B, int C, int D, int H, int W, int K, int cross);

@@ -17,10 +17,24 @@ for _n in ("uint16", "uint32", "uint64"):
         _NP_TO_TORCH[np.dtype(_n)] = getattr(torch, _n)
 
 
+_WORKER_HELP = (
+    "pea_b200's ground-truth functions run on the GPU, and this process cannot create a CUDA context: it is a fork-started "
+    "DataLoader worker (the reference calls gen_affs_ours / seg_to_aff / weight_binary_ratio inside Dataset.__getitem__, "
+    "scripts_cvppp/data/data_provider.py:204-225).  Either start the workers with DataLoader(..., multiprocessing_context='spawn'), "
+    "or -- the intended B200 use -- return the label map from __getitem__ and build the targets in the training loop with "
+    "pea_b200.make_targets_2d / make_targets_3d / make_targets_pyramid_* (or call the *_labels losses directly).")
+
+
 def device():
+    """The current CUDA device; explains itself when called where CUDA cannot start (DataLoader workers)."""
     if not torch.cuda.is_available():
         raise RuntimeError("pea_b200 needs a CUDA device: there is no CPU implementation in this package")
-    return torch.device("cuda", torch.cuda.current_device())
+    try:
+        return torch.device("cuda", torch.cuda.current_device())
+    except RuntimeError as ex:  # "Cannot re-initialize CUDA in forked subprocess"
+        if "fork" in str(ex).lower():
+            raise RuntimeError(_WORKER_HELP) from ex
+        raise
 
 
 def labels_to_device(labels):

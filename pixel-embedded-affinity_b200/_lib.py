@@ -30,6 +30,7 @@ class LossProblem(ctypes.Structure):
 SIGNATURES = {
     "pea_abi_version": (ci, []),
     "pea_strerror": (ctypes.c_char_p, [ci]),
+    "pea_debug_configure": (ci, [ci, ci]),
     "pea_workspace_bytes": (ctypes.c_size_t, [ci, ci, ci, ci, ci, ci, ci]),
     "pea_affs_fwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, ci, ctypes.c_int64, ctypes.c_int64, vp, ci,
                           ctypes.c_int64, vp, vp, ctypes.c_size_t, vp]),

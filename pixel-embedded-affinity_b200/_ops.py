@@ -33,6 +33,10 @@ for _n, _c in (("uint16", 1), ("uint32", 2), ("uint64", 3)):
         _LABEL_CODES[getattr(torch, _n)] = _c
 
 
+# label dtypes whose every value is representable in int32 (the label-driven loss kernels stage int32 planes)
+INT32_SAFE_LABELS = {torch.uint8, torch.int8, torch.int16, torch.int32} | ({torch.uint16} if hasattr(torch, "uint16") else set())
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 

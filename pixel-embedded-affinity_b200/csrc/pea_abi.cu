@@ -1,9 +1,12 @@
-#include <cstdlib>
+#include <atomic>
 // extern "C" entry points for the affinity ops (declared in include/pea_b200.h): argument validation,
 // workspace carving, kernel selection.  No allocation, no global state, everything on the caller's stream.
 #include "pea_common.cuh"
 
 namespace pea {
+
+static std::atomic<int> g_knobs[PEA_KNOB_COUNT];
+int debug_knob(int which) { return (which >= 0 && which < PEA_KNOB_COUNT) ? g_knobs[which].load(std::memory_order_relaxed) : 0; }
 
 // pea_affs_generic.cu
 int generic_partial_blocks(int64_t total);
@@ -180,6 +183,11 @@ static bool carve(void* ws, int B, int64_t N, int K, int cross, Workspace& out) 
     return true;
 }
 
+// the tiled kernels write `blocks` rows of K loss partials at the head of the workspace
+static bool partials_fit(int blocks, int K, const Workspace& ws) {
+    return blocks > 0 && (size_t)blocks * (size_t)K * sizeof(float) <= ws.bytes;
+}
+
 static int check_volume(int B, int C, int D, int H, int W, int K, Dims& d) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return PEA_E_SHAPE;
     if (C != 4 && C != 8 && C != 16 && C != 32) return PEA_E_CHANNELS;
@@ -205,6 +213,12 @@ static void fill_offsets(const int32_t* offsets, int K, OffsetTable& tab) {
 using namespace pea;
 
 extern "C" int pea_abi_version(void) { return PEA_ABI_VERSION; }
+
+extern "C" int pea_debug_configure(int knob, int value) {
+    if (knob < 0 || knob >= PEA_KNOB_COUNT) return PEA_E_MODE;
+    g_knobs[knob].store(value, std::memory_order_relaxed);
+    return PEA_OK;
+}
 
 extern "C" const char* pea_strerror(int code) {
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -358,14 +372,16 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
     // canonical multi_offset(shifts <= 12, neighbor=4) table (one view, or two views with the second one constant):
     // fully unrolled persistent kernel.
-    // PEA_NO_CANON (read per call, no state kept): test knob that sends these calls to the table-driven axis kernel.
-    if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC && grad_partner == nullptr && getenv("PEA_NO_CANON") == nullptr &&
+    // PEA_KNOB_NO_CANON: test knob (pea_debug_configure) that sends these calls to the table-driven axis kernel.
+    if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC && grad_partner == nullptr && debug_knob(PEA_KNOB_NO_CANON) == 0 &&
         canon2d_eligible(C, D, H, W, tab, emb, partner ? partner : emb, target, weight) && canon2d_mask_ok(mask, mask_dtype)) {
         float* parts = ws.rinvE;
+        const int nblk = canon2d_blocks(B, H, W);  // one evaluation: the launcher and the finalize kernel agree by construction
+        if (!partials_fit(nblk, K, ws)) return PEA_E_WORKSPACE;
         if ((rc = launch_canon2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts,
                                  grad_emb, st)))
             return rc;
-        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, canon2d_blocks(B, H, W), K, sc, loss_out);
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
     }
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC &&
         B <= 65535 &&
@@ -373,17 +389,21 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         !((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(weight)) & 3)) {
         // axis-aligned tables (every shipped 2-D config): TMA-staged kernel
         float* parts = ws.rinvE;
+        const int nblk = axis2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP);
+        if (!partials_fit(nblk, K, ws)) return PEA_E_WORKSPACE;
         if ((rc = launch_axis2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs, parts,
                                 grad_emb, st)))
             return rc;
-        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, axis2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
     }
     if (tiled2_ok && !tiled3_ok && impl != PEA_IMPL_GENERIC) {
         float* parts = ws.rinvE;
+        const int nblk = tiled2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP);
+        if (!partials_fit(nblk, K, ws)) return PEA_E_WORKSPACE;
         if ((rc = launch_tiled2d(emb, partner, d, tab, border == PEA_BORDER_WRAP, target, weight, mask, mask_dtype, affs,
                                  parts, grad_emb, st)))
             return rc;
-        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, tiled2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP), K, sc, loss_out);
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
     }
     const bool tiled_ok = tiled3_ok;
     if (tiled_ok && impl != PEA_IMPL_GENERIC) {
@@ -401,11 +421,12 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
             return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
         }
 #endif
+        const int nblk3 = cross ? cross3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W);
+        if (!partials_fit(nblk3, K, ws)) return PEA_E_WORKSPACE;
         rc = cross ? launch_cross3d_norm5(emb, partner, d, tab, target, weight, affs, parts, grad_emb, st)
                    : launch_fused3d_norm5(emb, d, tab, target, weight, affs, parts, grad_emb, st);
         if (rc) return rc;
-        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, cross ? cross3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W),
-                                                 K, sc, loss_out);
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk3, K, sc, loss_out);
     }
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
@@ -445,13 +466,17 @@ extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* lab
     if (semantics == 1) {  // 3-D: seg_to_aff targets of the 12-offset table, zero border
         const float* labf = reinterpret_cast<const float*>(labels);
         if (!tiled3d_norm5_eligible(C, D, H, W, tab, border, PEA_MASK_NONE, false, emb, labf, labf)) return PEA_E_MODE;
+        const int nblk = fused3d_norm5_blocks(B, H, W);
+        if (!partials_fit(nblk, K, ws)) return PEA_E_WORKSPACE;
         if ((rc = launch_fused3d_norm5_labels(emb, labels, wtab, d, tab, affs, parts, grad_emb, st))) return rc;
-        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, fused3d_norm5_blocks(B, H, W), K, sc, loss_out);
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
     }
     if (D != 1 || !canon2d_eligible(C, 1, H, W, tab, emb, emb, emb, reinterpret_cast<const float*>(labels))) return PEA_E_MODE;
+    const int nblk = canon2d_blocks(B, H, W);
+    if (!partials_fit(nblk, K, ws)) return PEA_E_WORKSPACE;
     if ((rc = launch_canon2d_labels(emb, labels, wtab, ignore, d, tab, border == PEA_BORDER_WRAP, affs, parts, grad_emb, st)))
         return rc;
-    return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, canon2d_blocks(B, H, W), K, sc, loss_out);
+    return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
 }
 
 extern "C" int pea_affs_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,

@@ -840,9 +840,8 @@ static int persistent_grid(int n_tiles, int ty) {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
         sms = 148;
     int g = sms * (ty <= 8 ? 2 : 1);
-    // test knob: a small grid makes every CTA walk many tiles even on small images (read per call, no state kept)
-    if (const char* cap = getenv("PEA_AXIS_MAX_CTAS")) {
-        const int c = atoi(cap);
+    // test knob (pea_debug_configure): a small grid makes every CTA walk many tiles even on small images
+    if (const int c = debug_knob(PEA_KNOB_MAX_CTAS)) {
         if (c > 0 && c < g) g = c;
     }
     return n_tiles < g ? n_tiles : g;

@@ -403,10 +403,10 @@ static bool plan2d(const OffsetTable& tab, int H, int W, int wrap, Plan2D& plan)
     }
     if (P > 64 || (int64_t)(tab.K > 16 ? tab.K : 16) * H * W >= ((int64_t)1 << 31)) return false;
     const int cands[3] = {16, 12, 8};
-    const char* force = getenv("PEA_TUNE_TY2D");  // tuning aid only: pin the tile height
+    const int force = debug_knob(PEA_KNOB_TUNE_TY2D);  // tuning aid only (pea_debug_configure): pin the tile height
     for (int i = 0; i < 3; ++i) {
         const int TY = cands[i];
-        if (force && atoi(force) != TY) continue;
+        if (force && force != TY) continue;
         const size_t tile = rect ? (size_t)16 * (TY + 2 * P) * (t2::TX + 2 * P) * 4
                                  : (size_t)16 * ((size_t)(TY + 2 * P) * t2::TX + (size_t)TY * (t2::TX + 2 * P)) * 4;
         const size_t scratch = (size_t)tab.K * TY * 32 * 4;

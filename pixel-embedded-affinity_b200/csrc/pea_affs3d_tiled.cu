@@ -1,19 +1,21 @@
-// Fused 3-D kernel for the AC3/AC4 12-offset set (embedding_loss_norm5, scripts_ac3ac4/loss/loss_embedding_mse.py:169-194):
-// embedding -> 12 axis-aligned affinities -> per-channel weighted MSE -> d loss / d embedding, ONE pass over HBM.
+// Tiled 3-D kernels for the AC3/AC4 12-offset set (scripts_ac3ac4/loss/loss_embedding_mse.py): a CTA owns TY x 32 voxel
+// columns of one sample and MARCHES along z; raw neighbour vectors are staged per slice by TMA (cp.async.bulk.tensor,
+// 5-D maps, zero fill outside the volume == the reference's "valid region only" rule), the z pairs never touch memory.
 //
-// Design (DESIGN.md "K4"):
-//   * one CTA owns an in-plane tile of TY x 32 voxel columns of one sample and MARCHES along z;
-//     each thread owns one column and keeps the last 5 slices' unit vectors e^ and gradient accumulators G in
-//     REGISTER RINGS, so the four z-pairs (shift 1..4) are evaluated once each with no neighbour traffic at all;
-//   * the eight in-plane offsets (y, x shifts 1/3/9/27, both directions in the gather-form backward) read RAW
-//     neighbour vectors from shared memory, staged per slice by TMA (cp.async.bulk.tensor, 5-D map, zero fill
-//     outside the volume == the reference's "valid region only" rule) into a y-column box, two y+-27 arm boxes
-//     and an x-row box; the neighbour's 1/|x| is recomputed in registers (16 FMA + MUFU) instead of being
-//     staged, so no normalised copy of the embedding ever exists in HBM;
-//   * TMA for slice z+1 is issued as soon as the last reader of a buffer has passed (two mbarriers, two
-//     __syncthreads per slice): copies overlap the x-part / z-part / epilogue of slice z;
-//   * loss: 12 per-thread accumulators over the march -> warp shuffle -> one row of partials per CTA ->
-//     fixed-order finalize kernel (deterministic).
+//   fused3d_norm5_tm   (default, embedding_loss_norm5 :169-194 and its label-driven flavour)  loss + backward, ONE pass:
+//       z rings (unit vectors + gradient accumulators of the last four slices) in TENSOR MEMORY (tcgen05.st / ld as a
+//       second register file, slot = z & 3), 12 warps per SM; y-column box + two y+-27 arm boxes + x-row box of raw
+//       vectors, neighbour 1/|x| recomputed in registers; target / weight by channel-strided TMA groups refilled by the
+//       last warp that has finished reading them (release / acquire counters, no __syncthreads in the slice loop);
+//       gather-form backward (20 pair evaluations per voxel); loss partials -> fixed-order finalize kernel.
+//   cross3d_norm5_tm   (ema_embedding_loss_norm5 :263-289)  two views, second one constant: no reverse pairs, partner
+//       ring in Tensor Memory.
+//   fwd3d_norm5        (inf_embedding_loss_norm5 :212-234, z-sharded volumes)  forward only, 4-slice register ring,
+//       optional external halo (peer GPU memory) for the ring warm-up, relu epilogue.
+//   fused3d_norm5 / cross3d_norm5  the round-1 register-ring variants (PEA_K4_TMEM = 0 / PEA_K4X_TMEM = 0), kept as the
+//       A/B reference point of DESIGN.md's history: 250 registers, 8 warps per SM.
+// What was measured and rejected for the one-view kernel (lane-packed pairs, scalar gradient update, balanced tile
+// heights, in-kernel loss finalize) lives in pea_affs3d_k4v2.cu and DESIGN.md section 4.
 #include "pea_k4_common.cuh"
 
 #ifndef PEA_TILE_Y3D

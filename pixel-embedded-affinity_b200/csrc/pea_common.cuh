@@ -57,4 +57,7 @@ __device__ __forceinline__ float load_mask(const void* mask, int mask_dtype, int
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Test-only dispatch knobs (pea_debug_configure, include/pea_b200.h): one relaxed atomic load per call, 0 in production.
+int debug_knob(int which);
+
 }  // namespace pea

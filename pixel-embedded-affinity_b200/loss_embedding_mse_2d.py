@@ -16,10 +16,30 @@ from .loss import is_weighted_mse
 
 
 def _check_mode(mode):
-    if mode != 'ours':
-        # the reference's other branch (nn.CosineSimilarity on un-normalised embeddings, :11-13) is not
-        # selected by any shipped config (cvppp.yaml:25, bbbc039v1.yaml dis_mode: 'ours')
-        raise NotImplementedError("pea_b200 implements mode='ours' (normalised dot product) only")
+    """mode == 'ours' (every shipped config: cvppp.yaml:25, bbbc039v1.yaml dis_mode) takes the CUDA kernels; any other value
+    selects the reference's second branch, nn.CosineSimilarity(dim=1, eps=1e-6) on the UN-normalised embeddings
+    (:11-13, :53-55, :73-75), composed from torch ops on the device (``_cosine_*`` below: complete, not accelerated)."""
+    return mode == 'ours'
+
+
+def _cosine_affs(anchor, partner, offsets):
+    cos = torch.nn.CosineSimilarity(dim=1, eps=1e-6)
+    return [cos(torch.roll(partner, shifts=(-int(o[0]), -int(o[1])), dims=(2, 3)), anchor) for o in offsets]
+
+
+def _cosine_loss(embedding, partner, target, weightmap, mask, criterion, offsets, coef):
+    """The reference loop (:35-46 / :87-94) in its cosine branch: no normalisation, masked criterion per offset."""
+    embedding = ops.check_embedding("embedding", embedding, 4)
+    partner = embedding if partner is None else ops.check_embedding("ema_embedding", partner, 4)
+    maskf = mask.float()
+    per = _cosine_affs(embedding, partner, offsets)
+    affs = torch.stack(per, dim=1)
+    loss, each = 0, []
+    for k, a in enumerate(per):
+        lk = criterion(a * maskf[:, k], target[:, k] * maskf[:, k], weightmap[:, k])
+        loss = loss + (lk * coef[k] if coef[k] != 1 else lk)
+        each.append(lk.detach())
+    return loss, affs, LossList(torch.stack(each))
 
 
 def _norms_2d(B, W, K):
@@ -38,11 +58,15 @@ def _prep(embedding, target, weightmap, mask, offsets):
     return embedding, target, weightmap, mask, offs3
 
 
-def embedding2affs(embedding, offsets, mode='ours'):
-    """:58-66.  (B,C,H,W) -> (B,K,H,W); affs[:,k][y,x] = <e^[y,x], e^[(y+dy)%H,(x+dx)%W]>."""
-    _check_mode(mode)
+def embedding2affs(embedding, offsets, mode='ours', relu=False):
+    """:58-66.  (B,C,H,W) -> (B,K,H,W); affs[:,k][y,x] = <e^[y,x], e^[(y+dy)%H,(x+dx)%W]>.
+    ``relu=True`` (default off: the reference's result) folds the caller's ``F.relu(pred)`` (scripts_cvppp/main.py:312,
+    inference) into the kernel's store (PEA_EPI_RELU); the result is then detached (inference form)."""
     embedding = ops.check_embedding("embedding", embedding, 4)
-    return Affinities.apply(embedding, None, ops.offsets3(offsets, 2), ops.BORDER_WRAP, ops.IMPL_AUTO)
+    if not _check_mode(mode):
+        return torch.stack(_cosine_affs(embedding, embedding, offsets), dim=1)
+    return Affinities.apply(embedding, None, ops.offsets3(offsets, 2), ops.BORDER_WRAP, ops.IMPL_AUTO,
+                            ) if not relu else ops.affs_fwd(embedding.detach(), None, ops.offsets3(offsets, 2), ops.BORDER_WRAP, relu=True)
 
 
 def _generic_criterion(affs, target, weightmap, mask, criterion, coef):
@@ -61,7 +85,9 @@ def embedding_loss(embedding, target, weightmap, mask, criterion, offsets, affs0
     """:18-47.  Returns (loss 0-dim tensor, affs (B,K,H,W) carrying grad, all_loss sequence of K floats).
 
     ``affs0_weight`` is accepted and ignored, as in the reference (:26-33 vs the commented-out :38)."""
-    _check_mode(mode)
+    if not _check_mode(mode):
+        e, t, w, m, _ = _prep(embedding, target, weightmap, mask, offsets)
+        return _cosine_loss(e, None, t, w, m, criterion, offsets, [1] * len(offsets))
     embedding, target, weightmap, mask, offs3 = _prep(embedding, target, weightmap, mask, offsets)
     B, C, H, W = embedding.shape
     K = offs3.shape[0]
@@ -83,7 +109,9 @@ def embedding_loss_multi(embeddings, targets, weightmaps, masks, criterion, offs
     ``WeightedMSE`` and at most 8 scales of at most 12 offsets the list runs through one work-list kernel that also
     finalizes every loss, and backward scales all gradients in one launch; anything else falls back to the calls above.
     Returns a list of (loss, affs, all_loss)."""
-    _check_mode(mode)
+    if not _check_mode(mode):
+        return [embedding_loss(e, t, w, m, criterion, o, affs0_weight, mode)
+                for e, t, w, m, o in zip(embeddings, targets, weightmaps, masks, offsets_list)]
     n = len(embeddings)
     if not (len(targets) == len(weightmaps) == len(masks) == len(offsets_list) == n):
         raise ValueError("embeddings, targets, weightmaps, masks and offsets_list must have the same length")
@@ -106,7 +134,11 @@ def ema_embedding_loss(embedding, ema_embedding, target, weightmap, mask, criter
                        mode='ours'):
     """:79-95.  Two-view variant: a = <e^[p], u^[p+o]>; offsets 0 and 1 are scaled by ``affs0_weight``.
     Returns (loss, affs)."""
-    _check_mode(mode)
+    if not _check_mode(mode):
+        e, t, w, m, _ = _prep(embedding, target, weightmap, mask, offsets)
+        loss, affs, _ = _cosine_loss(e, ema_embedding, t, w, m, criterion, offsets,
+                                     [affs0_weight if k < 2 else 1 for k in range(len(offsets))])
+        return loss, affs
     embedding, target, weightmap, mask, offs3 = _prep(embedding, target, weightmap, mask, offsets)
     ema_embedding = ops.check_embedding("ema_embedding", ema_embedding, 4)
     if ema_embedding.shape != embedding.shape:
@@ -137,14 +169,16 @@ def embedding_loss_labels(embedding, labels, criterion, offsets, affs0_weight=1,
     ``multi_offset(shifts <= 12, neighbor=4)`` with ``WeightedMSE`` the three GT tensors never exist: one counting pass
     over the labels, then the loss kernel derives target / mask / weight itself (172 instead of 258 bytes per pixel,
     and no GT generation pass).  Everything else takes the two-step route.  Returns (loss, affs, all_loss)."""
-    _check_mode(mode)
     embedding = ops.check_embedding("embedding", embedding, 4)
     B, C, H, W = embedding.shape
     if labels.dim() != 3 or tuple(labels.shape) != (B, H, W) or not labels.is_cuda:
         raise ValueError(f"labels must be a CUDA tensor of shape {(B, H, W)}, got {tuple(labels.shape)}")
     offs3 = ops.offsets3(offsets, 2)
     K = offs3.shape[0]
-    if is_weighted_mse(criterion) and W % 4 == 0 and not labels.dtype.is_floating_point:
+    # the kernel stages int32 labels: only dtypes whose every value fits take the fused route (an int64 / uint32 / uint64
+    # id >= 2^31 would wrap and could collide with another id or flip the `> 0` test); the others go two-step, which
+    # compares the labels in their own dtype
+    if _check_mode(mode) and is_weighted_mse(criterion) and W % 4 == 0 and labels.dtype in ops.INT32_SAFE_LABELS:
         lab = labels.contiguous()
         lab32 = lab if lab.dtype == torch.int32 else lab.to(torch.int32)
         spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), np.ones(K, np.float32), affs_differentiable=True)

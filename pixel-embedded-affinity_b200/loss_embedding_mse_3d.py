@@ -167,7 +167,8 @@ def embedding_loss_norm5_labels(embedding, seg, criterion, affs0_weight=1):
     B, C, D, H, W = embedding.shape
     if seg.dim() != 4 or tuple(seg.shape) != (B, D, H, W) or not seg.is_cuda:
         raise ValueError(f"seg must be a CUDA tensor of shape {(B, D, H, W)}, got {tuple(seg.shape)}")
-    if is_weighted_mse(criterion) and W % 4 == 0 and not seg.dtype.is_floating_point:
+    # int32 staging in the kernel: only label dtypes whose every value fits take the fused route (see the 2-D function)
+    if is_weighted_mse(criterion) and W % 4 == 0 and seg.dtype in ops.INT32_SAFE_LABELS:
         lab = seg.contiguous()
         lab32 = lab if lab.dtype == torch.int32 else lab.to(torch.int32)
         offs3 = offsets_from_shifts(SHIFTS_NORM5)

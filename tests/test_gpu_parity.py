@@ -740,14 +740,22 @@ def test_axis2d_kernel_matches_generic_and_oracle(P, O, B, H, W, shifts, seed):
         close_t(outs[1][i].cpu(), outs[0][i].cpu(), what=f"zero-border axis kernel {what}")
 
 
+KNOB_NO_CANON, KNOB_MAX_CTAS = 0, 1   # include/pea_b200.h, pea_debug_configure (test-only dispatch knobs)
+
+
+def _knob(which, value):
+    from pea_b200._lib import lib, check
+    check("pea_debug_configure", lib.pea_debug_configure(which, int(value)))
+
+
 @pytest.mark.parametrize("shifts", [[1, 3, 5, 9, 11], [1, 3, 5, 9, 27]])
 @pytest.mark.parametrize("cap", [1, 3, 7])
-def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, shifts, monkeypatch):
+def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, shifts):
     """The 2-D kernels are persistent: a CTA walks tiles t, t + grid, ... and requests the TMA boxes of its next tile
     while it finishes the current one; tiles on the image edge (circular border) are filled / patched by hand in between.
     Shifts <= 12 take the fully unrolled canonical kernel (pea_affs2d_canon.cu), the CVPPP table with shift 27 the
     table-driven one (pea_affs2d_axis.cu); the two-view loss always takes the latter.  With the grid capped to a few
-    CTAs (PEA_AXIS_MAX_CTAS, read per call) every CTA alternates between both kinds of tile many times: affinities and
+    CTAs (pea_debug_configure(PEA_KNOB_MAX_CTAS)) every CTA alternates between both kinds of tile many times: affinities and
     gradient must be bit-identical to the uncapped launch, the loss equal up to the summation order of the per-CTA
     partials, and everything must match the oracle."""
     offsets = O.multi_offset(shifts, neighbor=4)
@@ -755,10 +763,7 @@ def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, shifts, monkeypatch):
     emb, ema, tgt, wgt, msk = _inputs_2d(O, B, 16, H, W, offsets, 95)
     outs = {}
     for name, val in (("full", None), ("capped", str(cap))):
-        if val is None:
-            monkeypatch.delenv("PEA_AXIS_MAX_CTAS", raising=False)
-        else:
-            monkeypatch.setenv("PEA_AXIS_MAX_CTAS", val)
+        _knob(KNOB_MAX_CTAS, 0 if val is None else val)
         e = dev(emb, True)
         l, a, _ = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
         l.backward()
@@ -766,7 +771,7 @@ def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, shifts, monkeypatch):
         l2, a2 = P.ema_embedding_loss(e2, dev(ema), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets)
         l2.backward()
         outs[name] = (float(l.detach()), a.detach().cpu(), e.grad.cpu(), float(l2.detach()), a2.detach().cpu(), e2.grad.cpu())
-    monkeypatch.delenv("PEA_AXIS_MAX_CTAS", raising=False)
+    _knob(KNOB_MAX_CTAS, 0)
     for i in (1, 2, 4, 5):
         assert torch.equal(outs["full"][i], outs["capped"][i])
     close_s(outs["capped"][0], outs["full"][0], what="loss, capped grid")
@@ -781,9 +786,9 @@ def test_axis2d_persistent_ctas_walk_many_tiles(P, O, cap, shifts, monkeypatch):
 
 @pytest.mark.parametrize("B,H,W,border", [(2, 130, 160, "wrap"), (1, 75, 100, "wrap"), (2, 64, 72, "zero"), (1, 131, 200, "zero")])
 @pytest.mark.parametrize("mask_kind", ["u8", "f32", "none"])
-def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, mask_kind, monkeypatch):
+def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, mask_kind):
     """multi_offset([1, 3, 5, 9, 11], 4) takes the fully unrolled canonical kernel (one view, and two views with the
-    second one constant); with PEA_NO_CANON set the same call takes the table-driven axis-aligned kernel, with
+    second one constant); with pea_debug_configure(PEA_KNOB_NO_CANON, 1) the same call takes the table-driven axis-aligned kernel, with
     IMPL_GENERIC the generic one.  All three must agree (1e-5 of the largest magnitude) on loss, affinities and
     gradient: both borders, partial tiles in x and y, every mask type, both view counts, with and without gradient."""
     from pea_b200 import _ops as ops
@@ -805,15 +810,12 @@ def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, 
     for grad, partner in ((True, None), (False, None), (True, par), (False, par)):
         outs = {}
         for name in ("canon", "axis", "generic"):
-            if name == "axis":
-                monkeypatch.setenv("PEA_NO_CANON", "1")
-            else:
-                monkeypatch.delenv("PEA_NO_CANON", raising=False)
+            _knob(KNOB_NO_CANON, 1 if name == "axis" else 0)
             impl = ops.IMPL_GENERIC if name == "generic" else ops.IMPL_AUTO
             lo, a, gr, _ = ops.affs_loss_fwd_bwd(emb, partner, offs3, bd, tgt, wgt, msk, norm, coef, want_affs=True,
                                                  want_grad=grad, impl=impl)
             outs[name] = (lo.cpu(), a.cpu(), gr.cpu() if grad else None)
-        monkeypatch.delenv("PEA_NO_CANON", raising=False)
+        _knob(KNOB_NO_CANON, 0)
         for other in ("axis", "generic"):
             close_t(outs["canon"][0], outs[other][0], what=f"loss vs {other}")
             close_t(outs["canon"][1], outs[other][1], what=f"affs vs {other}")
@@ -1205,3 +1207,41 @@ def test_consistency_flip_golden_and_oracle(P, O, golden):
     close_s(l, lo, what="flip + ema loss")
     close_t(a, ao, what="flip + ema affs")
     close_t(e.grad, eo.grad, what="flip + ema grad")
+
+
+def test_cosine_mode_and_masked_weights_and_wide_labels(P, O):
+    """The rarely used corners of the reference's signatures: dis_mode != 'ours' (nn.CosineSimilarity on un-normalised
+    embeddings, loss_embedding_mse.py:11-13), weight_binary_ratio(mask=...) (data_segmentation.py:215-225), int64 labels
+    with ids beyond int32 in the label-driven losses, and embedding2affs(relu=True)."""
+    offsets = O.multi_offset([1, 3], neighbor=4)
+    emb, ema, tgt, wgt, msk = _inputs_2d(O, 2, 16, 20, 24, offsets, 61)
+    eo = torch.tensor(emb, requires_grad=True)
+    lo, ao, allo = O.embedding_loss(eo, torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk), O.WeightedMSE(), offsets, mode='cos')
+    lo.backward()
+    e = dev(emb, True)
+    l, a, al = P.embedding_loss(e, dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets, mode='cos')
+    l.backward()
+    close_s(l, lo, what="cosine loss")
+    close_t(a, ao, what="cosine affs")
+    close_t(e.grad, eo.grad, what="cosine grad")
+    lo2, _ = O.ema_embedding_loss(torch.tensor(emb), torch.tensor(ema), torch.tensor(tgt), torch.tensor(wgt), torch.tensor(msk),
+                                  O.WeightedMSE(), offsets, affs0_weight=2, mode='cos')
+    l2, _ = P.ema_embedding_loss(dev(emb), dev(ema), dev(tgt), dev(wgt), dev(msk), P.WeightedMSE(), offsets, affs0_weight=2, mode='cos')
+    close_s(l2, lo2, what="cosine ema loss")
+    close_t(P.embedding2affs(dev(emb), offsets, mode='cos'), O.embedding2affs(torch.tensor(emb), offsets, mode='cos'), what="cosine embedding2affs")
+    close_t(P.embedding2affs(dev(emb), offsets, relu=True), torch.relu(O.embedding2affs(torch.tensor(emb), offsets)), what="relu epilogue 2D")
+    # masked class-balance weights (0/1 mask: bit-exact)
+    rng = np.random.RandomState(4)
+    lab = (rng.rand(30, 40) > 0.7).astype(np.float32)
+    m = (rng.rand(30, 40) > 0.3).astype(np.float32)
+    same(P.weight_binary_ratio(lab, mask=m), O.weight_binary_ratio(lab, mask=m), "masked weights (numpy in)")
+    same(P.weight_binary_ratio(torch.tensor(lab).cuda(), mask=torch.tensor(m).cuda()), O.weight_binary_ratio(lab, mask=m), "masked weights")
+    # int64 labels whose ids differ by 2^32: equal after a cast to int32, different in the reference
+    lab64 = np.where(O.voronoi_labels((32, 48), 6, 3) % 2 == 0, 5, 5 + (1 << 32)).astype(np.int64)
+    offs = O.multi_offset([1, 3, 5, 9, 11], neighbor=4)
+    x = rng.randn(1, 16, 32, 48).astype(np.float32)
+    to, mo = O.gen_affs_ours(lab64, offs, ignore=False, padding=True)
+    wo = np.stack([O.weight_binary_ratio(c) for c in to])
+    lo3, _, _ = O.embedding_loss(torch.tensor(x), torch.tensor(to[None]), torch.tensor(wo[None]), torch.tensor(mo[None]), O.WeightedMSE(), offs)
+    l3, _, _ = P.embedding_loss_labels(dev(x), torch.tensor(lab64[None]).cuda(), P.WeightedMSE(), offs)
+    close_s(l3, lo3, what="int64 labels beyond int32")

@@ -35,9 +35,9 @@ for case in range(n_cases):
     partner = par if rng.rand() < 0.4 else None
     cap = int(rng.choice([0, 1, 2, 5]))
     if cap:
-        os.environ["PEA_AXIS_MAX_CTAS"] = str(cap)
+        P._lib.lib.pea_debug_configure(1, int(cap))  # PEA_KNOB_MAX_CTAS
     else:
-        os.environ.pop("PEA_AXIS_MAX_CTAS", None)
+        P._lib.lib.pea_debug_configure(1, 0)
     norm = np.full(K, float(B * W), np.float32)
     coef = np.linspace(0.5, 1.5, K).astype(np.float32)
     outs = []
@@ -53,16 +53,16 @@ for case in range(n_cases):
     l1, a1, _ = P.embedding_loss_labels(e1, lab_d, P.WeightedMSE(), offsets, ignore=ign)
     l1.backward()
     t2, m2, w2 = P.make_targets_2d(lab_d, offsets, ignore=ign, padding=True)
-    os.environ["PEA_NO_CANON"] = "1"
+    P._lib.lib.pea_debug_configure(0, 1)  # PEA_KNOB_NO_CANON
     e2 = emb[:, :, 0].clone().requires_grad_(True)
     l2, a2, _ = P.embedding_loss(e2, t2, w2, m2, P.WeightedMSE(), offsets)
     l2.backward()
-    os.environ.pop("PEA_NO_CANON", None)
+    P._lib.lib.pea_debug_configure(0, 0)
     errs += [abs(float(l1) - float(l2)) / abs(float(l2)), float((a1 - a2).abs().max() / a2.abs().max()),
              float((e1.grad - e2.grad).abs().max() / e2.grad.abs().max())]
     worst = max(worst, max(errs))
     flag = "" if max(errs) <= 1e-5 and all(np.isfinite(errs)) else "   <-- FAIL"
     print(f"case {case}: B={B} H={H} W={W} shifts={shifts} border={border} mask={None if msk is None else msk.dtype} "
           f"two_view={partner is not None} cap={cap} ignore={ign}: " + " ".join(f"{e:.1e}" for e in errs) + flag, flush=True)
-os.environ.pop("PEA_AXIS_MAX_CTAS", None)
+P._lib.lib.pea_debug_configure(1, 0)
 print("worst", worst, "OK" if worst <= 1e-5 else "FAIL")
