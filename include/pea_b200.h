@@ -114,16 +114,13 @@ int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, in
  * loss_out (device, 1 + K floats) receives [loss, loss_0 .. loss_{K-1}].
  * grad_emb (B,C,D,H,W) receives d loss / d emb for an upstream gradient of 1; grad_partner likewise for
  * the partner embedding; either may be NULL (not computed).  affs may be NULL (not stored).
- * mask may be NULL with mask_dtype = PEA_MASK_NONE.
- * ticket (optional, may be NULL): one device uint32 that is ZERO on entry and is left zero.  With it the kernels that
- * support it reduce the per-CTA loss partials themselves (last CTA to arrive, fixed order: reproducible) instead of a
- * second launch; one call in flight per ticket word (the Python layer keeps one per stream). */
+ * mask may be NULL with mask_dtype = PEA_MASK_NONE. */
 int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int B, int C, int D, int H, int W,
                           const int32_t* offsets, int K, int border, int impl,
                           const float* target, const float* weight, const void* mask, int mask_dtype,
                           const float* loss_norm, const float* loss_coef,
                           float* affs, float* loss_out, float* grad_emb, float* grad_partner,
-                          void* workspace, size_t ws_bytes, uint32_t* ticket, void* stream);
+                          void* workspace, size_t ws_bytes, void* stream);
 
 /* Backward of pea_affs_fwd for an arbitrary upstream gradient (criterion other than WeightedMSE, or a
  * caller that back-propagates through the returned 2-D affs, scripts_cvppp/loss/loss_embedding_mse.py:46).
@@ -139,7 +136,8 @@ int pea_affs_bwd(const float* emb, const float* partner, int B, int C, int D, in
  * Every problem has the semantics of pea_affs_loss_fwd_bwd (same fields, same loss_out layout); `partner` != NULL makes
  * it the two-view loss with the second view constant (no grad_partner here).  Up to PEA_MULTI_MAX_PROBLEMS problems of
  * up to PEA_MULTI_MAX_OFFSETS offsets (|component| <= 127) and the same channel count C.  The kernel finalizes every
- * problem's loss itself: `ticket` is REQUIRED (one device uint32, zero on entry, left zero).  workspace: at least
+ * problem's loss itself (last CTA to arrive, fixed order: reproducible): `ticket` is REQUIRED -- one device uint32 that is
+ * ZERO on entry and is left zero; one call in flight per ticket word (the Python layer keeps one per stream).  workspace: at least
  * pea_affs_loss_multi_workspace(problems, n) bytes. */
 #define PEA_MULTI_MAX_PROBLEMS 8
 #define PEA_MULTI_MAX_OFFSETS 12

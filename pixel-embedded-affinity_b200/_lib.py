@@ -35,7 +35,7 @@ SIGNATURES = {
     "pea_affs_fwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, ci, ctypes.c_int64, ctypes.c_int64, vp, ci,
                           ctypes.c_int64, vp, vp, ctypes.c_size_t, vp]),
     "pea_affs_loss_fwd_bwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, vp, vp, vp, ci, c_float_p,
-                                   c_float_p, vp, vp, vp, vp, vp, ctypes.c_size_t, vp, vp]),
+                                   c_float_p, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "pea_affs_bwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "pea_scale_inplace": (ci, [vp, ctypes.c_int64, vp, vp]),
     "pea_consistency_flip": (ci, [vp, vp, ci, ci, ci, ci, ci, vp, vp]),

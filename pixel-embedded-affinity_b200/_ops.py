@@ -115,8 +115,8 @@ _TICKET_POOL = {}   # device index -> [int32 zeros (256,), slots handed out]
 
 
 def _ticket(device):
-    """One zero-initialised device word per (device, stream): the fused kernels that finalize the loss themselves count
-    their CTAs on it and leave it zero (include/pea_b200.h, `ticket`).  Slots come out of a per-device pool created on
+    """One zero-initialised device word per (device, stream): the multi-problem kernel, which finalizes the losses itself,
+    counts its CTAs on it and leaves it zero (include/pea_b200.h, pea_affs_loss_multi `ticket`).  Slots come out of a per-device pool created on
     the first call, so nothing is allocated per call and a captured CUDA graph keeps pointing at live memory.  Returns
     None (=> separate finalize launch) if the very first call on a device happens inside a graph capture."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -220,7 +220,7 @@ def affs_loss_fwd_bwd(emb, partner, offs3, border, target, weight, mask, loss_no
     with torch.cuda.device(dev):
         rc = lib.pea_affs_loss_fwd_bwd(_ptr(emb), _ptr(partner), B, C, D, H, W, optr, K, border, impl, _ptr(target),
                                        _ptr(weight), _ptr(mask), mdt, nptr, cptr, _ptr(affs), _ptr(loss_out), _ptr(grad),
-                                       _ptr(gpar), _ptr(ws), n, _ptr(_ticket(dev)), _stream())
+                                       _ptr(gpar), _ptr(ws), n, _stream())
     check("pea_affs_loss_fwd_bwd", rc)
     return loss_out, affs, grad, gpar
 

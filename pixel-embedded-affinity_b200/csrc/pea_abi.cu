@@ -30,10 +30,6 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
                        const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
-int fused3d_norm5_v2_blocks(int B, int H, int W);
-int launch_fused3d_norm5_v2(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
-                            const float* weight, float* affs, float* partials, float* grad, uint32_t* ticket,
-                            float* loss_out, const float* norm, const float* coef, cudaStream_t st);
 int launch_fused3d_norm5_labels(const float* emb, const int32_t* seg, const float* wtab, const Dims& d, const OffsetTable& tab,
                                 float* affs, float* partials, float* grad, cudaStream_t st);
 
@@ -65,9 +61,6 @@ int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, 
                          const float* target, const float* weight, float* affs, float* partials, float* grad,
                          cudaStream_t st);
 
-#ifndef PEA_K4_V2
-#define PEA_K4_V2 0  // 1: fused3d_norm5_v2 (pea_affs3d_k4v2.cu: in-kernel finalize, pair-evaluation variants; measured 3 us slower)
-#endif
 #ifndef PEA_PDL
 #define PEA_PDL 1  // 0: plain stream-ordered launches of the two tail kernels (A/B)
 #endif
@@ -339,8 +332,7 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
                                      const int32_t* offsets, int K, int border, int impl, const float* target,
                                      const float* weight, const void* mask, int mask_dtype, const float* loss_norm,
                                      const float* loss_coef, float* affs, float* loss_out, float* grad_emb,
-                                     float* grad_partner, void* workspace, size_t ws_bytes, uint32_t* ticket,
-                                     void* stream) {
+                                     float* grad_partner, void* workspace, size_t ws_bytes, void* stream) {
     if (!emb || !offsets || !target || !weight || !loss_norm || !loss_coef || !loss_out || !workspace) return PEA_E_NULL;
     if (impl != PEA_IMPL_AUTO && impl != PEA_IMPL_GENERIC && impl != PEA_IMPL_TILED) return PEA_E_MODE;
     Dims d;
@@ -350,7 +342,6 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     if (mask_dtype != PEA_MASK_NONE && mask_dtype != PEA_MASK_U8 && mask_dtype != PEA_MASK_F32) return PEA_E_DTYPE;
     if (mask_dtype != PEA_MASK_NONE && !mask) return PEA_E_NULL;
     if (reinterpret_cast<uintptr_t>(workspace) % 16) return PEA_E_ALIGN;
-    if (reinterpret_cast<uintptr_t>(ticket) % 4) return PEA_E_ALIGN;
     const int cross = partner != nullptr;
     if (!cross && grad_partner) return PEA_E_MODE;
     Workspace ws;
@@ -409,18 +400,6 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
     if (tiled_ok && impl != PEA_IMPL_GENERIC) {
         // the per-voxel plane at the head of the workspace doubles as the (much smaller) partials array
         float* parts = ws.rinvE;
-#if PEA_K4_V2
-        if (!cross) {
-            // one view: balanced tiles, lane-packed pairs, loss finalized by the last CTA when a ticket word is given
-            const int nblk = fused3d_norm5_v2_blocks(B, H, W);
-            if ((size_t)nblk * 12 * sizeof(float) > ws.bytes) return PEA_E_WORKSPACE;
-            if ((rc = launch_fused3d_norm5_v2(emb, d, tab, target, weight, affs, parts, grad_emb, ticket, loss_out, sc.norm,
-                                              sc.coef, st)))
-                return rc;
-            if (ticket) return PEA_OK;
-            return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
-        }
-#endif
         const int nblk3 = cross ? cross3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W);
         if (!partials_fit(nblk3, K, ws)) return PEA_E_WORKSPACE;
         rc = cross ? launch_cross3d_norm5(emb, partner, d, tab, target, weight, affs, parts, grad_emb, st)

@@ -14,8 +14,8 @@
 //       optional external halo (peer GPU memory) for the ring warm-up, relu epilogue.
 //   fused3d_norm5 / cross3d_norm5  the round-1 register-ring variants (PEA_K4_TMEM = 0 / PEA_K4X_TMEM = 0), kept as the
 //       A/B reference point of DESIGN.md's history: 250 registers, 8 warps per SM.
-// What was measured and rejected for the one-view kernel (lane-packed pairs, scalar gradient update, balanced tile
-// heights, in-kernel loss finalize) lives in pea_affs3d_k4v2.cu and DESIGN.md section 4.
+// What round 2 measured and rejected for the one-view kernel (lane-packed pairs, scalar gradient update, balanced tile
+// heights, in-kernel loss finalize; commit 160d351 holds that kernel) is written up in DESIGN.md section 4.
 #include "pea_k4_common.cuh"
 
 #ifndef PEA_TILE_Y3D

@@ -913,7 +913,7 @@ def test_2d_kernels_write_only_their_outputs(P, O, shifts, two_view, labels):
     else:
         rc = lib.pea_affs_loss_fwd_bwd(emb.data_ptr(), par.data_ptr() if two_view else None, B, C, 1, H, W, offs, K,
                                        ops.BORDER_WRAP, ops.IMPL_AUTO, tgt.data_ptr(), wgt.data_ptr(), msk.data_ptr(), ops.MASK_U8,
-                                       norm, coef, affs.data_ptr(), loss.data_ptr(), grad.data_ptr(), None, ws.data_ptr(), nws, None, st)
+                                       norm, coef, affs.data_ptr(), loss.data_ptr(), grad.data_ptr(), None, ws.data_ptr(), nws, st)
         check("pea_affs_loss_fwd_bwd", rc)
     torch.cuda.synchronize()
     for name, buf, n in (("affs", affs_buf, B * K * H * W), ("grad", grad_buf, B * C * H * W), ("loss", loss_buf, 1 + K),
