@@ -256,10 +256,18 @@ def our_step(P, w, e, tgt, wgt, msk, offsets, crit, partner=None):
     return loss
 
 
-LAUNCHES_PER_STEP = 3  # fused3d_norm5_tm, finalize_loss, scale_inplace (profiles/r1_launches_bench_cfg3.csv)
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused kernel at cfg3, from the committed
-# `ncu --set full` capture (profiles/r1_fused3d_tm_cfg3.txt); the algorithmic figure is 501.35 MB
-NCU_TRAFFIC_BYTES = {"cfg3": 304.79e6 + 166.37e6, "cfg2": 456.13e6 + 270.55e6}  # cfg2: profiles/r1_fused2d_canon_cfg2.txt
+LAUNCHES_PER_STEP = 3  # fused3d_norm5_tm, finalize_loss, scale_inplace: fallback when the profiler cannot count them
+
+
+def ncu_traffic(workload):
+    """DRAM bytes of one launch of the workload's dominant kernel, from the committed ncu capture (profiles/traffic.json
+    names the digest it came from).  A profiler number cannot be taken inside a timed run; None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f)[workload]
+        return float(e["dram_bytes_read"] + e["dram_bytes_write"]), e["source"], e["kernel"]
+    except Exception:  # noqa: BLE001
+        return None, None, None
 
 
 def time_workload(P, w, steps, warmup, device, flush, dist_on):
@@ -568,64 +576,99 @@ def time_step6(P, device, flush, iters=20):
     return out
 
 
-def time_cfg5(P, device, rank, world, kind3d=True, steps=5):
-    """BASELINE config 5: one data-parallel training step with the REFERENCE's backbone (UNet_PNI_embedding_deep,
-    scripts_ac3ac4/model/model_superhuman.py:443-492, built as scripts_ac3ac4/main.py:122-133 does with ac3ac4.yaml's
-    filters), wrapped in DistributedDataParallel (NCCL gradient all-reduce over NVLink) + the six PEA loss calls + Adam.
-    Reported: step time with this package's loss functions and with the reference's own loss functions running as
-    eager torch ops on the GPU (context), and the loss functions' share of the step."""
+def time_cfg5(P, device, rank, world, dim=3, steps=5):
+    """BASELINE config 5: one data-parallel training step with the REFERENCE's backbone, unmodified --
+    dim 3: UNet_PNI_embedding_deep (scripts_ac3ac4/model/model_superhuman.py:443-492, built as main.py:122-133 does with
+    ac3ac4.yaml's filters) on (B,1,18,160,160); dim 2: ResidualUNet2D_deep (scripts_cvppp/model/unet2d_residual.py:324-353,
+    main.py:111-115) on (B,3,544,544) -- wrapped in DistributedDataParallel (NCCL gradient all-reduce over NVLink), the
+    six PEA loss calls of the training loop (main.py:223-230 / :284-293) and the optimizer step.  Reported: step time with
+    this package's loss functions and with the reference's own loss functions running as eager torch ops on the GPU
+    (context), and the loss functions' share of the step."""
     from oracle import ref_loader
     if not ref_loader.available():
         return {"unavailable": "reference model files not staged (baseline/_ref)"}
     ref = ref_loader.load(models=True)
-    B, D = 2, 18
+    B = 2   # ac3ac4.yaml / cvppp.yaml batch_size
     torch.manual_seed(1234)
-    model = ref.unet3d.UNet_PNI_embedding_deep(in_planes=1, out_planes=12, filters=[28, 36, 48, 64, 80], upsample_mode='bilinear',
-                                                decode_ratio=1, merge_mode='add', pad_mode='zero', bn_mode='async',
-                                                relu_mode='elu', init_mode='kaiming_normal', emd=16).to(device)
+    g = torch.Generator(device="cpu").manual_seed(77 + rank)
+    crit_p, crit_r = P.WeightedMSE(), ref.crit.WeightedMSE()
+
+    def rnd01(*shape):
+        return (torch.rand(shape, generator=g) > 0.5).float().to(device)
+
+    def rndw(*shape):
+        return (torch.rand(shape, generator=g) * 2 + 0.1).to(device)
+
+    if dim == 3:
+        D = 18
+        model = ref.unet3d.UNet_PNI_embedding_deep(in_planes=1, out_planes=12, filters=[28, 36, 48, 64, 80], upsample_mode='bilinear',
+                                                    decode_ratio=1, merge_mode='add', pad_mode='zero', bn_mode='async',
+                                                    relu_mode='elu', init_mode='kaiming_normal', emd=16).to(device)
+        name, inp = "UNet_PNI_embedding_deep", (B, 1, D, 160, 160)
+        tgt, wgt = rnd01(B, 12, D, 160, 160), rndw(B, 12, D, 160, 160)
+        downs = [(rnd01(B, 3, D, h, h), rndw(B, 3, D, h, h)) for h in (10, 20, 40, 80)]
+        L = ref.loss3d
+
+        def losses(ours, outs, ema):
+            emds, emb = list(outs[:4]), outs[4]
+            if ours:
+                l0, _ = P.embedding_loss_norm5(emb, tgt, wgt, crit_p)
+                l1, _ = P.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit_p)
+                ls = [r[0] for r in P.embedding_loss_norm1_multi(emds, [d[0] for d in downs], [d[1] for d in downs], crit_p)]
+            else:
+                l0, _ = L.embedding_loss_norm5(emb, tgt, wgt, crit_r)
+                l1, _ = L.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit_r)
+                ls = [L.embedding_loss_norm1(e, t, w, crit_r)[0] for e, (t, w) in zip(emds, downs)]
+            return l0 + l1 + ls[0] + ls[1] + ls[2] + ls[3]
+        opt_of = lambda m: torch.optim.Adam(m.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, amsgrad=True)
+    else:
+        model = ref.unet2d.ResidualUNet2D_deep(in_channels=3, out_channels=2, nfeatures=[16, 32, 64, 128, 256], emd=16,
+                                               if_sigmoid=False).to(device)
+        name, inp = "ResidualUNet2D_deep", (B, 3, 544, 544)
+        offsets = P.multi_offset([1, 3, 5, 9, 27], 4)
+        tgt, wgt, msk = rnd01(B, 10, 544, 544), rndw(B, 10, 544, 544), rnd01(B, 10, 544, 544)
+        # outputs come coarsest first (34^2 .. 272^2): emd4, emd3, emd2, emd1 = the first 2, 4, 6, 8 offsets (main.py:266, :284-287)
+        ks, hs = (2, 4, 6, 8), (34, 68, 136, 272)
+        downs = [(rnd01(B, k, h, h), rndw(B, k, h, h), rnd01(B, k, h, h)) for k, h in zip(ks, hs)]
+        L = ref.loss2d
+
+        def losses(ours, outs, ema):
+            emds, emb = list(outs[:4]), outs[4]
+            if ours:
+                l0, _, _ = P.embedding_loss(emb, tgt, wgt, msk, crit_p, offsets)
+                l1, _ = P.ema_embedding_loss(emb, ema, tgt, wgt, msk, crit_p, offsets)
+                ls = [r[0] for r in P.embedding_loss_multi(emds, [d[0] for d in downs], [d[1] for d in downs], [d[2] for d in downs],
+                                                           crit_p, [offsets[:k] for k in ks])]
+            else:
+                l0, _, _ = L.embedding_loss(emb, tgt, wgt, msk, crit_r, offsets)
+                l1, _ = L.ema_embedding_loss(emb, ema, tgt, wgt, msk, crit_r, offsets)
+                ls = [L.embedding_loss(e, d[0], d[1], d[2], crit_r, offsets[:k])[0] for e, d, k in zip(emds, downs, ks)]
+            return l0 + l1 + ls[0] + ls[1] + ls[2] + ls[3] + torch.nn.functional.mse_loss(emb, ema)   # + criterion_ct (main.py:295)
+        opt_of = lambda m: torch.optim.Adam(m.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=False)
     nparams = sum(p.numel() for p in model.parameters())
     if world > 1:
         # broadcast_buffers=False: the step runs the model twice (second view), and a buffer broadcast in the second
         # forward would modify BatchNorm buffers the first forward's graph still needs
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], broadcast_buffers=False)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, amsgrad=True)
-    g = torch.Generator(device="cpu").manual_seed(77 + rank)
-    x = torch.rand((B, 1, D, 160, 160), generator=g).to(device)
-    x2 = torch.rand((B, 1, D, 160, 160), generator=g).to(device)
-
-    def tw(K, h):
-        t = (torch.rand((B, K, D, h, h), generator=g) > 0.5).float().to(device)
-        w = (torch.rand((B, K, D, h, h), generator=g) * 2 + 0.1).to(device)
-        return t, w
-    tgt, wgt = tw(12, 160)
-    downs = [tw(3, h) for h in (10, 20, 40, 80)]
-    crit_p, crit_r = P.WeightedMSE(), ref.crit.WeightedMSE()
-    L3 = ref.loss3d
-
-    def losses(ours, emds, emb, ema):
-        if ours:
-            l0, _ = P.embedding_loss_norm5(emb, tgt, wgt, crit_p)
-            l1, _ = P.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit_p)
-            ls = [r[0] for r in P.embedding_loss_norm1_multi(emds, [d[0] for d in downs], [d[1] for d in downs], crit_p)]
-        else:
-            l0, _ = L3.embedding_loss_norm5(emb, tgt, wgt, crit_r)
-            l1, _ = L3.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit_r)
-            ls = [L3.embedding_loss_norm1(e, t, w, crit_r)[0] for e, (t, w) in zip(emds, downs)]
-        return l0 + l1 + ls[0] + ls[1] + ls[2] + ls[3]
+        # find_unused_parameters for the 2-D net: its mask head (binary_seg) takes no part in the loss the training loop
+        # builds (scripts_cvppp/main.py:295-308), which the reference's nn.DataParallel does not mind but DDP does
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], broadcast_buffers=False,
+                                                          find_unused_parameters=(dim == 2))
+    opt = opt_of(model)
+    x, x2 = torch.rand(inp, generator=g).to(device), torch.rand(inp, generator=g).to(device)
 
     def train_step(ours):
         opt.zero_grad(set_to_none=True)
         with torch.no_grad():          # second view first: its forward must not touch state the graph below depends on
-            ema = model(x2)[-1].detach().clone()
-        e1, e2, e3, e4, emb = model(x)
-        loss = losses(ours, [e1, e2, e3, e4], emb, ema)
+            ema = model(x2)[4].detach().clone()
+        outs = model(x)
+        loss = losses(ours, outs, ema)
         loss.backward()
         opt.step()
         return loss
 
-    out = {"model": "UNet_PNI_embedding_deep (reference file, unmodified)", "params": nparams, "per_gpu_batch": B,
-           "input": f"({B},1,18,160,160) per GPU", "collective": "DDP NCCL all-reduce of the backbone gradients" if world > 1 else "none (1 GPU)"}
-    for name, ours in (("ours", True), ("reference_loss_on_gpu", False)):
+    out = {"model": name + " (reference file, unmodified)", "params": nparams, "per_gpu_batch": B,
+           "input": f"{inp} per GPU", "collective": "DDP NCCL all-reduce of the backbone gradients" if world > 1 else "none (1 GPU)"}
+    for tag, ours in (("ours", True), ("reference_loss_on_gpu", False)):
         for _ in range(2):
             train_step(ours)
         torch.cuda.synchronize()
@@ -640,26 +683,27 @@ def time_cfg5(P, device, rank, world, kind3d=True, steps=5):
         ms = torch.tensor([s_.elapsed_time(t_) / steps], device=device, dtype=torch.float64)
         if world > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        out[name + "_step_ms"] = float(ms)
-        out[name + "_loss"] = float(loss.detach())
+        out[tag + "_step_ms"] = float(ms)
+        out[tag + "_loss"] = float(loss.detach())
     # the loss functions alone (fwd + bwd to the embeddings), same tensors, CUDA events
     with torch.no_grad():
         outs = model(x)
-    leaf = [o.detach().requires_grad_(True) for o in outs]
-    ema = model(x2)[-1].detach()
-    for name, ours in (("ours", True), ("reference_loss_on_gpu", False)):
+        ema = model(x2)[4].detach().clone()
+    leaf = [o.detach().requires_grad_(True) for o in outs[:5]]
+    for tag, ours in (("ours", True), ("reference_loss_on_gpu", False)):
         for _ in range(2):
-            losses(ours, leaf[:4], leaf[4], ema).backward()
+            losses(ours, leaf, ema).backward()
         torch.cuda.synchronize()
         s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_.record()
         for _ in range(steps):
-            losses(ours, leaf[:4], leaf[4], ema).backward()
+            losses(ours, leaf, ema).backward()
         t_.record()
         torch.cuda.synchronize()
-        out[name + "_loss_part_ms"] = s_.elapsed_time(t_) / steps
+        out[tag + "_loss_part_ms"] = s_.elapsed_time(t_) / steps
     out["samples_per_s"] = world * B / (out["ours_step_ms"] * 1e-3)
     out["loss_share_of_step"] = out["ours_loss_part_ms"] / out["ours_step_ms"]
+    out["loss_share_of_step_with_reference_loss"] = out["reference_loss_on_gpu_loss_part_ms"] / out["reference_loss_on_gpu_step_ms"]
     del model, opt
     torch.cuda.empty_cache()
     return out
@@ -936,19 +980,23 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
     e2e_value = world * vox_step * e2e_steps / (float(e2e_t) * 1e-3)
 
-    lab_ms = lab_bytes = lapi_ms = lapi_bytes = None
-    if rank == 0:
-        lab_ms, lab_bytes = time_e2e_labels_only(P, w, e2e_steps, device, res["inputs"])
-        lapi_ms, lapi_bytes = time_e2e_label_api(P, w, e2e_steps, device, res["inputs"])
+    # the label-driven end-to-end variants run on EVERY rank (same barrier / max-over-ranks rule as the headline e2e)
+    lab_ms, lab_bytes = time_e2e_labels_only(P, w, e2e_steps, device, res["inputs"])
+    lapi_ms, lapi_bytes = time_e2e_label_api(P, w, e2e_steps, device, res["inputs"])
+    if dist_on:
+        both = torch.tensor([lab_ms, lapi_ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(both, op=torch.distributed.ReduceOp.MAX)
+        lab_ms, lapi_ms = float(both[0]), float(both[1])
     res["inputs"] = None
-    zres = c5 = None
+    zres, c5 = None, {}
     if not args.quick:
         torch.cuda.empty_cache()
         zres = time_zshard(P, device, rank, world, 5)
-        try:
-            c5 = time_cfg5(P, device, rank, world)
-        except Exception as ex:  # noqa: BLE001
-            c5 = {"unavailable": f"{type(ex).__name__}: {ex}"}
+        for dim in (3, 2):
+            try:
+                c5[dim] = time_cfg5(P, device, rank, world, dim)
+            except Exception as ex:  # noqa: BLE001
+                c5[dim] = {"unavailable": f"{type(ex).__name__}: {ex}"}
     if rank == 0:
         peak, peak_src = measured_peak()
         ms_step = total_ms / args.steps
@@ -989,16 +1037,17 @@ def run_ours(args, rank, world, local_rank):
             "config": config_dict(w, args.workload),
             "parallelism": f"dp{world}: every rank runs the workload's batch (independent batches, no data-path collective)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic if args.traffic is not None else NCU_TRAFFIC_BYTES.get(args.workload),
+                         "traffic": args.traffic if args.traffic is not None else ncu_traffic(args.workload)[0],
+                         "traffic_source": "--traffic" if args.traffic is not None else ncu_traffic(args.workload)[1],
                          "peak_source": peak_src,
-                         "kernel": "whole fused step (all pea kernels of one fwd+bwd)",
+                         "kernel": "whole fused step (all pea kernels of one fwd+bwd); dominant kernel: " + str(ncu_traffic(args.workload)[2]),
                          "algorithmic_bytes_per_step": alg_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "what": "embedding+target+weight(+mask) from pinned host each step, loss read back"},
-            "e2e_labels_only": {"value": vox_step * e2e_steps / (lab_ms * 1e-3), "unit": UNIT,
+            "e2e_labels_only": {"value": world * vox_step * e2e_steps / (lab_ms * 1e-3), "unit": UNIT, "n_gpus": world,
                                 "h2d_bytes_per_step": lab_bytes,
                                 "what": "embedding resident (backbone output); labels uploaded, GT generated on device"},
-            "e2e_label_api": {"value": vox_step * e2e_steps / (lapi_ms * 1e-3), "unit": UNIT,
+            "e2e_label_api": {"value": world * vox_step * e2e_steps / (lapi_ms * 1e-3), "unit": UNIT, "n_gpus": world,
                               "h2d_bytes_per_step": lapi_bytes, "d2h_bytes_per_step": 4,
                               "what": "embedding + int32 labels from pinned host each step through the label-driven loss "
                                       "(embedding_loss_labels / embedding_loss_norm5_labels), loss read back"},
@@ -1021,8 +1070,8 @@ def run_ours(args, rank, world, local_rank):
         if zres is not None:
             zres["roofline_frac_per_gpu"] = zres["hbm_gbs_aggregate"] / world / peak
             also["cfg4"] = zres
-        if c5 is not None:
-            also["cfg5_3d"] = c5
+        for dim, r5 in c5.items():
+            also[f"cfg5_{dim}d"] = r5
         if also:
             line["also"] = also
         emit(line)

@@ -82,6 +82,39 @@ def test_new_entry_points_reject_bad_arguments_without_touching_the_device():
     assert r(one, 1, 3, 4, 8, 8, 10, 1, None) == -2     # plane smaller than D*H*W
 
 
+def test_round2_entry_points_reject_bad_arguments_without_touching_the_device():
+    """ABI v5 additions: multi-problem loss, gradient scaling list, patch blending, consistency flip, test knobs."""
+    import pea_b200
+    from pea_b200._lib import LossProblem
+    lib = pea_b200._lib.lib
+    one = ctypes.c_void_p(16)
+    offs = (ctypes.c_int32 * 6)(0, -1, 0, 0, 0, -1)
+    nrm = (ctypes.c_float * 2)(1.0, 1.0)
+    pr = (LossProblem * 1)()
+    pr[0].emb = pr[0].target = pr[0].weight = pr[0].loss_out = 16
+    pr[0].offsets, pr[0].loss_norm, pr[0].loss_coef = offs, nrm, nrm
+    pr[0].B, pr[0].D, pr[0].H, pr[0].W, pr[0].K, pr[0].border, pr[0].mask_dtype = 1, 1, 8, 8, 2, 0, 0
+    f = lib.pea_affs_loss_multi
+    assert lib.pea_affs_loss_multi_workspace(pr, 1) > 0 and lib.pea_affs_loss_multi_workspace(pr, 9) == 0
+    assert f(pr, 1, 16, one, 1 << 20, None, None) == -1      # the ticket word is required
+    assert f(pr, 0, 16, one, 1 << 20, one, None) == -2
+    assert f(pr, 1, 5, one, 1 << 20, one, None) == -3
+    assert f(pr, 1, 16, one, 8, one, None) == -5              # workspace too small
+    pr[0].K = 13
+    assert f(pr, 1, 16, one, 1 << 20, one, None) == -4        # more than PEA_MULTI_MAX_OFFSETS
+    pr[0].K, pr[0].border = 2, 7
+    assert f(pr, 1, 16, one, 1 << 20, one, None) == -8
+    b = lib.pea_blend_add
+    assert b(None, one, 12, 4, 8, 8, one, one, 8, 16, 16, 0, 0, 0, None) == -1
+    assert b(one, one, 12, 4, 8, 8, one, one, 8, 16, 16, 6, 0, 0, None) == -2     # patch leaves the volume
+    assert lib.pea_blend_finish(one, one, 12, 8, 16, 16, 4, 0, 0, 0, one, None) == -2   # nothing left after the crop
+    c = lib.pea_consistency_flip
+    assert c(None, one, 1, 16, 1, 8, 8, one, None) == -1
+    assert c(one, one, 1, 16, 1, 8, 8, one, None) == -8       # in place is refused
+    assert lib.pea_scale_multi(None, None, None, 1, None) == -1
+    assert lib.pea_debug_configure(99, 1) == -8 and lib.pea_debug_configure(0, 0) == 0
+
+
 def test_offset_tables_match_reference_convention(golden):
     import pea_b200
     g = golden["gt"]
