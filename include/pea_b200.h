@@ -243,8 +243,9 @@ int pea_replicate_first(float* affs, int B, int K, int D, int H, int W, int64_t 
  *                             target = gen_affs_ours(labels, offsets, ignore, padding)[0], mask = [1] (pairs across the
  *                             image edge dropped) and weight derived inside the kernel: results equal
  *                             pea_gt_targets followed by pea_affs_loss_fwd_bwd with a uint8 mask.
- * Implemented (C = 16): semantics 0 (gen_affs_ours) with the canonical 2-D tables multi_offset(shifts <= 12,
- * neighbor=4), D = 1, either border; semantics 1 (seg_to_aff without replicate pad) with the 12-offset AC3/AC4 table,
+ * Implemented (C = 16): semantics 0 (gen_affs_ours), D = 1, either border, with the canonical 2-D tables
+ * multi_offset(shifts <= 12, neighbor=4) (unrolled kernel) and with every other axis-aligned table whose shifts are
+ * <= 28, e.g. CVPPP's multi_offset([1, 3, 5, 9, 27], 4) (table-driven kernel, W % 4 == 0); semantics 1 (seg_to_aff without replicate pad) with the 12-offset AC3/AC4 table,
  * PEA_BORDER_ZERO.  Anything else returns PEA_E_MODE and the caller takes the two-step route.
  * counts: device scratch of pea_gt_counts_bytes(B, K). */
 int pea_gt_pair_weights(const void* labels, int label_dtype, int B, int D, int H, int W,

@@ -53,6 +53,8 @@ int launch_canon2d(const float* emb, const float* partner, const Dims& d, const 
                    cudaStream_t st);
 int launch_canon2d_labels(const float* emb, const int32_t* labels, const float* wtab, int ignore, const Dims& d,
                           const OffsetTable& tab, int wrap, float* affs, float* partials, float* grad, cudaStream_t st);
+int launch_axis2d_labels(const float* emb, const int32_t* labels, const float* wtab, int ignore, const Dims& d,
+                         const OffsetTable& tab, int wrap, float* affs, float* partials, float* grad, cudaStream_t st);
 int launch_axis2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap,
                   const float* target, const float* weight, const void* mask, int mask_dtype, float* affs, float* partials,
                   float* grad, cudaStream_t st);
@@ -450,7 +452,17 @@ extern "C" int pea_affs_loss_labels_fwd_bwd(const float* emb, const int32_t* lab
         if ((rc = launch_fused3d_norm5_labels(emb, labels, wtab, d, tab, affs, parts, grad_emb, st))) return rc;
         return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk, K, sc, loss_out);
     }
-    if (D != 1 || !canon2d_eligible(C, 1, H, W, tab, emb, emb, emb, reinterpret_cast<const float*>(labels))) return PEA_E_MODE;
+    if (D != 1) return PEA_E_MODE;
+    if (!canon2d_eligible(C, 1, H, W, tab, emb, emb, emb, reinterpret_cast<const float*>(labels)) ||
+        debug_knob(PEA_KNOB_NO_CANON) != 0) {
+        // any other axis-aligned table (CVPPP's shift 27): the table-driven axis kernel's label-driven flavour
+        if (B > 65535 || !axis2d_eligible(C, 1, H, W, tab, border == PEA_BORDER_WRAP, false, emb, emb)) return PEA_E_MODE;
+        const int nb = axis2d_blocks(B, H, W, tab, border == PEA_BORDER_WRAP);
+        if (!partials_fit(nb, K, ws)) return PEA_E_WORKSPACE;
+        if ((rc = launch_axis2d_labels(emb, labels, wtab, ignore, d, tab, border == PEA_BORDER_WRAP, affs, parts, grad_emb, st)))
+            return rc;
+        return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nb, K, sc, loss_out);
+    }
     const int nblk = canon2d_blocks(B, H, W);
     if (!partials_fit(nblk, K, ws)) return PEA_E_WORKSPACE;
     if ((rc = launch_canon2d_labels(emb, labels, wtab, ignore, d, tab, border == PEA_BORDER_WRAP, affs, parts, grad_emb, st)))

@@ -69,6 +69,14 @@ __device__ __forceinline__ float ldg_f32_early(const float* p, bool pred) {
         : "l"(p), "r"((int)pred));
     return v;
 }
+__device__ __forceinline__ int32_t ldg_i32_early(const int32_t* p, bool pred) {
+    int32_t v;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.s32 %0, 0;\n\t@q ld.global.nc.s32 %0, [%1];\n\t}"
+        : "=r"(v)
+        : "l"(p), "r"((int)pred));
+    return v;
+}
 __device__ __forceinline__ uint32_t ldg_u8_early(const uint8_t* p, bool pred) {
     uint32_t v;
     asm volatile(
@@ -107,6 +115,11 @@ struct Params {
     // y offsets first, then x offsets: channel id, signed shift, 2 * coef / norm of that channel
     int chan[kMaxK], shift[kMaxK];
     float gcoef[kMaxK];
+    // label-driven flavour (LAB): target / mask / weight derived in the kernel from the int32 label plane (gen_affs_ours
+    // semantics) and the per-(sample, channel) weight pairs of pea_gt_pair_weights; target / weight / mask are null
+    const int32_t* labels;
+    const float* wtab;  // [B][K][2]: weight where the target is 1 / 0
+    int ignore;
 };
 
 template <int TY, int PMAX>
@@ -454,7 +467,7 @@ __device__ __forceinline__ uint32_t arrive_count(uint32_t* cnt) {
     return old;
 }
 
-template <int TY, int PMAX, bool CROSS, int MASK, bool GRAD>
+template <int TY, int PMAX, bool CROSS, int MASK, bool GRAD, bool LAB = false>
 __global__ void __launch_bounds__(TY * 32, (TY <= 8) ? 2 : 1)
 fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, const Params P,
                const int tiles_x, const int tiles_y, const int n_tiles) {
@@ -518,8 +531,34 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
         const bool patch = wrap && !inner;
         const uint32_t goal = kWarps * (it + 1) - 1;
 
-        const float* tgt_b = P.target + (int64_t)b * K * Nu + pix;
-        const float* wgt_b = P.weight + (int64_t)b * K * Nu + pix;
+        const float* tgt_b = LAB ? nullptr : P.target + (int64_t)b * K * Nu + pix;
+        const float* wgt_b = LAB ? nullptr : P.weight + (int64_t)b * K * Nu + pix;
+        // LAB: the pixel's own label; partners' labels are fetched per offset like target / weight / mask otherwise
+        const int32_t* lab_b = LAB ? P.labels + (int64_t)b * Nu + pix : nullptr;
+        const int32_t lp = LAB ? ldg_i32_early(lab_b, live) : 0;
+        // gen_affs_ours (scripts_cvppp/utils/affinity_ours.py:17-39): target = same label (ignore: and both non-zero); a
+        // pair whose other end lies outside the image is masked out (mask 0; the target's padding value is immaterial) --
+        // the ground truth never wraps, whatever the border rule of the affinities is
+        auto fetch_lab = [&](int i) -> KV {
+            KV v = {0.f, 0.f, 0.f, 0.f, 1u, 1u};
+            if (i >= ntot) return v;
+            const bool isx = i >= ny;
+            const int s = P.shift[i];
+            const int qx = isx ? x + s : x, qy = isx ? y : y + s;  // partner of the pair anchored at this pixel
+            const int rx = isx ? x - s : x, ry = isx ? y : y - s;  // anchor of the pair whose partner is this pixel
+            const bool vf = live && (unsigned)qx < (unsigned)W && (unsigned)qy < (unsigned)H;
+            const bool vr = GRAD && live && (unsigned)rx < (unsigned)W && (unsigned)ry < (unsigned)H;
+            const int32_t lq = ldg_i32_early(lab_b + (vf ? (int64_t)(qy * W + qx) - (int64_t)pix : 0), vf);
+            const int32_t lr = ldg_i32_early(lab_b + (vr ? (int64_t)(ry * W + rx) - (int64_t)pix : 0), vr);
+            const bool sf = lp == lq && (!P.ignore || (lp != 0 && lq != 0));
+            const bool sr = lr == lp && (!P.ignore || (lp != 0 && lr != 0));
+            const float* wt = P.wtab + ((int64_t)b * K + P.chan[i]) * 2;
+            v.t = sf ? 1.f : 0.f;
+            v.w = ldg_f32_early(wt + (sf ? 0 : 1), vf);
+            v.t2 = sr ? 1.f : 0.f;
+            v.w2 = ldg_f32_early(wt + (sr ? 0 : 1), vr);
+            return v;
+        };
         const uint8_t* m8_b = MASK == PEA_MASK_U8 ? reinterpret_cast<const uint8_t*>(P.mask) + (int64_t)b * K * Nu + pix : nullptr;
         const float* mf_b = MASK == PEA_MASK_F32 ? reinterpret_cast<const float*>(P.mask) + (int64_t)b * K * Nu + pix : nullptr;
 
@@ -630,7 +669,7 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
 #ifdef PEA_AXIS_NOFETCH  // timing experiments only
             auto fetch = [&](int i) -> KV { KV v = {0.5f, 1.25f, 0.25f, 0.75f, 1u, 1u}; return v; };
 #else
-            auto fetch = [&](int i) -> KV { return INNER ? fetch_inner(i) : fetch_edge(i); };
+            auto fetch = [&](int i) -> KV { return LAB ? fetch_lab(i) : (INNER ? fetch_inner(i) : fetch_edge(i)); };
 #endif
 #if PEA_AXIS_DEPTH == 4
             KV kv0 = fetch(0), kv1 = fetch(1), kv2 = fetch(2), kv3;
@@ -906,6 +945,29 @@ static int launch_axis_p(const float* src, const Dims& d, const a2::Params& P, b
     return launch_axis_g<TY, PMAX, false, PEA_MASK_NONE>(mY, mX, P, grid, st);
 }
 
+template <int TY, int PMAX>
+static int launch_axis_lab(const float* src, const Dims& d, const a2::Params& P, cudaStream_t st) {
+    using G_ = a2::Geo<TY, PMAX>;
+    CUtensorMap mY, mX;
+    int rc;
+    if ((rc = encode_volume_map(&mY, src, d.B, 16, 1, d.H, d.W, a2::TX, G_::YR, 1, 16))) return rc;
+    if ((rc = encode_volume_map(&mX, src, d.B, 16, 1, d.H, d.W, G_::XW, TY, 1, 16))) return rc;
+    const int tiles_x = (P.W + a2::TX - 1) / a2::TX, tiles_y = (P.H + TY - 1) / TY, n_tiles = tiles_x * tiles_y * P.B;
+    const int g = persistent_grid(n_tiles, TY);
+    const size_t smem = sizeof(a2::Stage<TY, PMAX>) + 128;
+    cudaError_t e;
+    if (P.grad) {
+        auto kern = a2::fused2d_axis_p<TY, PMAX, false, PEA_MASK_NONE, true, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<g, TY * 32, smem, st>>>(mY, mX, P, tiles_x, tiles_y, n_tiles);
+    } else {
+        auto kern = a2::fused2d_axis_p<TY, PMAX, false, PEA_MASK_NONE, false, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        kern<<<g, TY * 32, smem, st>>>(mY, mX, P, tiles_x, tiles_y, n_tiles);
+    }
+    return (int)cudaGetLastError();
+}
+
 // fused loss (+ gradient w.r.t. the anchor view) for an axis-aligned table; target / weight must be given
 int launch_axis2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap,
                   const float* target, const float* weight, const void* mask, int mask_dtype, float* affs, float* partials,
@@ -918,6 +980,7 @@ int launch_axis2d(const float* emb, const float* partner, const Dims& d, const O
     P.emb = emb; P.par = partner ? partner : emb;
     P.target = target; P.weight = weight; P.mask = mask;
     P.affs = affs; P.grad = grad; P.partials = partials;
+    P.labels = nullptr; P.wtab = nullptr; P.ignore = 0;
     for (int i = 0; i < pl.ny + pl.nx; ++i) {
         P.chan[i] = pl.chan[i];
         P.shift[i] = pl.shift[i];
@@ -928,6 +991,29 @@ int launch_axis2d(const float* emb, const float* partner, const Dims& d, const O
     const float* src = partner ? partner : emb;
     if (pl.pmax == 12) return launch_axis_p<PEA_AXIS_TY, 12>(src, d, P, partner != nullptr, mask_dtype, grid, st);
     return launch_axis_p<12, 28>(src, d, P, partner != nullptr, mask_dtype, grid, st);
+}
+
+// Label-driven flavour for every axis-aligned table (e.g. CVPPP's multi_offset([1, 3, 5, 9, 27], 4), which the canonical
+// kernel does not take): target = gen_affs_ours(labels, offsets, ignore, padding)[0], mask = [1], weight from the pair
+// table of pea_gt_pair_weights -- none of the three tensors exists.
+int launch_axis2d_labels(const float* emb, const int32_t* labels, const float* wtab, int ignore, const Dims& d,
+                         const OffsetTable& tab, int wrap, float* affs, float* partials, float* grad, cudaStream_t st) {
+    PlanAxis pl;
+    if (!plan_axis(tab, d.H, d.W, wrap, pl)) return PEA_E_MODE;
+    a2::Params P;
+    P.B = d.B; P.H = d.H; P.W = d.W; P.K = tab.K; P.wrap = wrap;
+    P.ny = pl.ny; P.nx = pl.nx;
+    P.emb = emb; P.par = emb;
+    P.target = nullptr; P.weight = nullptr; P.mask = nullptr;
+    P.affs = affs; P.grad = grad; P.partials = partials;
+    P.labels = labels; P.wtab = wtab; P.ignore = ignore;
+    for (int i = 0; i < pl.ny + pl.nx; ++i) {
+        P.chan[i] = pl.chan[i];
+        P.shift[i] = pl.shift[i];
+        P.gcoef[i] = tab.gcoef[pl.chan[i]];
+    }
+    for (int i = pl.ny + pl.nx; i < a2::kMaxK; ++i) { P.chan[i] = 0; P.shift[i] = 0; P.gcoef[i] = 0.f; }
+    return pl.pmax == 12 ? launch_axis_lab<PEA_AXIS_TY, 12>(emb, d, P, st) : launch_axis_lab<12, 28>(emb, d, P, st);
 }
 
 }  // namespace pea

@@ -827,7 +827,10 @@ def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, 
     (2, 130, 160, [1, 3, 5, 9, 11], np.uint8, False),    # canonical table: GT derived inside the loss kernel
     (1, 75, 100, [1, 3, 5, 9, 11], np.int32, True),      # partial tiles in x and y, ignore=True
     (1, 64, 96, [1, 2, 4, 8, 12], np.uint8, False),
-    (1, 67, 96, [1, 3, 5, 9, 27], np.uint8, False),      # CVPPP table: two-step route behind the same call
+    (1, 67, 96, [1, 3, 5, 9, 27], np.uint8, False),      # CVPPP table: label-driven flavour of the table-driven axis kernel
+    (2, 130, 160, [1, 3, 5, 9, 27], np.int16, True),     # ... interior + edge tiles, ignore=True
+    (1, 64, 96, [2, 7], np.uint8, False),                # a table the canonical kernel does not know
+    (1, 66, 94, [1, 3, 5, 9, 27], np.uint8, False),      # W % 4 != 0: two-step route behind the same call
 ])
 def test_embedding_loss_labels_equals_gt_then_loss(P, O, B, H, W, shifts, ldtype, ignore):
     """embedding_loss_labels(embedding, labels, ...) == gen_affs_ours + weight_binary_ratio per (sample, channel) +
@@ -869,7 +872,7 @@ def test_embedding_loss_labels_equals_gt_then_loss(P, O, B, H, W, shifts, ldtype
 
 @pytest.mark.parametrize("shifts,two_view,labels", [([1, 3, 5, 9, 11], False, False), ([1, 3, 5, 9, 11], True, False),
                                                      ([1, 3, 5, 9, 11], False, True), ([1, 3, 5, 9, 27], False, False),
-                                                     ([1, 3, 5, 9, 27], True, False)])
+                                                     ([1, 3, 5, 9, 27], True, False), ([1, 3, 5, 9, 27], False, True)])
 def test_2d_kernels_write_only_their_outputs(P, O, shifts, two_view, labels):
     """Guard bands (compute-sanitizer is not available on the GPU pool): affinities, gradient, loss vector and workspace
     are carved out of larger poisoned buffers and handed to the C ABI directly; at a shape with partial tiles in x and
