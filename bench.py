@@ -1028,6 +1028,8 @@ def run_ours(args, rank, world, local_rank):
             also["cfg4_epilogue"] = time_inference_epilogue(P, device)
             also["cfg2_labels"] = time_labels_pipeline(P, WORKLOADS["cfg2"], device, flush)
             also["cfg2_labels"]["roofline_frac"] = also["cfg2_labels"]["hbm_gbs"] / peak
+            also["cfg1_labels"] = time_labels_pipeline(P, WORKLOADS["cfg1"], device, flush)   # CVPPP table: axis kernel's label flavour
+            also["cfg1_labels"]["roofline_frac"] = also["cfg1_labels"]["hbm_gbs"] / peak
             also["step6"] = time_step6(P, device, flush)
             torch.cuda.empty_cache()
         line = {

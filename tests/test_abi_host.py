@@ -68,8 +68,9 @@ def test_new_entry_points_reject_bad_arguments_without_touching_the_device():
     assert f(one, one, 0, 16, 1, 64, 64, offs, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -2
     assert f(one, one, 1, 16, 1, 64, 64, offs, 2, 0, 5, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -8   # semantics
     assert f(one, one, 1, 16, 1, 64, 64, offs, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 0, None) == -5          # workspace
-    # a table that is not multi_offset(shifts <= 12, 4): the caller must take the two-step route
-    assert f(one, one, 1, 16, 1, 64, 64, offs, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -8
+    # a table that is not axis-aligned (a diagonal offset): the caller must take the two-step route
+    diag = (ctypes.c_int32 * 6)(0, -1, -1, 0, 0, -1)
+    assert f(one, one, 1, 16, 1, 64, 64, diag, 2, 0, 0, 0, one, nrm, nrm, one, one, one, one, 1 << 30, None) == -8
     g = lib.pea_gt_pair_weights
     assert g(None, 0, 1, 1, 8, 8, offs, 2, 0, 0, 1, 1.0, one, one, 64, None) == -1
     assert g(one, 0, 1, 1, 8, 8, offs, 2, 3, 0, 1, 1.0, one, one, 64, None) == -8     # semantics
