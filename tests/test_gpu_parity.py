@@ -1248,3 +1248,61 @@ def test_cosine_mode_and_masked_weights_and_wide_labels(P, O):
     lo3, _, _ = O.embedding_loss(torch.tensor(x), torch.tensor(to[None]), torch.tensor(wo[None]), torch.tensor(mo[None]), O.WeightedMSE(), offs)
     l3, _, _ = P.embedding_loss_labels(dev(x), torch.tensor(lab64[None]).cuda(), P.WeightedMSE(), offs)
     close_s(l3, lo3, what="int64 labels beyond int32")
+
+
+def test_multi_and_flip_write_only_their_outputs(P, O):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): the multi-problem launch and the flip kernel get
+    output buffers carved out of larger poisoned ones; every byte outside must stay untouched, every element inside
+    must be written (partial 32-voxel chunks, partial 32 x 32 flip tiles)."""
+    POISON, PAD = -12345.0, 2048
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * PAD,), POISON, dtype=torch.float32, device="cuda")
+        return buf, buf[PAD:PAD + n].view(shape)
+
+    from pea_b200 import _ops as ops
+    from pea_b200._lib import lib, check, LossProblem
+    import ctypes
+    shapes = [(1, 16, 3, 5, 7), (2, 16, 3, 9, 11)]   # 105 and 594 voxels: neither a multiple of 32
+    g = torch.Generator().manual_seed(3)
+    offs = (ctypes.c_int32 * 9)(-1, 0, 0, 0, -1, 0, 0, 0, -1)
+    nrm = (ctypes.c_float * 3)(7.0, 7.0, 7.0)
+    cf = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
+    arr = (LossProblem * 2)()
+    keep, bufs = [], []
+    for i, shp in enumerate(shapes):
+        B, C, D, H, W = shp
+        emb = torch.randn(shp, generator=g).cuda()
+        tgt = (torch.rand((B, 3, D, H, W), generator=g) > 0.5).float().cuda()
+        wgt = (torch.rand((B, 3, D, H, W), generator=g) + 0.1).cuda()
+        ab, affs = guarded((B, 3, D, H, W))
+        gb, grad = guarded(shp)
+        lb, lout = guarded((4,))
+        keep += [emb, tgt, wgt]
+        bufs += [(ab, affs), (gb, grad), (lb, lout)]
+        a = arr[i]
+        a.emb, a.target, a.weight, a.affs, a.grad_emb, a.loss_out = (emb.data_ptr(), tgt.data_ptr(), wgt.data_ptr(), affs.data_ptr(),
+                                                                     grad.data_ptr(), lout.data_ptr())
+        a.offsets, a.loss_norm, a.loss_coef = offs, nrm, cf
+        a.B, a.D, a.H, a.W, a.K, a.border, a.mask_dtype = B, D, H, W, 3, ops.BORDER_ZERO, ops.MASK_NONE
+    nws = lib.pea_affs_loss_multi_workspace(arr, 2)
+    wb, ws = guarded(((nws + 3) // 4,))
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check("pea_affs_loss_multi", lib.pea_affs_loss_multi(arr, 2, 16, ws.data_ptr(), nws, ticket.data_ptr(),
+                                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(ticket) == 0, "the ticket word must be left zero"
+    for buf, view in bufs + [(wb, ws)]:
+        n = view.numel()
+        assert bool((buf[:PAD] == POISON).all()) and bool((buf[PAD + n:] == POISON).all()), "guard band overwritten"
+    for buf, view in bufs:
+        assert not bool((view == POISON).any()) and bool(torch.isfinite(view).all()), "output element left unwritten"
+    x = torch.randn((3, 2, 2, 37, 37), generator=g).cuda()
+    ob, out = guarded(tuple(x.shape))
+    rules = torch.tensor([[1, 1, 0, 1], [0, 0, 1, 1], [1, 0, 0, 0]], dtype=torch.int32).cuda()
+    check("pea_consistency_flip", lib.pea_consistency_flip(x.data_ptr(), rules.data_ptr(), 3, 2, 2, 37, 37, out.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert bool((ob[:PAD] == POISON).all()) and bool((ob[PAD + out.numel():] == POISON).all()), "flip: guard band overwritten"
+    assert torch.equal(out.cpu(), O.convert_consistency_flip(x.cpu(), rules.cpu()))

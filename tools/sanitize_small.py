@@ -39,5 +39,25 @@ for impl in (ops.IMPL_GENERIC, ops.IMPL_TILED):
     lx, ax = P.ema_embedding_loss(e3, torch.tensor(emb2[::-1].copy()).cuda(), t2, w2, m2, crit, offsets); lx.backward()
 ops.set_default_impl(ops.IMPL_AUTO)
 P.gen_affs_ours(lab, offsets, padding=True); P.seg_to_aff(seg); P.weight_binary_ratio(t2[0, 0].cpu().numpy())
+# round 2: multi-problem launch (3-D and 2-D), label-driven axis kernel (CVPPP table), flip, patch blending, pyramid GT
+embs = [torch.tensor(rng.randn(1, 16, 5, h, h).astype(np.float32)).cuda().requires_grad_(True) for h in (6, 12)]
+tw = [(torch.rand(1, 3, 5, h, h).cuda().round(), torch.rand(1, 3, 5, h, h).cuda() + 0.1) for h in (6, 12)]
+r = P.embedding_loss_norm1_multi(embs, [t for t, _ in tw], [w for _, w in tw], crit)
+(r[0][0] + r[1][0]).backward()
+offs27 = P.multi_offset([1, 3, 5, 9, 27], 4)
+lab2 = torch.tensor(np.stack([O.voronoi_labels((66, 96), 6, 4), O.voronoi_labels((66, 96), 6, 5)])).cuda()
+e27 = torch.tensor(rng.randn(2, 16, 66, 96).astype(np.float32)).cuda().requires_grad_(True)
+l27, a27, _ = P.embedding_loss_labels(e27, lab2, crit, offs27); l27.backward()
+(t27, m27, w27), downs = P.make_targets_pyramid_2d(lab2[:, :64, :], offs27)
+em2 = [torch.tensor(rng.randn(2, 16, 64 // f, 96 // f).astype(np.float32)).cuda().requires_grad_(True) for f in (2, 4)]
+ks = (8, 6)
+r2 = P.embedding_loss_multi(em2, [d[:, :k] for d, k in zip(downs, ks)], [d[:, k:2 * k] for d, k in zip(downs, ks)],
+                            [d[:, 2 * k:] for d, k in zip(downs, ks)], crit, [offs27[:k] for k in ks])
+(r2[0][0] + r2[1][0]).backward()
+P.convert_consistency_flip(torch.tensor(rng.randn(2, 4, 3, 37, 37).astype(np.float32)).cuda(), torch.tensor([[1, 0, 1, 1], [0, 1, 1, 0]]).cuda())
+bl = P.VolumeBlender(12, (D, H, W + 4), (D, H, W), "cuda")
+bl.add_vol(P.inf_embedding_loss_norm5(torch.tensor(emb).cuda(), relu=True, replicate_border=True), (0, 0, 0))
+bl.add_vol(f, (0, 0, 4))
+bl.get_results((0, 2, 2), one_minus=True)
 torch.cuda.synchronize()
-print("sanitize_small ok", float(l.detach()), float(lx.detach()))
+print("sanitize_small ok", float(l.detach()), float(lx.detach()), float(l27.detach()))
