@@ -512,6 +512,15 @@ def time_step6(P, device, flush, iters=20):
     crit = P.WeightedMSE()
 
     def step(multi):
+        if multi == "fused":   # one gradient buffer for the two full-resolution losses + the multi-scale launch
+            l01, _, _, _ = P.embedding_loss_norm5_self_and_cross(emb, ema, tgt, wgt, crit, affs0_weight=1)
+            ls = [r[0] for r in P.embedding_loss_norm1_multi(emds, [d[0] for d in downs], [d[1] for d in downs], crit)]
+            loss = l01 + ls[0] + ls[1] + ls[2] + ls[3]
+            loss.backward()
+            emb.grad = None
+            for e in emds:
+                e.grad = None
+            return loss
         l0, _ = P.embedding_loss_norm5(emb, tgt, wgt, crit, affs0_weight=1)
         l1, _ = P.ema_embedding_loss_norm5(emb, ema, tgt, wgt, crit, affs0_weight=1)
         if multi:
@@ -526,7 +535,7 @@ def time_step6(P, device, flush, iters=20):
         return loss
 
     out = {}
-    for name, multi in (("six_calls", False), ("multi", True)):
+    for name, multi in (("six_calls", False), ("multi", True), ("fused", "fused")):
         n_ours, _, n_all = count_launches(lambda: step(multi))
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -569,7 +578,7 @@ def time_step6(P, device, flush, iters=20):
             for e, (t, w) in zip(emds, downs):
                 lo = lo + n1(e.detach().cpu(), t.cpu(), w.cpu(), impl.WeightedMSE())[0]
         out["loss_cpu_" + kind] = float(lo)
-        out["parity_rel"] = abs(out["multi_loss"] - float(lo)) / abs(float(lo))
+        out["parity_rel"] = max(abs(out[k] - float(lo)) / abs(float(lo)) for k in ("multi_loss", "fused_loss"))
     except Exception as ex:  # noqa: BLE001
         out["parity_rel"] = f"not run ({type(ex).__name__}: {ex})"
     out["workload"] = f"six loss calls of one AC3/AC4 training step, B={B}: norm5 + two-view norm5 at 18x160x160, norm1 at 18x{{10,20,40,80}}^2"

@@ -67,6 +67,11 @@ extern "C" {
 /* Epilogue flag, or-ed into `impl` of pea_affs_fwd: store max(a, 0) -- the caller-side F.relu(pred) of
  * scripts_ac3ac4/inference.py:165, scripts_cvppp/main.py:312 folded into the kernel's store. */
 #define PEA_EPI_RELU 0x100
+/* Flag or-ed into `impl` of pea_affs_loss_fwd_bwd: grad_emb += d loss / d emb instead of grad_emb = ... -- the two losses of
+ * a training step that share an embedding (scripts_ac3ac4/main.py:223-224: embedding_loss_norm5, then
+ * ema_embedding_loss_norm5 on the same `embedding`) write ONE gradient buffer, instead of two buffers that autograd adds
+ * in a third pass.  Taken by the tiled two-view 3-D kernel only (12-offset set, partner != NULL, C = 16); PEA_E_MODE else. */
+#define PEA_EPI_GRAD_ACCUMULATE 0x200
 
 int pea_abi_version(void);
 const char* pea_strerror(int code);

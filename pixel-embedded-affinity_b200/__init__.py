@@ -11,7 +11,8 @@ from .loss_embedding_mse_2d import (embedding_loss, ema_embedding_loss, embeddin
                                     embedding_loss_multi)
 from .loss_embedding_mse_3d import (embedding_loss_norm1, embedding_loss_norm5, ema_embedding_loss_norm1,
                                     ema_embedding_loss_norm5, inf_embedding_loss_norm1, inf_embedding_loss_norm5,
-                                    embedding_loss_norm5_labels, embedding_loss_norm1_multi)
+                                    embedding_loss_norm5_labels, embedding_loss_norm1_multi,
+                                    embedding_loss_norm5_self_and_cross)
 from .affinity_ours import gen_offsets, multi_offset, gen_affs_ours
 from .data_affinity import mknhood3d, seg_to_aff
 from .data_segmentation import weight_binary_ratio

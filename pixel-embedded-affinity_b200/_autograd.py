@@ -147,6 +147,58 @@ class FusedAffinityLossLabels(torch.autograd.Function):
         return ge, None, None, None, None, None
 
 
+class FusedSelfAndCrossLoss(torch.autograd.Function):
+    """The two full-resolution losses of a training step that share one embedding (scripts_ac3ac4/main.py:223-224): the
+    one-view loss writes d/d embedding, the two-view loss (second view constant) ADDS its own into the same buffer
+    (PEA_EPI_GRAD_ACCUMULATE) -- one gradient buffer and no accumulation pass by autograd.  The differentiable output is
+    coef_self * L_self + coef_cross * L_cross (the coefficients are folded into the kernels' loss coefficients, so the
+    buffer already holds the gradient of that sum); the two parts come back as plain values."""
+
+    @staticmethod
+    def forward(ctx, emb, partner, target, weight, spec_self, spec_cross):
+        need = ctx.needs_input_grad[0]
+        lo_s, affs, grad, _ = ops.affs_loss_fwd_bwd(emb, None, spec_self.offs3, spec_self.border, target, weight, None,
+                                                    spec_self.loss_norm, spec_self.loss_coef, want_grad=need, impl=spec_self.impl)
+        try:
+            lo_c, affs_c, _, _ = ops.affs_loss_fwd_bwd(emb, partner, spec_cross.offs3, spec_cross.border, target, weight, None,
+                                                       spec_cross.loss_norm, spec_cross.loss_coef, want_grad=need,
+                                                       impl=spec_cross.impl, grad_into=grad if need else None)
+        except ops.PeaError as ex:  # shape the tiled two-view kernel does not take: separate buffer, one add
+            if ex.code != -8:
+                raise
+            lo_c, affs_c, gc, _ = ops.affs_loss_fwd_bwd(emb, partner, spec_cross.offs3, spec_cross.border, target, weight, None,
+                                                        spec_cross.loss_norm, spec_cross.loss_coef, want_grad=need,
+                                                        impl=spec_cross.impl)
+            if need:
+                grad.add_(gc)
+        ctx.need, ctx.grad_buf = need, grad
+        ctx.spec_self, ctx.spec_cross = spec_self, spec_cross
+        if need:
+            ctx.save_for_backward(emb, partner, target, weight)
+        ctx.set_materialize_grads(False)
+        total = lo_s[0] + lo_c[0]
+        ctx.mark_non_differentiable(affs, affs_c, lo_s, lo_c)
+        return total, affs, affs_c, lo_s, lo_c
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_total, *unused):
+        if not ctx.need or g_total is None:
+            return None, None, None, None, None, None
+        ge = ctx.grad_buf
+        if ge is None:  # handed out by an earlier backward (retain_graph=True): recompute both
+            emb, partner, target, weight = ctx.saved_tensors
+            ss, sc = ctx.spec_self, ctx.spec_cross
+            _, _, ge, _ = ops.affs_loss_fwd_bwd(emb, None, ss.offs3, ss.border, target, weight, None, ss.loss_norm, ss.loss_coef,
+                                                want_affs=False, want_grad=True, impl=ss.impl)
+            _, _, gc, _ = ops.affs_loss_fwd_bwd(emb, partner, sc.offs3, sc.border, target, weight, None, sc.loss_norm, sc.loss_coef,
+                                                want_affs=False, want_grad=True, impl=sc.impl)
+            ge.add_(gc)
+        ctx.grad_buf = None
+        ops.scale_inplace(ge, g_total.to(device=ge.device, dtype=torch.float32))
+        return ge, None, None, None, None, None
+
+
 class MultiFusedAffinityLoss(torch.autograd.Function):
     """n small fused losses in ONE launch (ops.affs_loss_multi) and their gradient scaling in ONE launch.
 

@@ -7,7 +7,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import lib, check, c_float_p, c_int32_p, LossProblem, MULTI_MAX_PROBLEMS, MULTI_MAX_OFFSETS
+from ._lib import lib, check, c_float_p, c_int32_p, LossProblem, MULTI_MAX_PROBLEMS, MULTI_MAX_OFFSETS, PeaError
 
 BORDER_WRAP, BORDER_ZERO = 0, 1
 MASK_NONE, MASK_U8, MASK_F32 = 0, 1, 2
@@ -194,9 +194,13 @@ def affs_fwd(emb, partner, offs3, border, impl=None, z_skip=0, out=None, halo=No
     return affs
 
 
+EPI_GRAD_ACCUMULATE = 0x200  # PEA_EPI_GRAD_ACCUMULATE
+
+
 def affs_loss_fwd_bwd(emb, partner, offs3, border, target, weight, mask, loss_norm, loss_coef, want_affs=True,
-                      want_grad=True, want_grad_partner=False, impl=IMPL_AUTO):
-    """One fused launch sequence.  Returns (loss_out (1+K,), affs or None, grad_emb or None, grad_partner or None)."""
+                      want_grad=True, want_grad_partner=False, impl=IMPL_AUTO, grad_into=None):
+    """One fused launch sequence.  Returns (loss_out (1+K,), affs or None, grad_emb or None, grad_partner or None).
+    ``grad_into``: an existing gradient buffer of emb's shape that this call ADDS to (PEA_EPI_GRAD_ACCUMULATE)."""
     B, C, D, H, W = _dims5(emb)
     K = offs3.shape[0]
     dev = emb.device
@@ -210,7 +214,12 @@ def affs_loss_fwd_bwd(emb, partner, offs3, border, target, weight, mask, loss_no
     else:
         raise TypeError(f"mask must be uint8 or float32 here, got {mask.dtype}")
     affs = torch.empty((B, K) + spatial, dtype=torch.float32, device=dev) if want_affs else None
-    grad = torch.empty_like(emb) if want_grad else None
+    if grad_into is not None:
+        if tuple(grad_into.shape) != tuple(emb.shape) or grad_into.dtype != torch.float32 or not grad_into.is_contiguous():
+            raise ValueError("grad_into must be a contiguous float32 tensor of the embedding's shape")
+        grad, impl = grad_into, impl | EPI_GRAD_ACCUMULATE
+    else:
+        grad = torch.empty_like(emb) if want_grad else None
     gpar = torch.empty_like(partner) if (want_grad_partner and partner is not None) else None
     loss_out = torch.empty(1 + K, dtype=torch.float32, device=dev)
     ws, n = _workspace(B, C, D, H, W, K, partner is not None, dev)

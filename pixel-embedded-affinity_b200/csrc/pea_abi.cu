@@ -61,7 +61,7 @@ int launch_axis2d(const float* emb, const float* partner, const Dims& d, const O
 
 int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab,
                          const float* target, const float* weight, float* affs, float* partials, float* grad,
-                         cudaStream_t st);
+                         int accumulate, cudaStream_t st);
 
 #ifndef PEA_PDL
 #define PEA_PDL 1  // 0: plain stream-ordered launches of the two tail kernels (A/B)
@@ -336,6 +336,8 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
                                      const float* loss_coef, float* affs, float* loss_out, float* grad_emb,
                                      float* grad_partner, void* workspace, size_t ws_bytes, void* stream) {
     if (!emb || !offsets || !target || !weight || !loss_norm || !loss_coef || !loss_out || !workspace) return PEA_E_NULL;
+    const int accumulate = (impl & PEA_EPI_GRAD_ACCUMULATE) ? 1 : 0;
+    impl &= ~PEA_EPI_GRAD_ACCUMULATE;
     if (impl != PEA_IMPL_AUTO && impl != PEA_IMPL_GENERIC && impl != PEA_IMPL_TILED) return PEA_E_MODE;
     Dims d;
     int rc = check_volume(B, C, D, H, W, K, d);
@@ -363,6 +365,8 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
                            grad_partner == nullptr;
     const bool tiled2_ok = tiled2d_eligible(C, D, H, W, tab, border == PEA_BORDER_WRAP, grad_partner != nullptr);
     if (impl == PEA_IMPL_TILED && !tiled3_ok && !tiled2_ok) return PEA_E_MODE;
+    // only the tiled two-view 3-D kernel adds into an existing gradient buffer
+    if (accumulate && !(tiled3_ok && cross && impl != PEA_IMPL_GENERIC && grad_emb)) return PEA_E_MODE;
     // canonical multi_offset(shifts <= 12, neighbor=4) table (one view, or two views with the second one constant):
     // fully unrolled persistent kernel.
     // PEA_KNOB_NO_CANON: test knob (pea_debug_configure) that sends these calls to the table-driven axis kernel.
@@ -404,7 +408,7 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         float* parts = ws.rinvE;
         const int nblk3 = cross ? cross3d_norm5_blocks(B, H, W) : fused3d_norm5_blocks(B, H, W);
         if (!partials_fit(nblk3, K, ws)) return PEA_E_WORKSPACE;
-        rc = cross ? launch_cross3d_norm5(emb, partner, d, tab, target, weight, affs, parts, grad_emb, st)
+        rc = cross ? launch_cross3d_norm5(emb, partner, d, tab, target, weight, affs, parts, grad_emb, accumulate, st)
                    : launch_fused3d_norm5(emb, d, tab, target, weight, affs, parts, grad_emb, st);
         if (rc) return rc;
         return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk3, K, sc, loss_out);

@@ -46,6 +46,8 @@ struct Params {
     float* partials;  // [gridDim.x][12]
     float gcoef[12];
     const float* wtab;  // label-driven flavour: [B][12][2] weight where the target is 1 / 0 (pea_gt_pair_weights)
+    int accumulate;     // two-view kernel: grad += instead of grad = (PEA_EPI_GRAD_ACCUMULATE: the one-view loss of the same
+                        // training step already wrote its gradient there)
 };
 
 
@@ -870,6 +872,9 @@ struct ParamsF {
 #ifndef PEA_K3_BLK
 #define PEA_K3_BLK 4
 #endif
+#ifndef PEA_K3_ROTSPREAD
+#define PEA_K3_ROTSPREAD 0  // 1: D - 3 starting slices instead of two phases (measured at 2 x 13 slices: 0.571 vs 0.563 ms, no gain)
+#endif
 #ifndef PEA_K3_STCS
 #define PEA_K3_STCS 0   // 1: affinities leave with st.global.cs (evict-first): write-once data does not displace the halos in L2
 #endif
@@ -936,7 +941,18 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
     // Odd CTAs therefore start with the part of the slab that needs no halo (slices 4 .. D-1, ring warmed up on the
     // slab's own first slices) and visit slices 0 .. 3 last: NVLink demand is spread over the whole kernel.
     const bool ext = P.halo != nullptr;
+#if PEA_K3_ROTSPREAD
+    // experiment (round 2): D - 3 different starting slices (0, i.e. halo first, or 4 .. D-1) dealt out by block index, so
+    // that the resident CTAs ask for their halo at D - 3 different points of their lifetime instead of two.  No gain:
+    // the link carries 268 MB in the time the slab takes either way
+    int rot = 0;
+    if (ext && zs == 0 && D > 4) {
+        const int j = (int)(blockIdx.x % (unsigned)(D - 3));
+        rot = j == 0 ? 0 : 3 + j;
+    }
+#else
     const int rot = (ext && zs == 0 && D > 4 && (blockIdx.x & 1)) ? 4 : 0;
+#endif
     const int nz = D - zs;
     auto slice_of = [&](int i) { const int r = i + rot; return zs + (r >= nz ? r - nz : r); };
     if (threadIdx.x == 0) {
@@ -996,7 +1012,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
         }
     };
     bool pending = true;  // raw halo values sit in the ring slots, to be normalised before the next z part
-    if (rot) warm_issue(P.emb, P.emb_plane, 4);                    // slices 0 .. 3 of the slab precede slice 4
+    if (rot) warm_issue(P.emb + (int64_t)(rot - 4) * HW, P.emb_plane, 4);   // slices rot-4 .. rot-1 of the slab precede slice rot
     else if (ext) warm_issue(P.halo, P.halo_plane, P.halo_n);
     else warm_issue(P.emb + (int64_t)(zs - (zs > 4 ? 4 : zs)) * HW, P.emb_plane, zs > 4 ? 4 : zs);
 
@@ -1524,12 +1540,25 @@ cross3d_norm5_tm(const __grid_constant__ CUtensorMap mapY, const __grid_constant
             if (!(rp < 1e12f)) eg = 0.f;
             const f32x2 neg = pack2(-eg, -eg), r2 = pack2(rp, rp);
             float* dst = grad_b + zoff;
+            if (P.accumulate) {  // CTA-uniform: add to what the one-view kernel left there (same thread, same address)
+                float prev[kC];
+#pragma unroll
+                for (int c = 0; c < kC; ++c) prev[c] = dst[(int64_t)c * N];
+#pragma unroll
+                for (int i = 0; i < kC2; ++i) {
+                    float lo, hi;
+                    unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
+                    dst[(int64_t)(2 * i) * N] = prev[2 * i] + lo;
+                    dst[(int64_t)(2 * i + 1) * N] = prev[2 * i + 1] + hi;
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < kC2; ++i) {
                 float lo, hi;
                 unpack2(mul2(fma2(e[i], neg, G[i]), r2), lo, hi);
                 dst[(int64_t)(2 * i) * N] = lo;
                 dst[(int64_t)(2 * i + 1) * N] = hi;
+            }
             }
         }
     }
@@ -1591,7 +1620,7 @@ int launch_fused3d_norm5_rf(const float* emb, const Dims& d, const OffsetTable& 
     if ((rc = encode_volume_map(&mW, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 12))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
-    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr; P.accumulate = 0;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
     const int grid = tiled3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::Stage<TY>) + 1024;
@@ -1645,7 +1674,7 @@ int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab
     if ((rc = encode_volume_map(&mW1, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 1))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
-    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr; P.accumulate = 0;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
     const int grid = fused3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::StageM<TY>) + 128;
@@ -1678,7 +1707,7 @@ int launch_fused3d_norm5_labels(const float* emb, const int32_t* seg, const floa
     if ((rc = encode_volume_map(&mLx, lab, d.B, 1, d.D, d.H, d.W, t3::XW, TY, 1, 1))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
-    P.target = nullptr; P.weight = nullptr; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = wtab;
+    P.target = nullptr; P.weight = nullptr; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = wtab; P.accumulate = 0;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
     const int grid = fused3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::StageM<TY>) + 128;
@@ -1739,7 +1768,7 @@ int cross3d_norm5_blocks(int B, int H, int W) { return B * ((H + kTileYX - 1) / 
 
 int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab,
                          const float* target, const float* weight, float* affs, float* partials, float* grad,
-                         cudaStream_t st) {
+                         int accumulate, cudaStream_t st) {
     constexpr int TY = kTileYX;
     if (reinterpret_cast<uintptr_t>(partner) & 15) return PEA_E_ALIGN;
     CUtensorMap mY, mA, mX, mO, mT, mW;
@@ -1752,7 +1781,7 @@ int launch_cross3d_norm5(const float* emb, const float* partner, const Dims& d, 
     if ((rc = encode_volume_map(&mW, weight, d.B, 12, d.D, d.H, d.W, t3::TX, TY, 1, 12))) return rc;
     t3::Params P;
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W;
-    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr;
+    P.target = target; P.weight = weight; P.affs = affs; P.grad = grad; P.partials = partials; P.wtab = nullptr; P.accumulate = (accumulate && grad) ? 1 : 0;
     for (int k = 0; k < 12; ++k) P.gcoef[k] = tab.gcoef[k];
     const int grid = cross3d_norm5_blocks(d.B, d.H, d.W);
     const size_t smem = sizeof(t3::StageX<TY>) + 1024;

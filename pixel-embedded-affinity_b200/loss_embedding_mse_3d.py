@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from . import _ops as ops
-from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, MultiFusedAffinityLoss, OpSpec
+from ._autograd import (Affinities, FusedAffinityLoss, FusedAffinityLossLabels, FusedSelfAndCrossLoss,
+                        MultiFusedAffinityLoss, OpSpec)
 from ._lib import PeaError
 from .loss import is_weighted_mse
 
@@ -122,6 +123,41 @@ def ema_embedding_loss_norm1(embedding, ema_embedding, target, weightmap, criter
                              fill=True):
     """:30-51"""
     return _loss3d(embedding, ema_embedding, target, weightmap, criterion, [shift] * 3, affs0_weight, 1)
+
+
+def embedding_loss_norm5_self_and_cross(embedding, ema_embedding, target, weightmap, criterion, affs0_weight=1,
+                                        coef_self=1.0, coef_cross=1.0):
+    """Training-step form of the two full-resolution calls of scripts_ac3ac4/main.py:223-224:
+
+        loss_embedding, pred  = embedding_loss_norm5(embedding, target, weightmap, criterion, affs0_weight)
+        loss_embedding_cross, _ = ema_embedding_loss_norm5(embedding, ema_embedding, target, weightmap, criterion, affs0_weight)
+        total = coef_self * loss_embedding + coef_cross * loss_embedding_cross
+
+    Returns (total, loss_embedding, pred, loss_embedding_cross); only ``total`` is differentiable (the parts are values).
+    Both kernels write ONE gradient buffer -- the two-view kernel adds into what the one-view kernel left
+    (PEA_EPI_GRAD_ACCUMULATE) -- so autograd does not accumulate two (B,16,D,H,W) gradients in a third pass; the second
+    view is a constant, as in both shipped training loops.  Other criteria / shapes: the two calls above."""
+    if not is_weighted_mse(criterion):
+        l0, pred = embedding_loss_norm5(embedding, target, weightmap, criterion, affs0_weight)
+        l1, _ = ema_embedding_loss_norm5(embedding, ema_embedding, target, weightmap, criterion, affs0_weight)
+        return coef_self * l0 + coef_cross * l1, l0.detach(), pred, l1.detach()
+    embedding = ops.check_embedding("embedding", embedding, 5)
+    ema_embedding = ops.check_embedding("ema_embedding", ema_embedding, 5).detach()
+    if ema_embedding.shape != embedding.shape:
+        raise ValueError("ema_embedding and embedding shapes differ")
+    B, C, D, H, W = embedding.shape
+    target = ops.check_like("target", target, (B, 12, D, H, W))
+    weightmap = ops.check_like("weightmap", weightmap, (B, 12, D, H, W))
+    offs3 = offsets_from_shifts(SHIFTS_NORM5)
+    norms = _norms_3d(embedding.shape, SHIFTS_NORM5)
+    coef = np.ones(12, np.float32)
+    coef[:3] = affs0_weight
+    spec_s = OpSpec(offs3, ops.BORDER_ZERO, norms, coef * np.float32(coef_self), affs_differentiable=False)
+    spec_c = OpSpec(offs3, ops.BORDER_ZERO, norms, coef * np.float32(coef_cross), affs_differentiable=False)
+    total, pred, _, lo_s, lo_c = FusedSelfAndCrossLoss.apply(embedding, ema_embedding, target, weightmap, spec_s, spec_c)
+    # loss_out[0] carries the scaled sum; the unscaled parts are sum_k coef_k * loss_k with the caller's affs0_weight
+    cw = torch.as_tensor(coef, device=embedding.device)
+    return total, (lo_s[1:] * cw).sum(), pred, (lo_c[1:] * cw).sum()
 
 
 def _inf3d(embedding, shifts, z_skip=0, out=None, halo=None, relu=False, replicate_border=False):

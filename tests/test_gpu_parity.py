@@ -1306,3 +1306,32 @@ def test_multi_and_flip_write_only_their_outputs(P, O):
     torch.cuda.synchronize()
     assert bool((ob[:PAD] == POISON).all()) and bool((ob[PAD + out.numel():] == POISON).all()), "flip: guard band overwritten"
     assert torch.equal(out.cpu(), O.convert_consistency_flip(x.cpu(), rules.cpu()))
+
+
+@pytest.mark.parametrize("B,D,H,W", [(2, 7, 33, 44), (1, 18, 40, 36)])
+def test_self_and_cross_share_one_gradient_buffer(P, O, B, D, H, W):
+    """embedding_loss_norm5_self_and_cross == embedding_loss_norm5 + ema_embedding_loss_norm5 on the same embedding
+    (scripts_ac3ac4/main.py:223-224): the two-view kernel ADDS into the one-view kernel's gradient buffer
+    (PEA_EPI_GRAD_ACCUMULATE).  Against the oracle's two calls: parts, prediction, total, gradient; an upstream scalar."""
+    emb, ema, tgt, wgt = _inputs_3d(O, B, 16, D, H, W, 12, 77)
+    eo = torch.tensor(emb, requires_grad=True)
+    l0, pred_o = O.embedding_loss_norm5(eo, torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(), affs0_weight=2)
+    l1, _ = O.ema_embedding_loss_norm5(eo, torch.tensor(ema), torch.tensor(tgt), torch.tensor(wgt), O.WeightedMSE(), affs0_weight=2)
+    (3.0 * (0.7 * l0 + 1.3 * l1)).backward()
+    e = dev(emb, True)
+    total, ls, pred, lc = P.embedding_loss_norm5_self_and_cross(e, dev(ema), dev(tgt), dev(wgt), P.WeightedMSE(), affs0_weight=2,
+                                                                coef_self=0.7, coef_cross=1.3)
+    (3.0 * total).backward()
+    close_s(ls, l0, what="one-view part")
+    close_s(lc, l1, what="two-view part")
+    close_s(total, 0.7 * float(l0) + 1.3 * float(l1), what="total")
+    close_t(pred, pred_o, what="prediction")
+    close_t(e.grad, eo.grad, what="shared gradient buffer")
+    assert not pred.requires_grad and not ls.requires_grad
+    # the ABI flag is refused where no kernel implements it
+    from pea_b200 import _ops as ops
+    from pea_b200.loss_embedding_mse_3d import offsets_from_shifts
+    with pytest.raises(ops.PeaError):
+        ops.affs_loss_fwd_bwd(dev(emb), None, offsets_from_shifts([1, 1, 1]), ops.BORDER_ZERO, dev(tgt)[:, :3].contiguous(),
+                              dev(wgt)[:, :3].contiguous(), None, np.ones(3, np.float32), np.ones(3, np.float32),
+                              grad_into=torch.zeros_like(dev(emb)))
