@@ -57,9 +57,19 @@ class LossList(collections.abc.Sequence):
         return self._dev
 
 
+def _refuse_grad(ctx, first, names):
+    """The fused functions differentiate with respect to the embeddings only; the reference's torch ops would also
+    propagate into target / weightmap / mask.  Nobody trains those, but a silent None would be wrong: refuse loudly."""
+    for i, n in enumerate(names):
+        if ctx.needs_input_grad[first + i]:
+            raise RuntimeError(f"pea_b200: {n} requires grad, but the fused affinity loss is differentiable with respect to "
+                               "the embeddings only (detach it, or use a criterion other than WeightedMSE)")
+
+
 class FusedAffinityLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb, partner, target, weight, mask, spec):
+        _refuse_grad(ctx, 2, ("target", "weightmap", "mask"))
         need_e = ctx.needs_input_grad[0]
         need_u = partner is not None and ctx.needs_input_grad[1]
         loss_out, affs, grad, gpar = ops.affs_loss_fwd_bwd(
@@ -156,6 +166,7 @@ class FusedSelfAndCrossLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, emb, partner, target, weight, spec_self, spec_cross):
+        _refuse_grad(ctx, 1, ("ema_embedding", "target", "weightmap"))
         need = ctx.needs_input_grad[0]
         lo_s, affs, grad, _ = ops.affs_loss_fwd_bwd(emb, None, spec_self.offs3, spec_self.border, target, weight, None,
                                                     spec_self.loss_norm, spec_self.loss_coef, want_grad=need, impl=spec_self.impl)
@@ -208,6 +219,7 @@ class MultiFusedAffinityLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, specs, n, *tensors):
         embs, pars, tgts, wgts, msks = (tensors[i * n:(i + 1) * n] for i in range(5))
+        _refuse_grad(ctx, 2 + n, ["ema_embedding"] * n + ["target"] * n + ["weightmap"] * n + ["mask"] * n)
         need = [ctx.needs_input_grad[2 + i] for i in range(n)]
         problems = [dict(emb=embs[i], partner=pars[i], offs3=specs[i].offs3, border=specs[i].border, target=tgts[i],
                          weight=wgts[i], mask=msks[i], loss_norm=specs[i].loss_norm, loss_coef=specs[i].loss_coef,

@@ -155,9 +155,13 @@ def embedding_loss_norm5_self_and_cross(embedding, ema_embedding, target, weight
     spec_s = OpSpec(offs3, ops.BORDER_ZERO, norms, coef * np.float32(coef_self), affs_differentiable=False)
     spec_c = OpSpec(offs3, ops.BORDER_ZERO, norms, coef * np.float32(coef_cross), affs_differentiable=False)
     total, pred, _, lo_s, lo_c = FusedSelfAndCrossLoss.apply(embedding, ema_embedding, target, weightmap, spec_s, spec_c)
-    # loss_out[0] carries the scaled sum; the unscaled parts are sum_k coef_k * loss_k with the caller's affs0_weight
-    cw = torch.as_tensor(coef, device=embedding.device)
-    return total, (lo_s[1:] * cw).sum(), pred, (lo_c[1:] * cw).sum()
+    # loss_out[0] of each kernel carries coef_self / coef_cross times the loss the reference's call returns
+
+    def part(lo, c):
+        if c != 0:
+            return lo[0] / float(c)   # no host -> device copy: stays CUDA-graph capturable
+        return sum(lo[1 + k] * float(coef[k]) for k in range(12))
+    return total, part(lo_s, coef_self), pred, part(lo_c, coef_cross)
 
 
 def _inf3d(embedding, shifts, z_skip=0, out=None, halo=None, relu=False, replicate_border=False):
