@@ -1084,10 +1084,12 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             const float az = hsum2(d0, d1);
             if (live) st_out(out + (int64_t)(3 * (j - 1)) * P.affs_plane, (z + zprev >= j) ? (P.relu ? fmaxf(az, 0.f) : az) : 0.f);
         }
+#ifndef PEA_K3_NOSHIFT  // timing experiment only (wrong results): what the ring shift costs
 #pragma unroll
         for (int s = 4; s >= 1; --s)
 #pragma unroll
             for (int i = 0; i < kC2; ++i) re[s][i] = re[s - 1][i];
+#endif
     }
 }
 
