@@ -1754,6 +1754,8 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
     P.halo = halo; P.halo_n = halo_n; P.halo_plane = halo_plane; P.relu = relu;
     const int grid = d.B * ((d.H + TY - 1) / TY) * ((d.W + t3::TX - 1) / t3::TX);
     const size_t smem = sizeof(t3::StageF<TY>) + 1024;
+    // (round 2 measured a Tensor-Memory ring + halo prefetch for this kernel as well: bit-identical, but 4.11 ms against
+    // 3.70 ms -- four dependent tcgen05.ld per slice cost more than the register ring's moves)
     auto kern = t3::fwd3d_norm5<TY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
