@@ -850,6 +850,48 @@ def time_inference_epilogue(P, device, shape=(100, 1024, 1024), iters=5):
     return out
 
 
+def time_reference_on_gpu(P, w, device, flush, iters=10):
+    """The reference's OWN loss function (the unmodified files under baseline/_ref, else the oracle port: the same torch
+    ops) running as eager PyTorch ops on this GPU, forward + backward on the workload's batch -- the implementation a user
+    of the reference has today on the same hardware.  L2 flushed between steps like the headline."""
+    O, kind = cpu_impl()
+    lab, emb, tgt, wgt, msk, offsets = device_inputs(P, w, 0, device)
+    e = emb.clone().requires_grad_(True)
+    crit = O.WeightedMSE()
+
+    def step():
+        if w["nd"] == 2:
+            loss, _, _ = O.embedding_loss(e, tgt, wgt, msk, crit, offsets)
+        else:
+            loss, _ = O.embedding_loss_norm5(e, tgt, wgt, crit)
+        loss.backward()
+        e.grad = None
+        return loss
+    for _ in range(3):
+        loss = step()
+    torch.cuda.synchronize()
+    per = []
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = step()
+        b.record()
+        torch.cuda.synchronize()
+        per.append(a.elapsed_time(b))
+    n_all = None
+    try:
+        _, _, n_all = count_launches(step)
+    except Exception:  # noqa: BLE001
+        pass
+    ms = statistics.median(per)
+    K = 12 if w["nd"] == 3 else 2 * len(w["shifts"])
+    vox = w["B"] * K * int(np.prod(w["spatial"]))
+    return {"what": "the reference's loss function as eager torch ops on this GPU, fwd+bwd, same batch", "kind": kind,
+            "ms_per_step": ms, "value": vox / (ms * 1e-3), "unit": UNIT, "kernel_launches_per_step": n_all,
+            "loss": float(loss.detach())}
+
+
 def cpu_baseline(w, seconds=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -1040,6 +1082,13 @@ def run_ours(args, rank, world, local_rank):
             also["cfg1_labels"] = time_labels_pipeline(P, WORKLOADS["cfg1"], device, flush)   # CVPPP table: axis kernel's label flavour
             also["cfg1_labels"]["roofline_frac"] = also["cfg1_labels"]["hbm_gbs"] / peak
             also["step6"] = time_step6(P, device, flush)
+            torch.cuda.empty_cache()
+            try:  # context line: what the reference itself does on this GPU (same batch, eager torch ops)
+                also["reference_on_gpu"] = time_reference_on_gpu(P, w, device, flush)
+                also["reference_on_gpu"]["ours_ms_per_step"] = ms_step
+                also["reference_on_gpu"]["speedup"] = also["reference_on_gpu"]["ms_per_step"] / ms_step
+            except Exception as ex:  # noqa: BLE001
+                also["reference_on_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
             torch.cuda.empty_cache()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -83,7 +83,8 @@ const char* pea_strerror(int code);
 #define PEA_KNOB_NO_CANON 0
 #define PEA_KNOB_MAX_CTAS 1
 #define PEA_KNOB_TUNE_TY2D 2
-#define PEA_KNOB_COUNT 3
+#define PEA_KNOB_GT_TWO_PASS 3 /* != 0: pea_gt_targets takes its two-launch route (count + write) instead of the one-launch one */
+#define PEA_KNOB_COUNT 4
 int pea_debug_configure(int knob, int value);
 
 /* Bytes of device workspace the affinity entry points need for a problem of this size.

@@ -1062,6 +1062,53 @@ def test_fused_batch_gt_matches_oracle(P, O):
             same(wgt[b], np.stack([O.weight_binary_ratio(c) for c in to]), "3D weight")
 
 
+@pytest.mark.parametrize("route", ["one_launch", "two_launch"])
+def test_fused_batch_gt_routes_bit_identical(P, O, route):
+    """pea_gt_targets has two routes: ONE cooperative launch (pass 1 parks its 4-bit results in shared memory, every
+    sample has a completion counter, pass 2 expands the bits into weights) and the two-launch route (count + write,
+    PEA_KNOB_GT_TWO_PASS) that volumes too large to be resident at once take.  Both against the oracle, bit for bit:
+    8-bit labels (packed-byte path) and wider ones, rows that are / are not a multiple of eight voxels, samples
+    whose channels are uniform, many slices per block (B = 5 samples of 96 x 136), replayed from a CUDA graph."""
+    KNOB_GT_TWO_PASS = 3
+    _knob(KNOB_GT_TWO_PASS, 1 if route == "two_launch" else 0)
+    try:
+        offsets = O.multi_offset([1, 3, 5, 9, 11], neighbor=4)
+        for (B, H, W, dt) in ((5, 96, 136, np.uint8), (2, 52, 68, np.uint8), (3, 40, 64, np.int16), (2, 33, 36, np.int32)):
+            labs = np.stack([O.voronoi_labels((H, W), 9, 500 + b, background_frac=0.3, dtype=np.uint8) for b in range(B)]).astype(dt)
+            labs[B - 1] = 0
+            lab_d = torch.tensor(labs).cuda()
+            for ignore in (False, True):
+                tgt, msk, wgt = P.make_targets_2d(lab_d, offsets, ignore=ignore, padding=True)
+                for b in range(B):
+                    to, mo = O.gen_affs_ours(labs[b], offsets, ignore=ignore, padding=True)
+                    same(tgt[b], to, f"2D target {route} {dt.__name__} {H}x{W}")
+                    same(msk[b], mo, "2D mask")
+                    same(wgt[b], np.stack([O.weight_binary_ratio(c) for c in to]), "2D weight")
+        segs = np.stack([O.voronoi_labels((10, 40, 48), 14, 600 + b, z_scale=3.0, dtype=np.uint16) for b in range(3)])
+        for dt in (np.int32, np.uint8):
+            seg_d = torch.tensor((segs % 200).astype(dt)).cuda()
+            tgt, wgt = P.make_targets_3d(seg_d)
+            for b in range(3):
+                to = O.seg_to_aff_norm5((segs[b] % 200).astype(dt))
+                same(tgt[b], to, f"3D target {route} {dt.__name__}")
+                same(wgt[b], np.stack([O.weight_binary_ratio(c) for c in to]), "3D weight")
+        # captured and replayed: the counters behind the counts are zeroed by the captured memset every time
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            P.make_targets_3d(seg_d)
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(g):
+            t2, w2 = P.make_targets_3d(seg_d)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(t2, tgt) and torch.equal(w2, wgt), "graph replay differs"
+    finally:
+        _knob(KNOB_GT_TWO_PASS, 0)
+
+
 # =========================================================================== several small losses in one launch
 def test_norm1_multi_matches_single_calls_and_oracle(P, O):
     """embedding_loss_norm1_multi (ONE launch for the four deep-supervision scales, scripts_ac3ac4/main.py:227-230)
