@@ -263,10 +263,13 @@ __device__ __forceinline__ uint32_t gt_group(const L* __restrict__ s, bool bytes
         return eq;
     }
     if (m != 0u) {
+        // a row end: branch-free -- a pair outside the row reads the voxel itself (always a valid address) and is masked out
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            if (m & (1u << j)) eq |= gt_same<L, MODE>(q.here[j], __ldg(s + (nb + j)), ignore) ? (1u << j) : 0u;
+            const L there = __ldg(s + (((m >> j) & 1u) ? (uint32_t)(nb + j) : p + (uint32_t)j));
+            eq |= gt_same<L, MODE>(q.here[j], there, ignore) ? (1u << j) : 0u;
         }
+        eq &= m;
     }
     return eq | ((MODE == 0 && padding) ? (~m & FULL) : 0u);
 }
@@ -543,8 +546,9 @@ template <typename L, int MODE, int NV>
 static int run_gt_weights_nv(const void* labels, int B, int D, int H, int W, const GtTable& tab, int ignore, int padding,
                              double alpha, float* wtab, unsigned long long* counts, cudaStream_t st) {
     const int64_t N = (int64_t)D * H * W;
+    // counting only: no stores to amortise, so one group per thread and every SM full (8 blocks of 256 threads each)
     int64_t chunks = (148 * 8 + B - 1) / B;
-    const int64_t max_chunks = (N / NV + 1023) / 1024;
+    const int64_t max_chunks = (N / NV + 255) / 256;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)B * tab.K * sizeof(unsigned long long), st);
