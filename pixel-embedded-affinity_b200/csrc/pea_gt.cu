@@ -366,28 +366,37 @@ gt_fused_x4(const L* __restrict__ labels, int D, int H, int W, GtTable tab, int 
 }
 
 // One-launch route (cooperative launch: every block resident).  Work = slices of blockDim.x groups of NV voxels, dealt
-// round-robin to the blocks; a block runs pass 1 on all its slices (target + mask stores, counts, and the NV-bit results
-// parked in shared memory), then pass 2 on the same slices in the same order: it waits until every slice of the
-// slice's SAMPLE has been counted (one completion counter per sample, behind the counts) and expands the parked bits
-// into weights.  By the time a block has finished pass 1 of its last slice, the samples of its first slices are long
-// complete: no grid-wide barrier, no idle memory pipe, no second round of compares.
+// round-robin to the blocks.  A block
+//   1. COUNTS all its slices: compares only, the NV result bits (and the NV validity bits of the mask) of every
+//      (slice, offset, thread) parked in shared memory, counts -> global atomics, one completion counter per SAMPLE;
+//   2a. streams target (+ mask) of the same slices out of the parked bits -- nothing here depends on the counts, so this
+//      phase hides the wait for the other blocks;
+//   2b. per slice, waits until every slice of the slice's sample has been counted and streams the weights.
+// The store phases re-deal the parked bits so that consecutive lanes own consecutive quads whatever NV is: every 128-bit
+// store instruction of a warp covers 512 contiguous bytes.  No grid-wide barrier, no second round of compares, and the
+// store phases run at the pace of the memory system (about 20 instructions per offset and quad).
 template <typename L, int MODE, int NV>
 __global__ void __launch_bounds__(256)
 gt_fused_one(const L* __restrict__ labels, int B, int D, int H, int W, GtTable tab, int ignore, int padding, double alpha,
              float* __restrict__ target, uint8_t* __restrict__ mask, unsigned long long* __restrict__ counts,
-             float* __restrict__ weight, unsigned int sps, unsigned int n_slices) {
-    extern __shared__ uint8_t s_bits[];  // [slice of the block][k][thread]
+             float* __restrict__ weight, unsigned int sps, unsigned int n_slices, unsigned int its) {
+    constexpr uint32_t Q = NV / 4;  // quads per thread in phase 1
+    extern __shared__ uint8_t s_park[];  // [slice of the block][k][thread]: result bits, then (2-D) validity bits
     __shared__ unsigned int s_cnt[8][PEA_MAX_OFFSETS];
     __shared__ float s_pos[PEA_MAX_OFFSETS], s_neg[PEA_MAX_OFFSETS];
     const int K = tab.K;
-    const uint32_t HW = (uint32_t)H * W, N = HW * (uint32_t)D, NG = N / NV;
+    const uint32_t HW = (uint32_t)H * W, N = HW * (uint32_t)D, NG = N / NV, T = blockDim.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool with_mask = MODE == 0 && mask != nullptr;
+    uint8_t* s_bits = s_park;
+    uint8_t* s_inb = s_park + (size_t)its * K * T;
     unsigned int* done = reinterpret_cast<unsigned int*>(counts + (int64_t)B * K);  // [B], zeroed with the counts
-    for (int i = threadIdx.x; i < 8 * PEA_MAX_OFFSETS; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 8 * PEA_MAX_OFFSETS; i += T) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
+    // ---- 1: count
     uint32_t it = 0;
     for (uint32_t sl = blockIdx.x; sl < n_slices; sl += gridDim.x, ++it) {
-        const uint32_t b = sl / sps, gd = (sl - b * sps) * blockDim.x + threadIdx.x;
+        const uint32_t b = sl / sps, gd = (sl - b * sps) * T + threadIdx.x;
         const bool live = gd < NG;
         const uint32_t p = (live ? gd : 0u) * NV;
         const int z = (int)(p / HW);
@@ -395,8 +404,6 @@ gt_fused_one(const L* __restrict__ labels, int B, int D, int H, int W, GtTable t
         const int y = (int)(r / (uint32_t)W), x = (int)(r - (uint32_t)y * W);
         const L* s = labels + (int64_t)b * N;
         const bool bytes4 = sizeof(L) == 1 && (L)(-1) > (L)0 && (reinterpret_cast<uintptr_t>(s) & 3) == 0;
-        float* out = target + (int64_t)b * K * N;
-        uint8_t* mout = (MODE == 0 && mask) ? mask + (int64_t)b * K * N : nullptr;
         Own<L, NV> q;
         load_own(s, bytes4, p, q);
 #pragma unroll kGtUnroll
@@ -405,17 +412,11 @@ gt_fused_one(const L* __restrict__ labels, int B, int D, int H, int W, GtTable t
             uint32_t inb;
             const uint32_t bits = gt_group<L, MODE, NV>(s, bytes4, q, p, z, y, x, dz, dy, dx, dz * (int32_t)HW + dy * W + dx, D, H,
                                                         W, ignore, padding, inb);
-            const uint32_t o = (uint32_t)k * N + p;
-            if (live) {
-#pragma unroll
-                for (int i = 0; i < NV / 4; ++i) {
-                    *reinterpret_cast<float4*>(out + o + 4 * i) = quad_values(bits >> (4 * i), 1.f, 0.f);
-                    if (mout) *reinterpret_cast<uint32_t*>(mout + o + 4 * i) = quad_bytes(inb >> (4 * i));
-                }
-            }
             const unsigned int tot = __reduce_add_sync(0xffffffffu, live ? (unsigned)__popc(bits) : 0u);
             if (lane == 0) atomicAdd(&s_cnt[warp][k], tot);
-            s_bits[(it * (uint32_t)K + (uint32_t)k) * blockDim.x + threadIdx.x] = (uint8_t)bits;
+            const uint32_t slot = (it * (uint32_t)K + (uint32_t)k) * T + threadIdx.x;
+            s_bits[slot] = (uint8_t)bits;
+            if (with_mask) s_inb[slot] = (uint8_t)inb;
         }
         __syncthreads();
         if ((int)threadIdx.x < K) {
@@ -432,9 +433,33 @@ gt_fused_one(const L* __restrict__ labels, int B, int D, int H, int W, GtTable t
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(done + b, 1u);
     }
+    // the parked byte of thread g / Q holds quad g % Q of its group: lane -> consecutive quads
+    const uint32_t sub = threadIdx.x / Q, qsel = 4u * (threadIdx.x % Q);
+    // ---- 2a: target (+ mask)
     it = 0;
     for (uint32_t sl = blockIdx.x; sl < n_slices; sl += gridDim.x, ++it) {
-        const uint32_t b = sl / sps, gd = (sl - b * sps) * blockDim.x + threadIdx.x;
+        const uint32_t b = sl / sps, g0 = (sl - b * sps) * T;
+        float* tout = target + (int64_t)b * K * N;
+        uint8_t* mout = with_mask ? mask + (int64_t)b * K * N : nullptr;
+#pragma unroll
+        for (uint32_t h = 0; h < Q; ++h) {
+            const uint32_t g = h * (T / Q) + sub;  // thread whose byte this lane expands
+            const uint32_t gd = g0 + g;
+            if (gd < NG) {
+                const uint32_t px = gd * NV + qsel;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t slot = (it * (uint32_t)K + (uint32_t)k) * T + g;
+                    *reinterpret_cast<float4*>(tout + ((uint32_t)k * N + px)) = quad_values((uint32_t)s_bits[slot] >> qsel, 1.f, 0.f);
+                    if (with_mask) *reinterpret_cast<uint32_t*>(mout + ((uint32_t)k * N + px)) = quad_bytes((uint32_t)s_inb[slot] >> qsel);
+                }
+            }
+        }
+    }
+    // ---- 2b: weights, sample by sample
+    it = 0;
+    for (uint32_t sl = blockIdx.x; sl < n_slices; sl += gridDim.x, ++it) {
+        const uint32_t b = sl / sps, g0 = (sl - b * sps) * T;
         if (threadIdx.x == 0) {
             unsigned int seen;
             do {
@@ -444,31 +469,31 @@ gt_fused_one(const L* __restrict__ labels, int B, int D, int H, int W, GtTable t
         __syncthreads();
         if ((int)threadIdx.x < K) pair_weights(__ldcg(counts + (int64_t)b * K + threadIdx.x), N, alpha, s_pos[threadIdx.x], s_neg[threadIdx.x]);
         __syncthreads();
-        if (gd < NG) {
-            float* wout = weight + (int64_t)b * K * N + gd * NV;
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                const uint32_t bits = s_bits[(it * (uint32_t)K + (uint32_t)k) * blockDim.x + threadIdx.x];
+        float* wout = weight + (int64_t)b * K * N;
 #pragma unroll
-                for (int i = 0; i < NV / 4; ++i)
-                    *reinterpret_cast<float4*>(wout + (uint32_t)k * N + 4 * i) = quad_values(bits >> (4 * i), s_pos[k], s_neg[k]);
+        for (uint32_t h = 0; h < Q; ++h) {
+            const uint32_t g = h * (T / Q) + sub;
+            const uint32_t gd = g0 + g;
+            if (gd < NG) {
+                const uint32_t px = gd * NV + qsel;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t bits = (uint32_t)s_bits[(it * (uint32_t)K + (uint32_t)k) * T + g] >> qsel;
+                    *reinterpret_cast<float4*>(wout + ((uint32_t)k * N + px)) = quad_values(bits, s_pos[k], s_neg[k]);
+                }
             }
         }
         __syncthreads();  // s_pos / s_neg are rewritten for the next slice
     }
 }
 
-constexpr int kGtOneMaxBytes = 64 * 256;  // shared memory of the one-launch route: (slices per block) * K * threads
+constexpr int kGtOneMaxBytes = 24 * 1024;  // parked bits of the one-launch route: (slices per block) * K * threads (* 2 with a mask)
 
 template <typename L, int MODE, int NV>
 static int run_gt_fused_nv(const void* labels, int B, int D, int H, int W, const GtTable& tab, int ignore, int padding,
                            double alpha, float* target, uint8_t* mask, float* weight, unsigned long long* counts,
                            cudaStream_t st) {
     const int64_t N = (int64_t)D * H * W;
-    int64_t chunks = (148 * 8 + B - 1) / B;
-    const int64_t max_chunks = (N / NV + 1023) / 1024;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
     // counts + the per-sample completion counters of the one-launch route
     cudaError_t e = cudaMemsetAsync(counts, 0, pea_gt_counts_bytes(B, tab.K), st);
     if (e != cudaSuccess) return (int)e;
@@ -478,6 +503,7 @@ static int run_gt_fused_nv(const void* labels, int B, int D, int H, int W, const
         auto kern = gt_fused_one<L, MODE, NV>;
         int dev = 0, sms = 0, coop = 0;
         const int64_t NG = N / NV;
+        const int planes = (MODE == 0 && mask) ? 2 : 1;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop && sms > 0) {
             // every block gets the SAME number of slices (a block that finishes early only waits for the others at its
@@ -488,9 +514,11 @@ static int run_gt_fused_nv(const void* labels, int B, int D, int H, int W, const
             for (int thr = 256; thr >= 128; thr >>= 1) {
                 const int64_t sps = (NG + thr - 1) / thr, n_slices = sps * B;
                 if (n_slices >= ((int64_t)1 << 31)) continue;
-                for (int its = 1; its * tab.K * thr <= kGtOneMaxBytes; ++its) {
+                for (int its = 1; its * tab.K * thr * planes <= kGtOneMaxBytes; ++its) {
                     int per_sm = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, thr, (size_t)its * tab.K * thr) != cudaSuccess || per_sm < 1) break;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, thr, (size_t)its * tab.K * thr * planes) != cudaSuccess ||
+                        per_sm < 1)
+                        break;
                     const int64_t grid = (n_slices + its - 1) / its;
                     if (grid > (int64_t)per_sm * sms) continue;
                     const int64_t worst = (grid + sms - 1) / sms;  // blocks on the fullest SM
@@ -503,30 +531,43 @@ static int run_gt_fused_nv(const void* labels, int B, int D, int H, int W, const
             if (best_thr) {
                 const int64_t sps = (NG + best_thr - 1) / best_thr;
                 int B_ = B, D_ = D, H_ = H, W_ = W, ig = ignore, pad = padding;
-                unsigned int sps_ = (unsigned)sps, ns_ = (unsigned)(sps * B);
+                unsigned int sps_ = (unsigned)sps, ns_ = (unsigned)(sps * B), its_ = (unsigned)best_its;
                 GtTable t2 = tab;
-                void* args[] = {(void*)&lab, &B_, &D_, &H_, &W_, &t2, &ig, &pad, &alpha, &target, &mask, &counts, &weight, &sps_, &ns_};
+                void* args[] = {(void*)&lab, &B_, &D_, &H_, &W_, &t2, &ig, &pad, &alpha, &target, &mask, &counts, &weight, &sps_, &ns_, &its_};
                 e = cudaLaunchCooperativeKernel((const void*)kern, dim3(best_grid), dim3(best_thr), args,
-                                                (size_t)best_its * tab.K * best_thr, st);
+                                                (size_t)best_its * tab.K * best_thr * planes, st);
                 if (e == cudaSuccess) return 0;
                 (void)cudaGetLastError();  // not launchable as a cooperative grid here: the two-launch route below
             }
         }
     }
-    dim3 grid((unsigned)chunks, (unsigned)B);
-    gt_fused_x4<L, MODE, 1, NV><<<grid, 256, 0, st>>>(lab, D, H, W, tab, ignore, padding, alpha, target, mask, counts, weight);
-    gt_fused_x4<L, MODE, 2, NV><<<grid, 256, 0, st>>>(lab, D, H, W, tab, ignore, padding, alpha, target, mask, counts, weight);
-    return (int)cudaGetLastError();
+    return -1000;  // the caller takes the two-launch route
 }
 
-// Four voxels per thread: a warp's 128-bit stores then cover 512 contiguous bytes of a plane.  Eight per thread
-// (instantiable: NV = 8 when W % 8 == 0) halves the per-offset address / validity work but leaves every store instruction
-// with half-filled 32-byte sectors: measured 77.6 us against 61.6 us at B = 8, 520 x 696, K = 10.
+// One launch: eight voxels per thread in the counting phase when the rows allow it (the store phases are re-dealt quad
+// by quad either way).  Two launches (volumes too large to be resident at once, or no cooperative launch): four voxels
+// per thread -- eight would leave every 128-bit store instruction with half-filled 32-byte sectors (measured 77.6 us
+// against 61.6 us at B = 8, 520 x 696, K = 10 when the stores sat in the counting loop).
 template <typename L, int MODE>
 static int run_gt_fused(const void* labels, int B, int D, int H, int W, const GtTable& tab, int ignore, int padding,
                         double alpha, float* target, uint8_t* mask, float* weight, unsigned long long* counts,
                         cudaStream_t st) {
-    return run_gt_fused_nv<L, MODE, 4>(labels, B, D, H, W, tab, ignore, padding, alpha, target, mask, weight, counts, st);
+    int rc;
+    if (W % 8 == 0 && sizeof(L) <= 4)
+        rc = run_gt_fused_nv<L, MODE, 8>(labels, B, D, H, W, tab, ignore, padding, alpha, target, mask, weight, counts, st);
+    else
+        rc = run_gt_fused_nv<L, MODE, 4>(labels, B, D, H, W, tab, ignore, padding, alpha, target, mask, weight, counts, st);
+    if (rc != -1000) return rc;
+    const int64_t N = (int64_t)D * H * W;
+    int64_t chunks = (148 * 8 + B - 1) / B;
+    const int64_t max_chunks = (N / 4 + 1023) / 1024;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    const L* lab = static_cast<const L*>(labels);
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    gt_fused_x4<L, MODE, 1, 4><<<grid, 256, 0, st>>>(lab, D, H, W, tab, ignore, padding, alpha, target, mask, counts, weight);
+    gt_fused_x4<L, MODE, 2, 4><<<grid, 256, 0, st>>>(lab, D, H, W, tab, ignore, padding, alpha, target, mask, counts, weight);
+    return (int)cudaGetLastError();
 }
 
 // per-(sample, channel) counts -> the two values of the class-balance weight map: wtab[2 i] where the target is 1,
