@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PEA_ABI_VERSION 5
+#define PEA_ABI_VERSION 6
 #define PEA_MAX_OFFSETS 64
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -79,11 +79,12 @@ const char* pea_strerror(int code);
 /* TEST-ONLY: dispatch knobs of the parity tests (process-wide, 0 = production behaviour; the only mutable state in the
  * library, written by nothing but this call).  PEA_KNOB_NO_CANON != 0: the canonical 2-D tables take the table-driven
  * axis kernel; PEA_KNOB_MAX_CTAS = n > 0: persistent 2-D kernels launch at most n CTAs (every CTA walks many tiles);
- * PEA_KNOB_TUNE_TY2D = 8 / 12 / 16: pins the tile height of the generic 2-D tiled kernel. */
+ * PEA_KNOB_TUNE_TY2D = 8 / 12 / 16: pins the tile height of the generic 2-D tiled kernel; PEA_KNOB_GT_TWO_PASS != 0:
+ * pea_gt_targets takes its two-launch route even where the one-launch (cooperative) route is available. */
 #define PEA_KNOB_NO_CANON 0
 #define PEA_KNOB_MAX_CTAS 1
 #define PEA_KNOB_TUNE_TY2D 2
-#define PEA_KNOB_GT_TWO_PASS 3 /* != 0: pea_gt_targets takes its two-launch route (count + write) instead of the one-launch one */
+#define PEA_KNOB_GT_TWO_PASS 3
 #define PEA_KNOB_COUNT 4
 int pea_debug_configure(int knob, int value);
 
@@ -222,11 +223,14 @@ size_t pea_wbr_stats_bytes(int n_channels);
 int pea_weight_binary_ratio(const float* label, int n_channels, int64_t n_per_channel, double alpha,
                             float* weight, void* stats, size_t stats_bytes, void* stream);
 
-/* Whole-batch ground truth in two passes over the labels (the training-loop form of the three functions above,
+/* Whole-batch ground truth (the training-loop form of the three functions above,
  * scripts_cvppp/data/data_provider.py:204-225, scripts_ac3ac4/data/data_provider_labeled_deep.py:246-285 with
  * separate_weight): labels (B,D,H,W) -> target (B,K,D,H,W), [mask u8, semantics 0 only], weight (B,K,D,H,W), one
  * weight problem per (sample, channel).  semantics 0 = gen_affs_ours (ignore / padding apply), 1 = seg_to_aff
- * without replicate pad.  offsets: host int32[K*3] (dz,dy,dx).  counts: device scratch of pea_gt_counts_bytes(B,K). */
+ * without replicate pad.  offsets: host int32[K*3] (dz,dy,dx).  counts: device scratch of pea_gt_counts_bytes(B,K)
+ * (the per-(sample, channel) counts plus one completion counter per sample; ABI 6: 4 B more per sample than ABI 5).
+ * One cooperative launch when the whole batch can be resident (counting phase with the results parked in shared memory,
+ * then the stores); two launches (count + write, then recompute + write weights) otherwise.  Results are identical. */
 size_t pea_gt_counts_bytes(int B, int K);
 int pea_gt_targets(const void* labels, int label_dtype, int B, int D, int H, int W,
                    const int32_t* offsets, int K, int semantics, int ignore, int padding, double alpha,

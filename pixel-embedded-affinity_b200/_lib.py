@@ -57,7 +57,7 @@ SIGNATURES = {
     "pea_weight_binary_ratio": (ci, [vp, ci, ctypes.c_int64, ctypes.c_double, vp, vp, ctypes.c_size_t, vp]),
 }
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class PeaError(RuntimeError):

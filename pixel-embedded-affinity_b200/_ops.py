@@ -378,7 +378,7 @@ def weight_binary_ratio(label, n_channels, alpha=1.0):
 
 
 def gt_targets(labels4, offsets3_, semantics, ignore=False, padding=True, alpha=1.0, want_mask=True):
-    """labels (B,D,H,W) CUDA tensor -> (target (B,K,D,H,W) f32, mask u8 or None, weight f32): fused two-pass kernels."""
+    """labels (B,D,H,W) CUDA tensor -> (target (B,K,D,H,W) f32, mask u8 or None, weight f32): one cooperative launch (count, then stream the stores) or the two-launch route for volumes too large to be resident."""
     B, D, H, W = labels4.shape
     offs = np.asarray(offsets3_, dtype=np.int32).reshape(-1, 3)
     K = offs.shape[0]

@@ -16,7 +16,7 @@ def make_targets_2d(labels, offsets, ignore=False, padding=True):
     """labels (B,H,W) CUDA integer tensor -> target (B,K,H,W) f32, mask (B,K,H,W) u8, weightmap (B,K,H,W) f32."""
     if labels.dim() != 3 or not labels.is_cuda:
         raise ValueError("labels must be a (B,H,W) CUDA tensor")
-    if labels.shape[-1] % 4 == 0:   # fused two-pass kernels: four pixels per thread, 128-bit stores
+    if labels.shape[-1] % 4 == 0:   # fused batch kernel (pea_gt_targets): 128-bit stores, W % 4 == 0
         offs3 = ops.offsets3(offsets, 2)
         target, mask, weight = ops.gt_targets(labels.contiguous()[:, None], offs3, 0, ignore, padding)
         return target[:, :, 0], mask[:, :, 0], weight[:, :, 0]
