@@ -256,6 +256,16 @@ def our_step(P, w, e, tgt, wgt, msk, offsets, crit, partner=None):
     return loss
 
 
+# The dominant kernel's OTHER ceilings, as fractions of the HBM roofline ("three ceilings": per-voxel
+# need from the SASS counts of the shipped kernel, chip rate = 148 SMs x 1.965 GHz): a gather-form backward with 20 pair
+# evaluations per voxel cannot reach the HBM roofline on this chip whatever its memory behaviour is.
+ON_CHIP_CEILINGS = {
+    "cfg3": {"shared_memory_bandwidth": 0.86, "fp32_issue_port": 0.84, "instruction_issue": 0.96,
+             "how": "1815 B of LDS + TMA fill, 58 FP32-port clocks and 51 issue slots per voxel against 37.2 TB/s and "
+                    "1163 G scheduler-clocks/s; HBM roofline = 23.75 G voxels/s"},
+    "cfg2": {"shared_memory_bandwidth": 0.83, "how": "1792 B of LDS + TMA fill per 258 B pixel"},
+}
+
 LAUNCHES_PER_STEP = 3  # fused3d_norm5_tm, finalize_loss, scale_inplace: fallback when the profiler cannot count them
 
 
@@ -1104,7 +1114,8 @@ def run_ours(args, rank, world, local_rank):
                          "traffic_source": "--traffic" if args.traffic is not None else ncu_traffic(args.workload)[1],
                          "peak_source": peak_src,
                          "kernel": "whole fused step (all pea kernels of one fwd+bwd); dominant kernel: " + str(ncu_traffic(args.workload)[2]),
-                         "algorithmic_bytes_per_step": alg_bytes},
+                         "algorithmic_bytes_per_step": alg_bytes,
+                         "on_chip_ceilings": ON_CHIP_CEILINGS.get(args.workload)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "what": "embedding+target+weight(+mask) from pinned host each step, loss read back"},
             "e2e_labels_only": {"value": world * vox_step * e2e_steps / (lab_ms * 1e-3), "unit": UNIT, "n_gpus": world,

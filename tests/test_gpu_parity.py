@@ -1109,6 +1109,67 @@ def test_fused_batch_gt_routes_bit_identical(P, O, route):
         _knob(KNOB_GT_TWO_PASS, 0)
 
 
+@pytest.mark.parametrize("route", ["one_launch", "two_launch"])
+@pytest.mark.parametrize("B,D,H,W,dt,semantics", [(3, 1, 41, 72, np.uint8, 0), (2, 1, 30, 44, np.int32, 0), (2, 5, 24, 40, np.int32, 1),
+                                                   (1, 3, 17, 36, np.uint8, 1)])
+def test_gt_kernels_write_only_their_outputs(P, O, route, B, D, H, W, dt, semantics):
+    """Guard bands around target, mask, weight and the counts scratch of pea_gt_targets (compute-sanitizer is closed on the
+    GPU pool): buffers carved out of larger poisoned ones and handed to the C ABI directly, both routes, rows that are /
+    are not a multiple of eight voxels, last slices only partly filled.  Nothing outside the outputs may change, every
+    element inside must be written, and the results must equal the oracle's bit for bit."""
+    import ctypes
+    from pea_b200 import _ops as ops
+    from pea_b200._lib import lib, check
+    _knob(3, 1 if route == "two_launch" else 0)  # PEA_KNOB_GT_TWO_PASS
+    try:
+        if semantics == 0:
+            offsets = O.multi_offset([1, 3, 5, 9, 11], neighbor=4)
+            offs3 = ops.offsets3(offsets, 2)
+            labs = np.stack([O.voronoi_labels((H, W), 7, 80 + b, background_frac=0.3, dtype=np.uint8) for b in range(B)]).astype(dt)[:, None]
+        else:
+            from pea_b200.gt import NHOOD_NORM5
+            offs3 = np.asarray(NHOOD_NORM5, dtype=np.int32)
+            labs = np.stack([O.voronoi_labels((D, H, W), 7, 90 + b, z_scale=3.0, dtype=np.uint16) for b in range(B)])
+            labs = (labs % 200).astype(dt)
+        K = offs3.shape[0]
+        n = B * K * D * H * W
+        PAD = 4096
+        lab_d = torch.tensor(labs).cuda().contiguous()
+
+        def guarded(count, dtype, poison):
+            buf = torch.full((count + 2 * PAD,), poison, dtype=dtype, device="cuda")
+            return buf, buf[PAD:PAD + count]
+
+        t_buf, tgt = guarded(n, torch.float32, -12345.0)
+        w_buf, wgt = guarded(n, torch.float32, -12345.0)
+        m_buf, msk = guarded(n, torch.uint8, 77)
+        nbytes = lib.pea_gt_counts_bytes(B, K)
+        c_buf, cnt = guarded(nbytes // 8, torch.int64, -7)
+        offs = (ctypes.c_int32 * (3 * K))(*[int(v) for v in np.asarray(offs3).reshape(-1)])
+        rc = lib.pea_gt_targets(lab_d.data_ptr(), ops.label_code(lab_d), B, D, H, W, offs, K, semantics, 0, 1, 1.0,
+                                tgt.data_ptr(), msk.data_ptr() if semantics == 0 else None, wgt.data_ptr(), cnt.data_ptr(), nbytes,
+                                torch.cuda.current_stream().cuda_stream)
+        check("pea_gt_targets", rc)
+        torch.cuda.synchronize()
+        for name, buf, poison in (("target", t_buf, -12345.0), ("weight", w_buf, -12345.0), ("counts", c_buf, -7)) + \
+                ((("mask", m_buf, 77),) if semantics == 0 else ()):
+            assert bool((buf[:PAD] == poison).all()) and bool((buf[-PAD:] == poison).all()), f"{name}: guard band overwritten"
+        assert not bool((tgt == -12345.0).any()) and not bool((wgt == -12345.0).any()), "elements left unwritten"
+        tgt5, wgt5 = tgt.view(B, K, D, H, W).cpu().numpy(), wgt.view(B, K, D, H, W).cpu().numpy()
+        for b in range(B):
+            if semantics == 0:
+                to, mo = O.gen_affs_ours(labs[b, 0], offsets, ignore=False, padding=True)
+                same(tgt5[b, :, 0], to, "target")
+                same(msk.view(B, K, D, H, W)[b, :, 0], mo, "mask")
+                same(wgt5[b, :, 0], np.stack([O.weight_binary_ratio(c) for c in to]), "weight")
+            else:
+                to = O.seg_to_aff_norm5(labs[b])
+                same(tgt5[b], to, "target")
+                same(wgt5[b], np.stack([O.weight_binary_ratio(c) for c in to]), "weight")
+    finally:
+        _knob(3, 0)
+
+
 # =========================================================================== several small losses in one launch
 def test_norm1_multi_matches_single_calls_and_oracle(P, O):
     """embedding_loss_norm1_multi (ONE launch for the four deep-supervision scales, scripts_ac3ac4/main.py:227-230)

@@ -61,3 +61,16 @@ bl.add_vol(f, (0, 0, 4))
 bl.get_results((0, 2, 2), one_minus=True)
 torch.cuda.synchronize()
 print("sanitize_small ok", float(l.detach()), float(lx.detach()), float(l27.detach()))
+# round 2, second session: batch GT in one cooperative launch (8 and 4 voxels per thread, 8-bit and 32-bit labels, many
+# slices per block) and the two-launch route behind the test knob
+from pea_b200._lib import lib as _lib
+for two_pass in (0, 1):
+    _lib.pea_debug_configure(3, two_pass)  # PEA_KNOB_GT_TWO_PASS
+    for (Bg, Hg, Wg, dt) in ((3, 40, 64, np.uint8), (2, 36, 44, np.uint8), (2, 24, 40, np.int32)):
+        lg = np.stack([O.voronoi_labels((Hg, Wg), 6, 7 + b) for b in range(Bg)]).astype(dt)
+        P.make_targets_2d(torch.tensor(lg).cuda(), P.multi_offset([1, 3, 5, 9, 11], 4), ignore=bool(two_pass))
+    P.make_targets_3d(torch.tensor(np.stack([seg, seg]).astype(np.int32)).cuda())
+    P.make_targets_3d(torch.tensor((np.stack([seg, seg]) % 200).astype(np.uint8)).cuda())
+_lib.pea_debug_configure(3, 0)
+torch.cuda.synchronize()
+print("sanitize_small: done")
