@@ -860,6 +860,65 @@ def time_inference_epilogue(P, device, shape=(100, 1024, 1024), iters=5):
     return out
 
 
+def time_graph(fn, flush, iters=20, do_flush=True):
+    """Median ms of a CUDA-graph replay of fn (CUDA events around each replay; the L2 is flushed between replays unless
+    do_flush is False: steady-state number, working set partly resident in the 126 MB L2)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    for _ in range(3):
+        graph.replay()
+    per = []
+    for _ in range(iters):
+        if do_flush:
+            flush.zero_()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        graph.replay()
+        t.record()
+        torch.cuda.synchronize()
+        per.append(s.elapsed_time(t))
+    del graph
+    return statistics.median(per)
+
+
+def time_forward_and_warm(P, device, flush, peak):
+    """forward-only affinities (embedding2affs / inf_embedding_loss_norm5: 4C + 4K bytes per voxel) at
+    cfg1 - cfg3, and the fused fwd+bwd step of each with a WARM L2 (no flush between replays) next to the cold number the
+    other legs report -- a warm number above the HBM roofline is an L2 artefact, not a win."""
+    out = {}
+    for name in ("cfg1", "cfg2", "cfg3"):
+        w = WORKLOADS[name]
+        lab, emb, tgt, wgt, msk, offsets = device_inputs(P, w, 0, device)
+        K = 12 if w["nd"] == 3 else 2 * len(w["shifts"])
+        vox = w["B"] * int(np.prod(w["spatial"]))
+        with torch.no_grad():
+            fwd = (lambda: P.embedding2affs(emb, offsets)) if w["nd"] == 2 else (lambda: P.inf_embedding_loss_norm5(emb))
+            ms_f = time_graph(fwd, flush)
+        e = emb.clone().requires_grad_(True)
+        crit = P.WeightedMSE()
+
+        def step():
+            our_step(P, w, e, tgt, wgt, msk, offsets, crit)
+            e.grad = None
+        ms_w = time_graph(step, flush, do_flush=False)
+        ab, _ = algorithmic_bytes_per_step(w)
+        fb = (4 * C + 4 * K) * vox
+        out[name] = {"forward_only_ms": ms_f, "forward_only_hbm_gbs": fb / (ms_f * 1e-3) / 1e9,
+                     "forward_only_roofline_frac": fb / (ms_f * 1e-3) / 1e9 / peak,
+                     "fused_step_warm_l2_ms": ms_w, "fused_step_warm_l2_hbm_gbs_equiv": ab / (ms_w * 1e-3) / 1e9,
+                     "fused_step_warm_l2_frac_of_hbm_roofline": ab / (ms_w * 1e-3) / 1e9 / peak}
+        del lab, emb, tgt, wgt, msk, e
+    out["timing"] = "CUDA-graph replay, median of 20; forward-only with the L2 flushed, warm numbers without a flush"
+    return out
+
+
 def time_reference_on_gpu(P, w, device, flush, iters=10):
     """The reference's OWN loss function (the unmodified files staged under baseline/_ref) running as eager PyTorch ops on
     this GPU, forward + backward on the workload's batch -- the implementation a user
@@ -1094,6 +1153,8 @@ def run_ours(args, rank, world, local_rank):
             also["cfg1_labels"] = time_labels_pipeline(P, WORKLOADS["cfg1"], device, flush)   # CVPPP table: axis kernel's label flavour
             also["cfg1_labels"]["roofline_frac"] = also["cfg1_labels"]["hbm_gbs"] / peak
             also["step6"] = time_step6(P, device, flush)
+            torch.cuda.empty_cache()
+            also["forward_and_warm_l2"] = time_forward_and_warm(P, device, flush, peak)
             torch.cuda.empty_cache()
             try:  # context line: what the reference itself does on this GPU (same batch, eager torch ops)
                 also["reference_on_gpu"] = time_reference_on_gpu(P, w, device, flush)

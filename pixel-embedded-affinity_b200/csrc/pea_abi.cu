@@ -51,6 +51,9 @@ bool canon2d_mask_ok(const void* mask, int mask_dtype);
 int launch_canon2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap, const float* target,
                    const float* weight, const void* mask, int mask_dtype, float* affs, float* partials, float* grad,
                    cudaStream_t st);
+// pea_affs2d_fwd.cu
+bool fwd2d_canon_eligible(int C, int D, int H, int W, const OffsetTable& tab, const float* emb);
+int launch_fwd2d_canon(const float* emb, const Dims& d, const OffsetTable& tab, int wrap, int relu, float* affs, cudaStream_t st);
 int launch_canon2d_labels(const float* emb, const int32_t* labels, const float* wtab, int ignore, const Dims& d,
                           const OffsetTable& tab, int wrap, float* affs, float* partials, float* grad, cudaStream_t st);
 int launch_axis2d_labels(const float* emb, const int32_t* labels, const float* wtab, int ignore, const Dims& d,
@@ -272,6 +275,11 @@ extern "C" int pea_affs_fwd(const float* emb, const float* partner, int B, int C
     const bool tiled3_ok = tiled3d_fwd_eligible(C, W, tab, border, cross != 0, emb, emb_plane);
     if (impl == PEA_IMPL_TILED && !tiled2_ok && !tiled3_ok) return PEA_E_MODE;
     if (halo && (!tiled3_ok || impl == PEA_IMPL_GENERIC)) return PEA_E_MODE;  // only the tiled kernel reads an external halo
+    // 2-D, one view, axis-aligned neighbor-4 tables (every shipped 2-D config): unrolled forward kernel, relu in the store.
+    // PEA_KNOB_NO_CANON (tests) sends these calls to the older kernels below.
+    if (impl != PEA_IMPL_GENERIC && plain && !cross && D == 1 && debug_knob(PEA_KNOB_NO_CANON) == 0 &&
+        fwd2d_canon_eligible(C, D, H, W, tab, emb) && !(reinterpret_cast<uintptr_t>(affs) & 3))
+        return launch_fwd2d_canon(emb, d, tab, border == PEA_BORDER_WRAP, relu, affs, st);
     if (impl != PEA_IMPL_GENERIC) {
         if (tiled3_ok)
             return launch_fwd3d_norm5(emb, d, z_skip, emb_plane, affs_plane, affs, halo, halo ? halo_slices : 0, halo_plane, relu,

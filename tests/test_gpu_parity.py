@@ -823,6 +823,50 @@ def test_canonical2d_kernel_matches_table_driven_kernels(P, O, B, H, W, border, 
                 close_t(outs["canon"][2], outs[other][2], what=f"grad vs {other}")
 
 
+@pytest.mark.parametrize("shifts", [[1, 3, 5, 9, 11], [1, 3, 5, 9, 27], [2], [1, 2, 4, 8, 12, 28], [3, 7, 20]])
+@pytest.mark.parametrize("B,H,W", [(2, 130, 160), (1, 75, 100), (3, 33, 72)])
+def test_forward_only_2d_kernel(P, O, shifts, B, H, W):
+    """embedding2affs (scripts_cvppp/loss/loss_embedding_mse.py:58-66) at the axis-aligned neighbor-4 tables takes the
+    unrolled forward kernel (pea_affs2d_fwd.cu: shifts <= 12 double-buffered, up to 28 single-buffered).  Against the
+    oracle (circular border), the table-driven generic kernel and the older tiled kernel (PEA_KNOB_NO_CANON): both borders,
+    relu folded into the store or not, 1 - 6 shifts, partial tiles in x and y, a zero-norm pixel; a grid capped to 2 CTAs
+    (every CTA walks many tiles through both sets of boxes) must give bit-identical results."""
+    from pea_b200 import _ops as ops
+    offsets = O.multi_offset(shifts, neighbor=4)
+    offs3 = ops.offsets3(offsets, 2)
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    emb = torch.randn((B, 16, H, W), generator=g)
+    emb[0, :, 3, 5] = 0.0
+    emb_d = emb.cuda()
+    try:
+        for border in (ops.BORDER_WRAP, ops.BORDER_ZERO):
+            for relu in (False, True):
+                outs = {}
+                for name in ("new", "new_cap2", "old", "generic"):
+                    _knob(KNOB_NO_CANON, 1 if name == "old" else 0)
+                    _knob(KNOB_MAX_CTAS, 2 if name == "new_cap2" else 0)
+                    impl = ops.IMPL_GENERIC if name == "generic" else ops.IMPL_AUTO
+                    outs[name] = ops.affs_fwd(emb_d, None, offs3, border, impl=impl, relu=relu).cpu()
+                assert torch.equal(outs["new"], outs["new_cap2"]), "capped grid differs"
+                close_t(outs["new"], outs["generic"], what=f"vs generic, border {border}, relu {relu}")
+                close_t(outs["new"], outs["old"], what=f"vs tiled, border {border}, relu {relu}")
+                if border == ops.BORDER_WRAP:
+                    ao = O.embedding2affs(emb, offsets)
+                    close_t(outs["new"], torch.relu(ao) if relu else ao, what=f"vs oracle, relu {relu}")
+    finally:
+        _knob(KNOB_NO_CANON, 0)
+        _knob(KNOB_MAX_CTAS, 0)
+    # the public call, with and without autograd (backward through pea_affs_bwd)
+    e = emb_d.clone().requires_grad_(True)
+    a = P.embedding2affs(e, offsets)
+    a.square().sum().backward()
+    eo = emb.clone().requires_grad_(True)
+    ao = O.embedding2affs(eo, offsets)
+    ao.square().sum().backward()
+    close_t(a, ao, what="public call affs")
+    close_t(e.grad, eo.grad, what="public call grad")
+
+
 @pytest.mark.parametrize("B,H,W,shifts,ldtype,ignore", [
     (2, 130, 160, [1, 3, 5, 9, 11], np.uint8, False),    # canonical table: GT derived inside the loss kernel
     (1, 75, 100, [1, 3, 5, 9, 11], np.int32, True),      # partial tiles in x and y, ignore=True
