@@ -421,6 +421,27 @@ extern "C" int pea_affs_loss_fwd_bwd(const float* emb, const float* partner, int
         if (rc) return rc;
         return (int)launch_tail(finalize_loss_kernel, 1, 1024, st, parts, nblk3, K, sc, loss_out);
     }
+    // Offset sets no specialised kernel covers (embedding_loss_norm1 / ema_embedding_loss_norm1 at full resolution:
+    // TRAIN.embedding_mode == 1, scripts_ac3ac4/main.py:219-221; odd tables): the work-list kernel with ONE problem -- no
+    // 1 / |x| plane pass, neighbours' norms inline, loss finalized in the kernel.  B = 4, 18 x 160 x 160, K = 3:
+    // 415 -> 154 us.  The ticket word sits behind the partials in the caller's workspace and is zeroed in stream order.
+    if (impl == PEA_IMPL_AUTO && K <= PEA_MULTI_MAX_OFFSETS && grad_partner == nullptr && !accumulate &&
+        (int64_t)B * d.N < ((int64_t)1 << 31) - 64) {
+        bool small = true;
+        for (int k = 0; k < 3 * K; ++k) small = small && offsets[k] >= -127 && offsets[k] <= 127;
+        pea_loss_problem pr;
+        pr.emb = emb; pr.partner = partner; pr.target = target; pr.weight = weight; pr.mask = mask;
+        pr.affs = affs; pr.grad_emb = grad_emb; pr.loss_out = loss_out;
+        pr.offsets = offsets; pr.loss_norm = loss_norm; pr.loss_coef = loss_coef;
+        pr.B = B; pr.D = D; pr.H = H; pr.W = W; pr.K = K; pr.border = border; pr.mask_dtype = mask_dtype;
+        const size_t parts = align_up(pea_affs_loss_multi_workspace(&pr, 1), 256);
+        if (small && parts + 16 <= ws.bytes) {
+            uint32_t* ticket = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + parts);
+            cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
+            if (e != cudaSuccess) return (int)e;
+            return pea_affs_loss_multi(&pr, 1, C, workspace, parts, ticket, stream);
+        }
+    }
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
     rc = launch_fused_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP, cross,
