@@ -51,6 +51,9 @@ bool canon2d_mask_ok(const void* mask, int mask_dtype);
 int launch_canon2d(const float* emb, const float* partner, const Dims& d, const OffsetTable& tab, int wrap, const float* target,
                    const float* weight, const void* mask, int mask_dtype, float* affs, float* partials, float* grad,
                    cudaStream_t st);
+// pea_affs_multi.cu
+int launch_multi_upstream(const float* emb, const float* partner, int B, int C, int D, int H, int W, const int32_t* offsets, int K,
+                          int border, const float* grad_affs, float* grad_emb, cudaStream_t st);
 // pea_affs2d_fwd.cu
 bool fwd2d_canon_eligible(int C, int D, int H, int W, const OffsetTable& tab, const float* emb);
 int launch_fwd2d_canon(const float* emb, const Dims& d, const OffsetTable& tab, int wrap, int relu, float* affs, cudaStream_t st);
@@ -520,6 +523,12 @@ extern "C" int pea_affs_bwd(const float* emb, const float* partner, int B, int C
     OffsetTable tab;
     fill_offsets(offsets, K, tab);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // gradient for the anchor view only, at most 12 offsets: the work-list kernel in upstream mode (no 1 / |x| plane pass;
+    // cfg2 1.31 -> see DESIGN.md).  PEA_KNOB_NO_CANON (tests) keeps the table-driven kernel.
+    if (grad_emb && !grad_partner && debug_knob(PEA_KNOB_NO_CANON) == 0) {
+        rc = launch_multi_upstream(emb, partner, B, C, D, H, W, offsets, K, border, grad_affs, grad_emb, st);
+        if (rc != PEA_E_MODE) return rc;
+    }
     if ((rc = launch_rinv(emb, C, d, ws.rinvE, st))) return rc;
     if (cross && (rc = launch_rinv(partner, C, d, ws.rinvU, st))) return rc;
     return launch_fused_generic(emb, cross ? partner : emb, ws.rinvE, ws.rinvU, C, d, tab, border == PEA_BORDER_WRAP,

@@ -28,6 +28,7 @@ struct Problem {
     float* grad;   // may be null
     float* loss_out;
     int B, D, H, W, K, wrap, mask_dtype, cross;
+    int upstream;     // != 0: `target` holds d loss / d affs (K5, pea_affs_bwd): gradient only, no loss
     int chunk_begin;  // first 32-voxel chunk of this problem in the launch-wide chunk numbering
     signed char dz[kMaxK], dy[kMaxK], dx[kMaxK];
     float gcoef[kMaxK], norm[kMaxK], coef[kMaxK];
@@ -127,6 +128,24 @@ __global__ void __launch_bounds__(kThreads, 2) multi_fused(const __grid_constant
 #pragma unroll
                 for (int c = 0; c < C; ++c) xr[c] = __ldg(embB + (int64_t)c * N + q2);
             }
+            if (pr.upstream) {
+                // K5: the gradient arrives through the affinities; a pair the border rule drops has a constant affinity
+                const float u = vf ? __ldg(pr.target + idx) : 0.f, u2 = vr ? __ldg(pr.target + idx2) : 0.f;
+                float sq = 0.f, sr = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) sq = fmaf(xq[c], xq[c], sq);
+                const float g = u * inv_norm(sq);
+#pragma unroll
+                for (int c = 0; c < C; ++c) G[c] = fmaf(g, xq[c], G[c]);
+                if (rev) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) sr = fmaf(xr[c], xr[c], sr);
+                    const float g2 = u2 * inv_norm(sr);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) G[c] = fmaf(g2, xr[c], G[c]);
+                }
+                continue;
+            }
             const float t = __ldg(pr.target + idx), w = vf ? __ldg(pr.weight + idx) : 0.f, m = load_mask(pr.mask, pr.mask_dtype, idx);
             float t2 = 0.f, w2 = 0.f, m2 = 0.f;
             if (rev) {
@@ -176,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 2) multi_fused(const __grid_constant
         }
     }
 
+    if (bt.ticket == nullptr) return;  // gradient-only launch (upstream mode): no loss to finalize
     // ---- per-CTA partials (fixed order over warps), then the last CTA to arrive finalizes every problem
     __syncthreads();
     const int slots = bt.n * kMaxK;
@@ -285,6 +305,7 @@ extern "C" int pea_affs_loss_multi(const pea_loss_problem* problems, int n, int 
         p.B = s.B; p.D = s.D; p.H = s.H; p.W = s.W; p.K = s.K;
         p.wrap = s.border == PEA_BORDER_WRAP;
         p.mask_dtype = s.mask_dtype;
+        p.upstream = 0;
         for (int k = 0; k < s.K; ++k) {
             const int32_t oz = s.offsets[3 * k], oy = s.offsets[3 * k + 1], ox = s.offsets[3 * k + 2];
             if (oz < -127 || oz > 127 || oy < -127 || oy > 127 || ox < -127 || ox > 127) return PEA_E_OFFSETS;
@@ -318,6 +339,48 @@ extern "C" int pea_affs_loss_multi(const pea_loss_problem* problems, int n, int 
     }
     return (int)cudaGetLastError();
 }
+
+// K5 through the work-list kernel: grad_emb = d loss / d emb for the upstream gradient grad_affs of the affinities of ONE
+// volume (pea_affs_bwd); gradient w.r.t. the anchor view only.  Returns PEA_E_MODE when the problem does not fit the
+// kernel's limits (the caller then takes the table-driven kernel).
+namespace pea {
+int launch_multi_upstream(const float* emb, const float* partner, int B, int C, int D, int H, int W, const int32_t* offsets, int K,
+                          int border, const float* grad_affs, float* grad_emb, cudaStream_t st) {
+    if (K < 1 || K > PEA_MULTI_MAX_OFFSETS) return PEA_E_MODE;
+    if (C != 4 && C != 8 && C != 16 && C != 32) return PEA_E_MODE;
+    const int64_t total = (int64_t)B * D * H * W;
+    if (total >= ((int64_t)1 << 31) - 64) return PEA_E_MODE;
+    multi::Batch bt;
+    bt.n = 1;
+    multi::Problem& p = bt.p[0];
+    p.emb = emb; p.par = partner ? partner : emb; p.cross = partner ? 1 : 0;
+    p.target = grad_affs; p.weight = nullptr; p.mask = nullptr; p.affs = nullptr; p.grad = grad_emb; p.loss_out = nullptr;
+    p.B = B; p.D = D; p.H = H; p.W = W; p.K = K; p.wrap = border == PEA_BORDER_WRAP; p.mask_dtype = PEA_MASK_NONE;
+    p.upstream = 1;
+    for (int k = 0; k < K; ++k) {
+        const int32_t oz = offsets[3 * k], oy = offsets[3 * k + 1], ox = offsets[3 * k + 2];
+        if (oz < -127 || oz > 127 || oy < -127 || oy > 127 || ox < -127 || ox > 127) return PEA_E_MODE;
+        p.dz[k] = (signed char)oz; p.dy[k] = (signed char)oy; p.dx[k] = (signed char)ox;
+        p.norm[k] = 1.f; p.coef[k] = 1.f; p.gcoef[k] = 1.f;
+    }
+    p.chunk_begin = 0;
+    bt.total_chunks = (int)((total + 31) / 32);
+    bt.partials = nullptr;
+    bt.ticket = nullptr;
+    int64_t g = (bt.total_chunks + multi::kWarps - 1) / multi::kWarps;
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int cap = nsm > 0 && nsm <= 592 ? 2 * nsm : 296;
+    const int grid = (int)(g < 1 ? 1 : (g > cap ? cap : g));
+    switch (C) {
+        case 4: multi::multi_fused<4><<<grid, multi::kThreads, 0, st>>>(bt); break;
+        case 8: multi::multi_fused<8><<<grid, multi::kThreads, 0, st>>>(bt); break;
+        case 16: multi::multi_fused<16><<<grid, multi::kThreads, 0, st>>>(bt); break;
+        default: multi::multi_fused<32><<<grid, multi::kThreads, 0, st>>>(bt); break;
+    }
+    return (int)cudaGetLastError();
+}
+}  // namespace pea
 
 extern "C" int pea_scale_multi(float* const* bufs, const int64_t* lens, const float* const* scales, int n, void* stream) {
     if (!bufs || !lens || !scales) return PEA_E_NULL;

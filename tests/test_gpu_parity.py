@@ -867,6 +867,56 @@ def test_forward_only_2d_kernel(P, O, shifts, B, H, W):
     close_t(e.grad, eo.grad, what="public call grad")
 
 
+@pytest.mark.parametrize("case", ["2d_wrap", "2d_zero_two_views", "3d_norm5", "3d_diagonals_two_views"])
+def test_k5_backward_routes_agree(P, O, case):
+    """pea_affs_bwd (gradient through the affinities, for criteria the fused kernels do not implement): the work-list
+    kernel in upstream mode against the table-driven kernel (PEA_KNOB_NO_CANON) and torch autograd through the oracle's
+    affinities: 2-D and 3-D, both borders, one and two views (gradient for the anchor view), a zero-norm voxel."""
+    from pea_b200 import _ops as ops
+    g = torch.Generator().manual_seed(11)
+    if case.startswith("2d"):
+        shape, offs = (2, 16, 1, 50, 68), ops.offsets3(O.multi_offset([1, 3, 9, 27], neighbor=4), 2)
+        border = ops.BORDER_WRAP if case == "2d_wrap" else ops.BORDER_ZERO
+    else:
+        from pea_b200.data_affinity import NHOOD_NORM5
+        shape, border = (2, 16, 6, 30, 36), ops.BORDER_ZERO
+        offs = np.asarray(NHOOD_NORM5, np.int32) if case == "3d_norm5" else np.asarray(
+            [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-1, -1, -1], [-1, 1, 1], [0, -9, -4], [0, 4, -9]], np.int32)
+    two = case.endswith("two_views")
+    emb = torch.randn(shape, generator=g)
+    emb[0, :, 0, 3, 5] = 0.0
+    par = torch.randn(shape, generator=g) if two else None
+    K = offs.shape[0]
+    up = torch.randn((shape[0], K) + shape[2:], generator=g)
+    outs = {}
+    try:
+        for name in ("worklist", "table"):
+            _knob(KNOB_NO_CANON, 1 if name == "table" else 0)
+            ge, _ = ops.affs_bwd(emb.cuda(), par.cuda() if two else None, offs, border, up.cuda(), want_grad=True, want_grad_partner=False)
+            outs[name] = ge.cpu()
+    finally:
+        _knob(KNOB_NO_CANON, 0)
+    close_t(outs["worklist"], outs["table"], what="work-list vs table-driven kernel")
+    # torch autograd through plain torch ops (normalise, shift with the border rule, dot)
+    eo = emb.clone().requires_grad_(True)
+    en = torch.nn.functional.normalize(eo, p=2, dim=1)
+    un = torch.nn.functional.normalize(par, p=2, dim=1) if two else en
+    loss = 0.0
+    D, H, W = shape[2:]
+    for k, (dz, dy, dx) in enumerate(offs.tolist()):
+        if border == ops.BORDER_WRAP:
+            sh = torch.roll(un, shifts=(-dz, -dy, -dx), dims=(2, 3, 4))
+            a = (en * sh).sum(1)
+        else:
+            a = torch.zeros((shape[0], D, H, W))
+            zs = slice(max(0, -dz), min(D, D - dz)); ys = slice(max(0, -dy), min(H, H - dy)); xs = slice(max(0, -dx), min(W, W - dx))
+            zq = slice(max(0, dz), min(D, D + dz)); yq = slice(max(0, dy), min(H, H + dy)); xq = slice(max(0, dx), min(W, W + dx))
+            a[:, zs, ys, xs] = (en[:, :, zs, ys, xs] * un[:, :, zq, yq, xq]).sum(1)
+        loss = loss + (a * up[:, k]).sum()
+    loss.backward()
+    close_t(outs["worklist"], eo.grad, what="work-list kernel vs torch autograd")
+
+
 @pytest.mark.parametrize("B,H,W,shifts,ldtype,ignore", [
     (2, 130, 160, [1, 3, 5, 9, 11], np.uint8, False),    # canonical table: GT derived inside the loss kernel
     (1, 75, 100, [1, 3, 5, 9, 11], np.int32, True),      # partial tiles in x and y, ignore=True

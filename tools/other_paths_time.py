@@ -60,3 +60,18 @@ vox = w["B"] * int(np.prod(w["spatial"]))
 for name, impl in (("auto (work-list kernel)", ops.IMPL_AUTO), ("table-driven kernel", ops.IMPL_GENERIC)):
     ms = bench.time_graph(lambda: ops.affs_loss_fwd_bwd(emb, None, offs, ops.BORDER_ZERO, tgt, wgt, None, norm, coef, impl=impl), flush)
     report(f"shift_func(15)-like 12 offsets, fwd+bwd, {name}", ms, 272 * vox)
+from pea_b200._autograd import Affinities
+from pea_b200.data_affinity import NHOOD_NORM5
+# ---- K5: gradient through the affinities for criteria the fused kernels do not implement (MSELoss on the affinities here)
+for name in ("cfg2", "cfg3"):
+    w = bench.WORKLOADS[name]
+    lab, emb, tgt, wgt, msk, offsets = bench.device_inputs(P, w, 0, dev)
+    vox = w["B"] * int(np.prod(w["spatial"]))
+    K = tgt.shape[1]
+    e = emb.clone().requires_grad_(True)
+    up = torch.randn_like(tgt)
+    def k5():
+        a = P.embedding2affs(e, offsets) if w["nd"] == 2 else Affinities.apply(e, None, np.asarray(NHOOD_NORM5, np.int32), ops.BORDER_ZERO, ops.IMPL_AUTO)
+        a.backward(up)
+        e.grad = None
+    report(f"{name} affinities forward + backward through them (K5)", bench.time_graph(k5, flush), (64 + 4 * K + 64 + 4 * K + 64) * vox)
