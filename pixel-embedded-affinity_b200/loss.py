@@ -58,3 +58,10 @@ class WeightedBCE(nn.Module):
 def is_weighted_mse(criterion):
     """True for this package's WeightedMSE and for the reference's class of the same name."""
     return type(criterion).__name__ == "WeightedMSE"
+
+
+def is_plain_mse(criterion):
+    """True for the MSELoss wrapper (this package's or the reference's, loss.py:126-132): ``nn.MSELoss()`` with the mean
+    reduction, weight ignored -- i.e. the fused weighted-MSE kernels with unit weights and the element count as normaliser."""
+    inner = getattr(criterion, "criterion", None)
+    return type(criterion).__name__ == "MSELoss" and isinstance(inner, nn.MSELoss) and inner.reduction == "mean"

@@ -12,7 +12,7 @@ import torch
 from . import _ops as ops
 from ._autograd import Affinities, FusedAffinityLoss, FusedAffinityLossLabels, LossList, MultiFusedAffinityLoss, OpSpec
 from ._lib import PeaError
-from .loss import is_weighted_mse
+from .loss import is_plain_mse, is_weighted_mse
 
 
 def _check_mode(mode):
@@ -45,6 +45,11 @@ def _cosine_loss(embedding, partner, target, weightmap, mask, criterion, offsets
 def _norms_2d(B, W, K):
     # WeightedMSE sees a (B, H, W) prediction: prod(size()[2:]) * size()[0] == W * B, in float32 (loss.py:114-116)
     return np.full(K, np.float32(W) * np.float32(B), dtype=np.float32)
+
+
+def _norms_mean_2d(B, H, W, K):
+    # nn.MSELoss (mean): the (B, H, W) prediction's element count
+    return np.full(K, np.float32(B * H * W), dtype=np.float32)
 
 
 def _prep(embedding, target, weightmap, mask, offsets):
@@ -94,6 +99,10 @@ def embedding_loss(embedding, target, weightmap, mask, criterion, offsets, affs0
     if is_weighted_mse(criterion):
         spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), np.ones(K, np.float32), affs_differentiable=True)
         loss, affs, each = FusedAffinityLoss.apply(embedding, None, target, weightmap, mask, spec)
+        return loss, affs, LossList(each)
+    if is_plain_mse(criterion):  # TRAIN.loss_func == 'MSELoss': unit weights, mean over all B * H * W elements
+        spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_mean_2d(B, H, W, K), np.ones(K, np.float32), affs_differentiable=True)
+        loss, affs, each = FusedAffinityLoss.apply(embedding, None, target, torch.ones_like(target), mask, spec)
         return loss, affs, LossList(each)
     affs = Affinities.apply(embedding, None, offs3, ops.BORDER_WRAP, ops.IMPL_AUTO)
     loss, each = _generic_criterion(affs, target, weightmap, mask, criterion, [1] * K)
@@ -150,6 +159,10 @@ def ema_embedding_loss(embedding, ema_embedding, target, weightmap, mask, criter
     if is_weighted_mse(criterion):
         spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_2d(B, W, K), coef, affs_differentiable=True)
         loss, affs, _ = FusedAffinityLoss.apply(embedding, ema_embedding, target, weightmap, mask, spec)
+        return loss, affs
+    if is_plain_mse(criterion):
+        spec = OpSpec(offs3, ops.BORDER_WRAP, _norms_mean_2d(B, H, W, K), coef, affs_differentiable=True)
+        loss, affs, _ = FusedAffinityLoss.apply(embedding, ema_embedding, target, torch.ones_like(target), mask, spec)
         return loss, affs
     affs = Affinities.apply(embedding, ema_embedding, offs3, ops.BORDER_WRAP, ops.IMPL_AUTO)
     loss, _ = _generic_criterion(affs, target, weightmap, mask, criterion, [affs0_weight if k < 2 else 1 for k in range(K)])

@@ -17,7 +17,7 @@ from . import _ops as ops
 from ._autograd import (Affinities, FusedAffinityLoss, FusedAffinityLossLabels, FusedSelfAndCrossLoss,
                         MultiFusedAffinityLoss, OpSpec)
 from ._lib import PeaError
-from .loss import is_weighted_mse
+from .loss import is_plain_mse, is_weighted_mse
 
 SHIFTS_NORM5 = [1, 1, 1, 2, 3, 3, 3, 9, 9, 4, 27, 27]  # :176
 
@@ -58,9 +58,12 @@ def _loss3d(embedding, ema_embedding, target, weightmap, criterion, shifts, affs
     norms = _norms_3d(embedding.shape, shifts)
     coef = np.ones(K, np.float32)
     coef[:weighted_upto] = affs0_weight
-    if is_weighted_mse(criterion):
+    if is_weighted_mse(criterion) or is_plain_mse(criterion):
+        # MSELoss (TRAIN.loss_func == 'MSELoss'): mean over the cropped (B, 1, D', H', W') prediction == WeightedMSE's normaliser
+        # there (prod(size()[2:]) * size()[0]), with unit weights
         spec = OpSpec(offs3, ops.BORDER_ZERO, norms, coef, affs_differentiable=False)
-        loss, affs, _ = FusedAffinityLoss.apply(embedding, ema_embedding, target, weightmap, None, spec)
+        wm = weightmap if is_weighted_mse(criterion) else torch.ones_like(target)
+        loss, affs, _ = FusedAffinityLoss.apply(embedding, ema_embedding, target, wm, None, spec)
         return loss, affs
     # any other criterion: CUDA affinity op + the reference's per-channel cropped criterion calls (:159-163)
     affs = Affinities.apply(embedding, ema_embedding, offs3, ops.BORDER_ZERO, ops.IMPL_AUTO)
