@@ -487,6 +487,7 @@ gt_fused_one(const L* __restrict__ labels, int B, int D, int H, int W, GtTable t
     }
 }
 
+constexpr int kGtNotLaunched = -1000;  // run_gt_fused_nv: the one-launch route is not available here (not an error)
 constexpr int kGtOneMaxBytes = 24 * 1024;  // parked bits of the one-launch route: (slices per block) * K * threads (* 2 with a mask)
 
 template <typename L, int MODE, int NV>
@@ -541,7 +542,7 @@ static int run_gt_fused_nv(const void* labels, int B, int D, int H, int W, const
             }
         }
     }
-    return -1000;  // the caller takes the two-launch route
+    return kGtNotLaunched;  // the caller takes the two-launch route
 }
 
 // One launch: eight voxels per thread in the counting phase when the rows allow it (the store phases are re-dealt quad
@@ -557,7 +558,7 @@ static int run_gt_fused(const void* labels, int B, int D, int H, int W, const Gt
         rc = run_gt_fused_nv<L, MODE, 8>(labels, B, D, H, W, tab, ignore, padding, alpha, target, mask, weight, counts, st);
     else
         rc = run_gt_fused_nv<L, MODE, 4>(labels, B, D, H, W, tab, ignore, padding, alpha, target, mask, weight, counts, st);
-    if (rc != -1000) return rc;
+    if (rc != kGtNotLaunched) return rc;
     const int64_t N = (int64_t)D * H * W;
     int64_t chunks = (148 * 8 + B - 1) / B;
     const int64_t max_chunks = (N / 4 + 1023) / 1024;
