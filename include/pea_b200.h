@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PEA_ABI_VERSION 6
+#define PEA_ABI_VERSION 7
 #define PEA_MAX_OFFSETS 64
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -110,6 +110,29 @@ int pea_affs_fwd(const float* emb, const float* partner, int B, int C, int D, in
                  int z_skip, int64_t emb_plane, int64_t affs_plane,
                  const float* halo, int halo_slices, int64_t halo_plane,
                  float* affs, void* workspace, size_t ws_bytes, void* stream);
+
+/* z-sharded volumes, STAGED halo (ABI 7; SURVEY.md 8e, BASELINE config 4 -- the reference has no counterpart: it
+ * blends overlapping patches on the host, scripts_ac3ac4/data/provider_valid.py:306-348; the per-voxel arithmetic is
+ * inf_embedding_loss_norm5, scripts_ac3ac4/loss/loss_embedding_mse.py:212-234).
+ * pea_affs_fwd with `halo` in peer memory pulls 4 slices over NVLink from inside the compute kernel.  The staged
+ * flavour lets a COPY ENGINE pull them instead, while the kernel runs:
+ *   pea_zshard_stage_halo   enqueues, on `stream` (a side stream), one 3-D copy per band of `band_rows` image rows of
+ *                           tail (B, C, halo_slices, H, W; channel-plane stride tail_plane, a multiple of H*W) into
+ *                           `stage` (contiguous), rows [row0, H) only, each followed by a stream-ordered 32-bit write
+ *                           of `epoch` to flags[j] (j = band index; device memory, ceil((H - row0) / band_rows) words);
+ *   pea_zshard_affs_fwd     the 12-offset AC3/AC4 forward kernel on `stream` (the main stream): tiles whose first row
+ *                           is below row0 read `halo` (peer memory) directly, as pea_affs_fwd does -- their CTAs start
+ *                           before a band can have arrived; every other tile waits until its band's flag has reached
+ *                           `epoch` (signed 32-bit distance, so epochs may wrap) and reads `stage`.
+ * row0 and band_rows must be multiples of 8 (the kernel's tile height).  The caller advances `epoch` every step and
+ * orders the side stream behind the producer's writes of the tail (and the next step's copies behind this kernel).
+ * Results are bit-identical to pea_affs_fwd with the same halo. */
+int pea_zshard_stage_halo(const float* tail, int64_t tail_plane, float* stage, int B, int C, int halo_slices, int H, int W,
+                          int row0, int band_rows, uint32_t* flags, uint32_t epoch, void* stream);
+int pea_zshard_affs_fwd(const float* emb, int B, int C, int D, int H, int W, int64_t emb_plane, int64_t affs_plane,
+                        const float* halo, int halo_slices, int64_t halo_plane,
+                        const float* stage, const uint32_t* flags, uint32_t epoch, int row0, int band_rows,
+                        int relu, float* affs, void* stream);
 
 /* Fused embedding -> affinities -> weighted-MSE loss -> d loss / d embedding, one pass.
  *   replaces  embedding_loss / ema_embedding_loss      scripts_cvppp/loss/loss_embedding_mse.py:18-47,79-95

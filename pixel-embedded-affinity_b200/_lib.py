@@ -34,6 +34,9 @@ SIGNATURES = {
     "pea_workspace_bytes": (ctypes.c_size_t, [ci, ci, ci, ci, ci, ci, ci]),
     "pea_affs_fwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, ci, ctypes.c_int64, ctypes.c_int64, vp, ci,
                           ctypes.c_int64, vp, vp, ctypes.c_size_t, vp]),
+    "pea_zshard_stage_halo": (ci, [vp, ctypes.c_int64, vp, ci, ci, ci, ci, ci, ci, ci, vp, ctypes.c_uint32, vp]),
+    "pea_zshard_affs_fwd": (ci, [vp, ci, ci, ci, ci, ci, ctypes.c_int64, ctypes.c_int64, vp, ci, ctypes.c_int64, vp, vp,
+                                 ctypes.c_uint32, ci, ci, ci, vp, vp]),
     "pea_affs_loss_fwd_bwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, ci, vp, vp, vp, ci, c_float_p,
                                    c_float_p, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "pea_affs_bwd": (ci, [vp, vp, ci, ci, ci, ci, ci, c_int32_p, ci, ci, vp, vp, vp, vp, ctypes.c_size_t, vp]),
@@ -57,7 +60,7 @@ SIGNATURES = {
     "pea_weight_binary_ratio": (ci, [vp, ci, ctypes.c_int64, ctypes.c_double, vp, vp, ctypes.c_size_t, vp]),
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class PeaError(RuntimeError):

@@ -27,7 +27,8 @@ int cross3d_norm5_blocks(int B, int H, int W);
 bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool cross, const float* emb,
                           int64_t emb_plane);
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
-                       const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st);
+                       const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st,
+                       const StagedHalo* stage = nullptr);
 int launch_fused3d_norm5(const float* emb, const Dims& d, const OffsetTable& tab, const float* target,
                          const float* weight, float* affs, float* partials, float* grad, cudaStream_t st);
 int launch_fused3d_norm5_labels(const float* emb, const int32_t* seg, const float* wtab, const Dims& d, const OffsetTable& tab,

@@ -864,6 +864,15 @@ struct ParamsF {
     int halo_n;
     int64_t halo_plane;
     int relu;  // store max(a, 0): the caller-side F.relu(pred) folded into the kernel
+    // optional STAGED halo (pea_zshard_stage_halo): a local copy of the same four slices that a copy engine fills band
+    // by band (bands of `stage_band_rows` image rows, starting at row `stage_row0`) while this kernel runs; flag j
+    // reaches `stage_epoch` when band j has landed.  Tiles above stage_row0 read `halo` directly (their CTAs start
+    // before the first band can have arrived), the others wait for their band's flag and read the local copy.
+    const float* stage;
+    int64_t stage_plane;
+    const uint32_t* stage_flags;
+    uint32_t stage_epoch;
+    int stage_row0, stage_band_rows;
 };
 
 #ifndef PEA_K3_ORDER
@@ -885,6 +894,8 @@ __device__ __forceinline__ void st_out(float* p, float v) {
     *p = v;
 #endif
 }
+
+constexpr uint64_t kStageWaitNs = 40000;  // a staged band later than this is read from the peer in place
 
 template <int TY>
 __global__ void __launch_bounds__(TY * 32, (TY <= 8) ? 2 : 1)
@@ -941,6 +952,11 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
     // Odd CTAs therefore start with the part of the slab that needs no halo (slices 4 .. D-1, ring warmed up on the
     // slab's own first slices) and visit slices 0 .. 3 last: NVLink demand is spread over the whole kernel.
     const bool ext = P.halo != nullptr;
+    // staged halo: the copy engine runs ahead of the tile rows, the CTA reads local memory and needs no rotation
+    // (decided per CTA below: a band that has not landed within kStageWaitNs is read from the peer instead -- always
+    // correct, the peer's tail is complete before the launch -- so the kernel cannot hang on a copy that never runs)
+    bool staged = ext && P.stage_flags != nullptr && y0 >= P.stage_row0;
+    __shared__ int stage_ok;
 #if PEA_K3_ROTSPREAD
     // experiment (round 2): D - 3 different starting slices (0, i.e. halo first, or 4 .. D-1) dealt out by block index, so
     // that the resident CTAs ask for their halo at D - 3 different points of their lifetime instead of two.  No gain:
@@ -951,7 +967,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
         rot = j == 0 ? 0 : 3 + j;
     }
 #else
-    const int rot = (ext && zs == 0 && D > 4 && (blockIdx.x & 1)) ? 4 : 0;
+    const int rot = (ext && !staged && zs == 0 && D > 4 && (blockIdx.x & 1)) ? 4 : 0;
 #endif
     const int nz = D - zs;
     auto slice_of = [&](int i) { const int r = i + rot; return zs + (r >= nz ? r - nz : r); };
@@ -964,8 +980,19 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             issueY(slice_of(0));
             issueX(slice_of(0));
         }
+        if (staged) {   // the band of this tile's rows has landed when its flag carries this step's epoch
+            const uint32_t* f = P.stage_flags + (y0 - P.stage_row0) / P.stage_band_rows;
+            const uint64_t t0 = globaltimer_ns();
+            int ok = 1;
+            while ((int32_t)(ld_acquire_sys_u32(f) - P.stage_epoch) < 0) {
+                if (globaltimer_ns() - t0 > kStageWaitNs) { ok = 0; break; }
+                __nanosleep(256);
+            }
+            stage_ok = ok;
+        }
     }
-    __syncthreads();
+    __syncthreads();   // also carries thread 0's acquire to the threads that read the staged rows
+    if (staged) staged = stage_ok != 0;   // CTA-uniform
 
     f32x2 re[5][kC2];  // slot j: unit vector of slice z - j
 #pragma unroll
@@ -980,7 +1007,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
     // issue: volatile loads (the compiler may not sink them), raw values land in the ring slots; finish: normalise them.
     // Between the two the y and x parts of the next slice run (they need only the own vector and shared memory), so
     // the NVLink round trip of the halo is hidden behind ~80 % of a slice.
-    auto warm_issue = [&](const float* src, int64_t wplane, int nwarm) {
+    auto warm_issue = [&](const float* src, int64_t wplane, int nwarm, bool fresh = false) {
         const float* warm_b = src + (int64_t)b * kC * wplane + pix;
 #pragma unroll
         for (int j = 1; j <= 4; ++j) {
@@ -988,8 +1015,9 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
             const float* p = warm_b + (int64_t)(on ? nwarm - j : 0) * HW;
 #pragma unroll
             for (int i = 0; i < kC2; ++i) {
-                const float lo = ldg_early(p, on);
-                const float hi = ldg_early(p + wplane, on);
+                // `fresh`: the rows were written by a copy engine while this kernel was running -> L2-coherent loads
+                const float lo = fresh ? ldg_early_cg(p, on) : ldg_early(p, on);
+                const float hi = fresh ? ldg_early_cg(p + wplane, on) : ldg_early(p + wplane, on);
                 p += 2 * wplane;
                 re[j][i] = pack2(lo, hi);
             }
@@ -1013,6 +1041,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
     };
     bool pending = true;  // raw halo values sit in the ring slots, to be normalised before the next z part
     if (rot) warm_issue(P.emb + (int64_t)(rot - 4) * HW, P.emb_plane, 4);   // slices rot-4 .. rot-1 of the slab precede slice rot
+    else if (staged) warm_issue(P.stage, P.stage_plane, P.halo_n, true);
     else if (ext) warm_issue(P.halo, P.halo_plane, P.halo_n);
     else warm_issue(P.emb + (int64_t)(zs - (zs > 4 ? 4 : zs)) * HW, P.emb_plane, zs > 4 ? 4 : zs);
 
@@ -1738,7 +1767,8 @@ bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool
 }
 
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
-                       const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st) {
+                       const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st,
+                       const StagedHalo* stage) {
 #ifndef PEA_TILE_Y3D_FWD
 #define PEA_TILE_Y3D_FWD 8
 #endif
@@ -1752,6 +1782,12 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W; P.z_skip = z_skip;
     P.emb_plane = emb_plane; P.affs_plane = affs_plane; P.emb = emb; P.affs = affs;
     P.halo = halo; P.halo_n = halo_n; P.halo_plane = halo_plane; P.relu = relu;
+    P.stage = nullptr; P.stage_plane = 0; P.stage_flags = nullptr; P.stage_epoch = 0; P.stage_row0 = 0; P.stage_band_rows = 1;
+    if (stage && halo) {   // bands must start on tile rows: a tile waits for exactly one flag
+        if (stage->row0 % TY || stage->band_rows % TY || stage->band_rows <= 0) return PEA_E_SHAPE;
+        P.stage = stage->data; P.stage_plane = stage->plane; P.stage_flags = stage->flags; P.stage_epoch = stage->epoch;
+        P.stage_row0 = stage->row0; P.stage_band_rows = stage->band_rows;
+    }
     const int grid = d.B * ((d.H + TY - 1) / TY) * ((d.W + t3::TX - 1) / t3::TX);
     const size_t smem = sizeof(t3::StageF<TY>) + 1024;
     // (round 2 measured a Tensor-Memory ring + halo prefetch for this kernel as well: bit-identical, but 4.11 ms against

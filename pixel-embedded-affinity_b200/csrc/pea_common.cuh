@@ -23,6 +23,16 @@ struct Dims {
     int64_t N;  // D*H*W, voxels per (sample, channel) plane
 };
 
+// Local landing buffer of a z-shard's halo that a copy engine fills band by band while the forward kernel runs
+// (pea_zshard_stage_halo / pea_zshard_affs_fwd, include/pea_b200.h).
+struct StagedHalo {
+    const float* data;       // (B, C, halo_slices, H, W), channel-plane stride `plane`
+    int64_t plane;
+    const uint32_t* flags;   // flag j >= epoch (mod 2^32): rows [row0 + j * band_rows, ...) have landed
+    uint32_t epoch;
+    int row0, band_rows;
+};
+
 __host__ __device__ __forceinline__ int pmod(int a, int n) {
     int r = a % n;
     return r < 0 ? r + n : r;

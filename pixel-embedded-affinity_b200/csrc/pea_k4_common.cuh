@@ -128,6 +128,25 @@ __device__ __forceinline__ float ldg_early(const float* p, bool pred) {
         : "l"(p), "r"((int)pred));
     return v;
 }
+// the same for memory another engine wrote while the kernel was running (staged z-shard halo): L2 only, no L1 / texture path
+__device__ __forceinline__ float ldg_early_cg(const float* p, bool pred) {
+    float v;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.cg.f32 %0, [%1];\n\t}"
+        : "=f"(v)
+        : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 constexpr uint32_t kTmemCols = 512;

@@ -146,12 +146,18 @@ class PeerZShard:
         if self.world > 1:
             self.handle.barrier(channel=1)
 
-    def affinities(self, out=None, overlapped=False, compute=None):
-        """publish() -> 12-channel affinities of this rank's slab (halo read from the peer in place) -> release().
-        After it returns (stream-ordered) ``own`` may be rewritten for the next volume."""
+    def affinities(self, out=None, overlapped=False, compute=None, staged=None):
+        """publish() -> 12-channel affinities of this rank's slab -> release().  After it returns (stream-ordered)
+        ``own`` may be rewritten for the next volume.  Default: the kernel reads the tail from peer memory in place
+        (``fused_halo_affinities``).  ``staged=True``: a copy engine pulls the peer's tail into a local buffer band by band
+        while the ONE compute launch runs (``staged_halo_affinities``) -- same bits, measured no faster on NVLink 5
+        (0.556 - 0.569 ms against 0.555 ms per 13-slice slab at 1024 x 1024, 2 x B200), kept for slower links."""
+        staged = bool(staged) and compute is None and not overlapped
         self.publish()
         if overlapped:
             out = overlapped_halo_affinities(self, out=out, compute=compute)
+        elif staged and self.prev_tail is not None:
+            out = staged_halo_affinities(self, out=out)
         else:
             out = fused_halo_affinities(self.own, self.prev_tail, out=out, compute=compute)
         self.release()
@@ -168,6 +174,57 @@ def fused_halo_affinities(emb_own, prev_tail, out=None, compute=None):
     if out is None:
         out = torch.empty((B, 12, depth, H, W), device=emb_own.device, dtype=torch.float32)
     compute(emb_own, 0, out, prev_tail)
+    return out
+
+
+# Staged halo (round 2, ABI 7): the third way to get the four slices across.  `fused_halo_affinities` makes every CTA
+# pull its columns of the tail over NVLink itself (one launch); `overlapped_halo_affinities` uses the copy engine but
+# needs two launches and warms the ring up twice.  Here the copy engine pulls the tail in BANDS OF IMAGE ROWS, in the
+# order the kernel's tile rows are scheduled, each band followed by a stream-ordered flag write; the single compute
+# launch waits per tile row for its band's flag (bounded: a band later than 40 us is read from the peer instead, so the
+# kernel cannot hang on a copy that does not run) and reads local memory.  The first STAGED_ROW0 rows -- whose CTAs are
+# resident before any band can have landed -- read the peer directly as before.
+# Measured (tools/zshard_staged.py, 2 x B200, 13-slice slabs of 1024 x 1024): kernel without a halo 0.472 ms, in-place
+# halo 0.555 ms per step, staged 0.556 (row0 160, bands of 128 rows) - 0.569 ms (row0 96, bands of 64) - 0.620 (bands of
+# 256): no gain.  The same kernel with the tail in LOCAL memory (one GPU) takes 0.522 ms: of the 83 us a halo costs, 56
+# are the ring warm-up itself (268 MB more to read, a second warm-up for the CTAs that visit the halo slices last) and
+# 15 the two barriers; NVLink exposure is the remaining ~15 us, and the copy engine's own traffic gives those back.
+STAGED_ROW0 = 160        # first waves of CTAs (296 resident CTAs = 74 rows of 32-column tiles at W = 1024) read in place
+STAGED_BAND_ROWS = 128
+
+
+def staged_halo_affinities(shard, out=None, row0=None, band_rows=None):
+    """12-channel affinities of ``shard.own`` with the previous rank's tail pulled by a copy engine behind the running
+    kernel (pea_zshard_stage_halo + pea_zshard_affs_fwd, include/pea_b200.h).  Bit-identical to
+    ``fused_halo_affinities(shard.own, shard.prev_tail)``; call between ``publish()`` and ``release()``."""
+    from ._lib import lib, check
+    from ._ops import _ptr, _stream
+    B, C, depth, H, W = shard.own.shape
+    dev = shard.own.device
+    if out is None:
+        out = torch.empty((B, 12, depth, H, W), device=dev, dtype=torch.float32)
+    row0 = min(STAGED_ROW0 if row0 is None else row0, H) // 8 * 8
+    band_rows = STAGED_BAND_ROWS if band_rows is None else band_rows
+    stage, side = shard.staging()
+    nb = max(1, -(-(H - row0) // band_rows))
+    if getattr(shard, "_flags", None) is None or shard._flags.numel() < nb:
+        shard._flags = torch.zeros(nb, device=dev, dtype=torch.int32)
+        shard._epoch = 0
+    shard._epoch = (shard._epoch + 1) & 0x7FFFFFFF
+    tail = shard.prev_tail
+    ts, os_, es = tail.stride(), out.stride(), shard.own.stride()
+    cur = torch.cuda.current_stream(dev)
+    side.wait_stream(cur)            # behind publish(): the producer's tail is complete; behind the previous step's kernel
+    with torch.cuda.device(dev):
+        if row0 < H:
+            check("pea_zshard_stage_halo",
+                  lib.pea_zshard_stage_halo(_ptr(tail), int(ts[1]), _ptr(stage), B, C, int(tail.shape[2]), H, W, row0, band_rows,
+                                            _ptr(shard._flags), shard._epoch, side.cuda_stream))
+        check("pea_zshard_affs_fwd",
+              lib.pea_zshard_affs_fwd(_ptr(shard.own), B, C, depth, H, W, int(es[1]), int(os_[1]), _ptr(tail),
+                                      int(tail.shape[2]), int(ts[1]), _ptr(stage), _ptr(shard._flags), shard._epoch, row0,
+                                      band_rows, 0, _ptr(out), _stream()))
+    cur.wait_stream(side)            # release() and the next publish() follow the last copy as well as the kernel
     return out
 
 

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_strerror():
     import pea_b200
     lib = pea_b200._lib.lib
-    assert lib.pea_abi_version() == 6
+    assert lib.pea_abi_version() == 7
     assert lib.pea_strerror(0) == b"ok"
     assert b"channel" in lib.pea_strerror(-3)
     assert lib.pea_workspace_bytes(1, 16, 1, 8, 8, 2, 0) > 0

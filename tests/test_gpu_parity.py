@@ -1136,6 +1136,39 @@ def test_zshard_fused_peer_halo_is_bit_identical(P, O, world, D):
     assert torch.equal(part, whole[:, :, 2:])
 
 
+@pytest.mark.parametrize("shape,row0,band", [((1, 12, 64, 64), 8, 8), ((2, 9, 40, 96), 16, 16), ((1, 7, 72, 64), 0, 24),
+                                             ((1, 6, 48, 64), 48, 8)])
+def test_zshard_staged_halo_is_bit_identical(P, shape, row0, band):
+    """Staged halo (ABI 7): a copy engine pulls the previous slab's tail band by band on a side stream while the one
+    compute launch waits per tile row for its band's flag.  Emulated on one GPU (the "peer" tail is another local
+    buffer), rewritten every iteration so that a stale landing buffer or a flag from the previous epoch would show."""
+    from pea_b200.zshard import staged_halo_affinities, fused_halo_affinities, HALO
+
+    class Slab:   # what staged_halo_affinities needs of a PeerZShard
+        def __init__(self, own, tail):
+            self.own, self.prev_tail, self._stage = own, tail, None
+
+        def staging(self):
+            if self._stage is None:
+                B, C, _, H, W = self.own.shape
+                self._stage = torch.full((B, C, HALO, H, W), float("nan"), device="cuda")
+                self._side = torch.cuda.Stream()
+            return self._stage, self._side
+
+    B, D, H, W = shape
+    buf = torch.empty(B, 16, D + HALO, H, W, device="cuda")
+    slab = Slab(buf[:, :, HALO:], buf[:, :, :HALO])
+    for it in range(3):
+        torch.manual_seed(it)
+        buf.normal_()
+        whole = P.inf_embedding_loss_norm5(buf)
+        out = staged_halo_affinities(slab, row0=row0, band_rows=band)
+        assert torch.equal(out, whole[:, :, HALO:]), f"iteration {it}"
+        assert torch.equal(out, fused_halo_affinities(slab.own, slab.prev_tail))
+    if row0 < H:
+        assert int(slab._flags.max()) == 3 and int(slab._flags[: -(-(H - row0) // band)].min()) == 3   # one epoch per call
+
+
 def test_fused_batch_gt_matches_oracle(P, O):
     """make_targets_2d / _3d (two fused passes, 4 voxels per thread) vs the oracle, per (sample, channel) weights."""
     offsets = O.multi_offset([1, 3, 5, 9, 27], neighbor=4) + [[2, 3], [0, 40]]
