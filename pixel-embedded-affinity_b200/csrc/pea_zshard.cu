@@ -76,6 +76,7 @@ extern "C" int pea_zshard_affs_fwd(const float* emb, int B, int C, int D, int H,
     if (emb_plane == 0) emb_plane = N;
     if (affs_plane == 0) affs_plane = N;
     if (emb_plane < N || affs_plane < N) return PEA_E_SHAPE;
+    if (row0 < 0 || band_rows < 8 || row0 % 8 || band_rows % 8) return PEA_E_SHAPE;  // bands start on tile rows (8 rows)
     static const int32_t norm5[12 * 3] = {-1, 0, 0, 0, -1, 0, 0, 0, -1, -2, 0, 0, 0, -3, 0, 0, 0, -3,
                                           -3, 0, 0, 0, -9, 0, 0, 0, -9, -4, 0, 0, 0, -27, 0, 0, 0, -27};
     OffsetTable tab;

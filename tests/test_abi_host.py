@@ -154,3 +154,26 @@ def test_weighted_mse_matches_oracle_criterion():
     assert torch.equal(pea_b200.WeightedMSE()(p, t, w), O.WeightedMSE()(p, t, w))
     p5 = torch.randn(2, 1, 3, 5, 7)
     assert torch.equal(pea_b200.WeightedMSE()(p5, p5 * 0, None), O.WeightedMSE()(p5, p5 * 0, None))
+
+
+def test_staged_halo_entry_points_reject_bad_arguments_without_touching_the_device():
+    """ABI 7: pea_zshard_stage_halo / pea_zshard_affs_fwd (z-shards, halo pulled by a copy engine behind the kernel)."""
+    import pea_b200
+    lib = pea_b200._lib.lib
+    one = ctypes.c_void_p(16)
+    st = lib.pea_zshard_stage_halo   # (tail, tail_plane, stage, B, C, halo_slices, H, W, row0, band_rows, flags, epoch, stream)
+    assert st(None, 4 * 64, one, 1, 16, 4, 8, 8, 0, 8, one, 1, None) == -1
+    assert st(one, 4 * 64, one, 1, 16, 4, 8, 8, 0, 8, None, 1, None) == -1
+    assert st(one, 4 * 64, one, 1, 16, 5, 8, 8, 0, 8, one, 1, None) == -2      # at most four halo slices
+    assert st(one, 3 * 64, one, 1, 16, 4, 8, 8, 0, 8, one, 1, None) == -2      # plane smaller than the tail
+    assert st(one, 4 * 64 + 1, one, 1, 16, 4, 8, 8, 0, 8, one, 1, None) == -2  # plane not a whole number of slices
+    assert st(one, 4 * 64, one, 1, 16, 4, 8, 8, 9, 8, one, 1, None) == -2      # row0 beyond the image
+    assert st(one, 4 * 64, one, 1, 16, 4, 8, 8, 0, 0, one, 1, None) == -2
+    fw = lib.pea_zshard_affs_fwd     # (emb, B, C, D, H, W, emb_plane, affs_plane, halo, n, halo_plane, stage, flags, epoch, row0, band, relu, affs, stream)
+    assert fw(one, 1, 16, 6, 64, 64, 0, 0, one, 4, 4 * 4096, None, one, 1, 8, 8, 0, one, None) == -1
+    assert fw(one, 1, 8, 6, 64, 64, 0, 0, one, 4, 4 * 4096, one, one, 1, 8, 8, 0, one, None) == -2     # 16 channels only
+    assert fw(one, 1, 16, 6, 64, 64, 0, 0, one, 5, 5 * 4096, one, one, 1, 8, 8, 0, one, None) == -2
+    assert fw(one, 1, 16, 6, 64, 64, 0, 0, one, 4, 3 * 4096, one, one, 1, 8, 8, 0, one, None) == -2
+    assert fw(one, 1, 16, 6, 64, 64, 5 * 4096, 0, one, 4, 4 * 4096, one, one, 1, 8, 8, 0, one, None) == -2   # emb plane < D*H*W
+    assert fw(one, 1, 16, 6, 64, 64, 0, 0, one, 4, 4 * 4096, one, one, 1, 4, 8, 0, one, None) == -2    # bands start on tile rows
+    assert fw(one, 1, 16, 6, 64, 64, 0, 0, one, 4, 4 * 4096, one, one, 1, 8, 12, 0, one, None) == -2

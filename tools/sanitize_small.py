@@ -74,3 +74,26 @@ for two_pass in (0, 1):
 _lib.pea_debug_configure(3, 0)
 torch.cuda.synchronize()
 print("sanitize_small: done")
+# ABI 7: staged z-shard halo (copy engine + per-band flags on a side stream, one compute launch that waits per tile row)
+from pea_b200.zshard import staged_halo_affinities, fused_halo_affinities, HALO
+
+
+class _Slab:
+    def __init__(self, own, tail):
+        self.own, self.prev_tail, self._stage = own, tail, None
+
+    def staging(self):
+        if self._stage is None:
+            b, c, _, h, w = self.own.shape
+            self._stage = torch.zeros((b, c, HALO, h, w), device="cuda")
+            self._side = torch.cuda.Stream()
+        return self._stage, self._side
+
+
+zb = torch.randn(1, 16, 5 + HALO, 40, 64, device="cuda")
+zs = _Slab(zb[:, :, HALO:], zb[:, :, :HALO])
+for _ in range(2):
+    got = staged_halo_affinities(zs, row0=8, band_rows=16)
+assert torch.equal(got, fused_halo_affinities(zs.own, zs.prev_tail))
+torch.cuda.synchronize()
+print("sanitize_small: staged halo ok")
