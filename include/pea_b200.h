@@ -85,7 +85,9 @@ const char* pea_strerror(int code);
 #define PEA_KNOB_MAX_CTAS 1
 #define PEA_KNOB_TUNE_TY2D 2
 #define PEA_KNOB_GT_TWO_PASS 3
-#define PEA_KNOB_COUNT 4
+#define PEA_KNOB_K3_ROT_WAVES 4   /* z-shard forward kernel: 0 = default policy; n > 0: only CTAs of the first n waves visit
+                                   * the halo-dependent slices last; -1: none do (timing experiments, same results) */
+#define PEA_KNOB_COUNT 5
 int pea_debug_configure(int knob, int value);
 
 /* Bytes of device workspace the affinity entry points need for a problem of this size.

@@ -868,6 +868,7 @@ struct ParamsF {
     // by band (bands of `stage_band_rows` image rows, starting at row `stage_row0`) while this kernel runs; flag j
     // reaches `stage_epoch` when band j has landed.  Tiles above stage_row0 read `halo` directly (their CTAs start
     // before the first band can have arrived), the others wait for their band's flag and read the local copy.
+    int rot_ctas;  // CTAs with blockIdx.x below this (odd ones) visit the halo-dependent slices last
     const float* stage;
     int64_t stage_plane;
     const uint32_t* stage_flags;
@@ -967,7 +968,7 @@ fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
         rot = j == 0 ? 0 : 3 + j;
     }
 #else
-    const int rot = (ext && !staged && zs == 0 && D > 4 && (blockIdx.x & 1)) ? 4 : 0;
+    const int rot = (ext && !staged && zs == 0 && D > 4 && (blockIdx.x & 1) && (int)blockIdx.x < P.rot_ctas) ? 4 : 0;
 #endif
     const int nz = D - zs;
     auto slice_of = [&](int i) { const int r = i + rot; return zs + (r >= nz ? r - nz : r); };
@@ -1766,6 +1767,14 @@ bool tiled3d_fwd_eligible(int C, int W, const OffsetTable& tab, int border, bool
     return true;
 }
 
+// Waves of resident CTAs (2 per SM) whose odd CTAs use the rotated slice order with an external halo.  Only the FIRST
+// wave starts in lock step (296 CTAs asking for 19 MB of halo at t = 0); later CTAs start whenever an earlier one ends,
+// so their halo requests are spread already and the rotation only costs them a second ring warm-up (134 MB of re-reads
+// per 13-slice slab at 1024 x 1024).  2 x B200, 13-slice slabs, full step (tools/zshard_staged.py 26): no rotation
+// 0.580 ms, every CTA (the rule up to ABI 6) 0.561 - 0.566, first wave only 0.547, two / three / five waves 0.556 /
+// 0.555 / 0.560; start slices spread over D - 3 values need a run-time rotation (128 registers): slower throughout.
+constexpr int kRotWavesDefault = 1;
+
 int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_plane, int64_t affs_plane, float* affs,
                        const float* halo, int halo_n, int64_t halo_plane, int relu, cudaStream_t st,
                        const StagedHalo* stage) {
@@ -1782,6 +1791,13 @@ int launch_fwd3d_norm5(const float* emb, const Dims& d, int z_skip, int64_t emb_
     P.B = d.B; P.D = d.D; P.H = d.H; P.W = d.W; P.z_skip = z_skip;
     P.emb_plane = emb_plane; P.affs_plane = affs_plane; P.emb = emb; P.affs = affs;
     P.halo = halo; P.halo_n = halo_n; P.halo_plane = halo_plane; P.relu = relu;
+    {   // which CTAs take the rotated slice order (kernel comment "Slice order"): see kRotWavesDefault
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int knob = debug_knob(PEA_KNOB_K3_ROT_WAVES);
+        const int waves = knob == 0 ? kRotWavesDefault : knob;
+        P.rot_ctas = waves < 0 ? 0 : (waves >= (1 << 20) / (2 * sms) ? 1 << 30 : waves * 2 * sms);
+    }
     P.stage = nullptr; P.stage_plane = 0; P.stage_flags = nullptr; P.stage_epoch = 0; P.stage_row0 = 0; P.stage_band_rows = 1;
     if (stage && halo) {   // bands must start on tile rows: a tile waits for exactly one flag
         if (stage->row0 % TY || stage->band_rows % TY || stage->band_rows <= 0) return PEA_E_SHAPE;

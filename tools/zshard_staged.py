@@ -73,7 +73,18 @@ if sh.prev_tail is not None or world > 1:
     ref = Z.fused_halo_affinities(sh.own, sh.prev_tail).clone() if sh.prev_tail is not None else None
     sh.release()
     res["in-place halo, full step"] = timeit(step(lambda: Z.fused_halo_affinities(sh.own, sh.prev_tail, out=out)))
-    for row0, band in ((96, 64), (96, 128), (160, 128), (96, 256)):
+    from pea_b200._lib import lib as _lib
+    for waves in (-1, 1, 2, 1 << 20):   # PEA_KNOB_K3_ROT_WAVES: which waves of CTAs visit the halo slices last
+        assert _lib.pea_debug_configure(4, waves) == 0
+        if sh.prev_tail is not None:
+            sh.publish()
+            assert torch.equal(Z.fused_halo_affinities(sh.own, sh.prev_tail), ref), f"rot waves {waves}"
+            sh.release()
+        else:
+            sh.publish(); sh.release()
+        res[f"in-place halo, rot waves {waves}, full step"] = timeit(step(lambda: Z.fused_halo_affinities(sh.own, sh.prev_tail, out=out)))
+    _lib.pea_debug_configure(4, 0)
+    for row0, band in ((160, 128),) if os.environ.get("PEA_STAGED_SWEEP", "0") != "1" else ((96, 64), (96, 128), (160, 128), (96, 256)):
         sh.publish()   # collective: every rank, also the one without a halo
         got = Z.staged_halo_affinities(sh, row0=row0, band_rows=band) if sh.prev_tail is not None else None
         sh.release()
