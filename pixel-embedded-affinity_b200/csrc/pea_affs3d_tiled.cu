@@ -899,7 +899,11 @@ __device__ __forceinline__ void st_out(float* p, float v) {
 constexpr uint64_t kStageWaitNs = 40000;  // a staged band later than this is read from the peer in place
 
 template <int TY>
+#ifdef PEA_K3_MAXNREG   // timing experiments (tools/build_variant.sh): an explicit register cap instead of the launch bounds
+__global__ void __maxnreg__(PEA_K3_MAXNREG)
+#else
 __global__ void __launch_bounds__(TY * 32, (TY <= 8) ? 2 : 1)
+#endif
 fwd3d_norm5(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA,
             const __grid_constant__ CUtensorMap mapX, const ParamsF P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
