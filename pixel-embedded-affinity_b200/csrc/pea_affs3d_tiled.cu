@@ -877,10 +877,14 @@ struct ParamsF {
 };
 
 #ifndef PEA_K3_ORDER
-#define PEA_K3_ORDER 0  // tile -> CTA order of the forward kernel: 0 row-major, 1 column-major, 2 blocks of PEA_K3_BLK columns
+// tile -> CTA order of the forward kernel: 0 row-major, 1 column-major, 2 blocks of PEA_K3_BLK tile columns (row-major
+// inside a block).  A wave of 296 resident CTAs then covers a 512 x 148 pixel region instead of 1024 x 74: less of its
+// boundary lies above it, where the y halo (9 rows) and the y-27 arm reach into rows an earlier wave read long ago.
+// cfg4 on one GPU: order 0 3.65 ms, order 2 with blocks of 4 / 8 / 16 columns 3.56 / 3.54 / 3.52 ms, order 1 3.74 ms.
+#define PEA_K3_ORDER 2
 #endif
 #ifndef PEA_K3_BLK
-#define PEA_K3_BLK 4
+#define PEA_K3_BLK 16
 #endif
 #ifndef PEA_K3_ROTSPREAD
 #define PEA_K3_ROTSPREAD 0  // 1: D - 3 starting slices instead of two phases (measured at 2 x 13 slices: 0.571 vs 0.563 ms, no gain)
