@@ -206,6 +206,20 @@ __device__ __forceinline__ float pair(const float* __restrict__ nb, const f32x2 
     return w * diff * diff;
 }
 
+// Store of one affinity, predicated WITHOUT a branch: `if (affs_b && live) affs_b[o] = a;` ends a basic block after
+// every pair evaluation, so the next pair's shared-memory loads cannot be scheduled above it (the forward-only 2-D kernel
+// gained 7.5 % from the same change).  A predicated-off store touches no memory, so a null affs_b is fine.
+#ifndef PEA_CANON_BRANCHY_STORE
+#define PEA_CANON_BRANCHY_STORE 0   // 1: the `if` form (A/B)
+#endif
+__device__ __forceinline__ void st_affs(float* base, uint32_t off, float v, bool ok) {
+#if PEA_CANON_BRANCHY_STORE
+    if (ok) base[off] = v;
+#else
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(base + off), "f"(v), "r"((int)ok));
+#endif
+}
+
 template <int MASK>
 __device__ __forceinline__ float mask_sq(uint32_t raw) {
     if (MASK == PEA_MASK_NONE) return 1.f;
@@ -439,6 +453,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
         const float* ownY = &S.sY[0][ty + PM][tx];
         const float* ownX = &S.sX[0][ty][tx + PM];
         float* affs_b = P.affs ? P.affs + sample + pix : nullptr;
+        const bool st_ok = affs_b != nullptr && live;
         f32x2 e[kC2], G[kC2];
         float rp;
         {
@@ -492,7 +507,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 }
                 float a;
                 lossacc[2 * j] += pair<CHS_Y, GRAD>(ownY - s * TX, e, G, t_f, w_f, P.gcoef[2 * j], a);
-                if (affs_b && live) affs_b[(uint32_t)(2 * j) * Nu] = a;
+                st_affs(affs_b, (uint32_t)(2 * j) * Nu, a, st_ok);
                 if (REV) {
                     // rows below the image are zero fill in the weight box: pair dropped
                     float a2;
@@ -582,7 +597,7 @@ fused2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ 
                 }
                 float a;
                 lossacc[2 * j + 1] += pair<CHS_X, GRAD>(ownX - s, e, G, t_f, w_f, P.gcoef[2 * j + 1], a);
-                if (affs_b && live) affs_b[(uint32_t)(2 * j + 1) * Nu] = a;
+                st_affs(affs_b, (uint32_t)(2 * j + 1) * Nu, a, st_ok);
                 if (REV) {
                     float a2;
                     pair<CHS_X, true>(ownX + s, e, G, t_r, w_r, P.gcoef[2 * j + 1], a2);

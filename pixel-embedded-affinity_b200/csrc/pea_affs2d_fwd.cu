@@ -20,7 +20,15 @@
 #include "pea_tma.cuh"
 
 namespace pea {
+#ifndef PEA_K1C_BRANCHY_STORE
+#define PEA_K1C_BRANCHY_STORE 0
+#endif
+
 namespace f2 {
+
+__device__ __forceinline__ void st_pred(float* p, float v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)pred));
+}
 
 constexpr int kC = 16, kC2 = 8;
 constexpr int TX = 32, TY = 16, NT = TY * 32, NSMAX = 6;
@@ -192,10 +200,17 @@ fwd2d_canon(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CU
                 ay = fmaxf(ay, 0.f);
                 ax = fmaxf(ax, 0.f);
             }
+#if PEA_K1C_BRANCHY_STORE
             if (live) {
                 out[(uint32_t)(2 * j) * Nu] = ay;
                 out[(uint32_t)(2 * j + 1) * Nu] = ax;
             }
+#else
+            // predicated stores without a branch: `if (live)` makes ptxas sink both pair evaluations into the branch,
+            // one reconvergence region per shift that nothing is scheduled across (`out` is valid for dead lanes)
+            st_pred(out + (uint32_t)(2 * j) * Nu, ay, live);
+            st_pred(out + (uint32_t)(2 * j + 1) * Nu, ax, live);
+#endif
         }
         __syncthreads();  // every warp has left this set of boxes
         if (NBUF == 1 && threadIdx.x == 0 && tn < P.n_tiles) issue(tn, 0);
