@@ -24,6 +24,19 @@
 namespace pea {
 namespace a2 {
 
+// one affinity, predicated without a branch (a predicated-off store touches no memory, so a null base is fine): the `if`
+// form ends a basic block after every pair evaluation
+#ifndef PEA_AXIS_BRANCHY_STORE
+#define PEA_AXIS_BRANCHY_STORE 0
+#endif
+__device__ __forceinline__ void st_affs(float* p, float v, bool ok) {
+#if PEA_AXIS_BRANCHY_STORE
+    if (ok) *p = v;
+#else
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)ok));
+#endif
+}
+
 constexpr int kC = 16;
 constexpr int kC2 = 8;
 constexpr int TX = 32;
@@ -394,7 +407,7 @@ fused2d_axis(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ C
                     pair<CHS_Y, true>(ownY - s * TX, e, G, cur.t2, cur.w2 * mask_sq<MASK>(cur.m2), gco, a2);
                 }
             }
-            if (affs_b && (INNER || live)) affs_b[(uint32_t)c * Nu] = a;
+            st_affs(affs_b + (uint32_t)c * Nu, a, affs_b != nullptr && (INNER || live));
             S.sL[c][threadIdx.x] = lt;
         };
         // three rotating fetch buffers, statically named (a register-to-register rotation would wait on the loads)
@@ -720,7 +733,7 @@ fused2d_axis_p(const __grid_constant__ CUtensorMap mapY, const __grid_constant__
                         pair<CHS_Y, true>(ownY - s * TX, e, G, cur.t2, cur.w2 * mask_sq<MASK>(cur.m2), gco, a2);
                     }
                 }
-                if (affs_b && (INNER || live)) affs_b[(uint32_t)c * Nu] = a;
+                st_affs(affs_b + (uint32_t)c * Nu, a, affs_b != nullptr && (INNER || live));
                 S.sL[c][threadIdx.x] += lt;
             };
             bool xready = false, yfree = false;
