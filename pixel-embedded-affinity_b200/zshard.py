@@ -210,7 +210,7 @@ def staged_halo_affinities(shard, out=None, row0=None, band_rows=None):
     if getattr(shard, "_flags", None) is None or shard._flags.numel() < nb:
         shard._flags = torch.zeros(nb, device=dev, dtype=torch.int32)
         shard._epoch = 0
-    shard._epoch = (shard._epoch + 1) & 0x7FFFFFFF
+    shard._epoch = (shard._epoch + 1) & 0xFFFFFFFF   # full 32-bit wrap: the kernel compares the signed distance flag - epoch
     tail = shard.prev_tail
     ts, os_, es = tail.stride(), out.stride(), shard.own.stride()
     cur = torch.cuda.current_stream(dev)

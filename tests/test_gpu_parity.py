@@ -1167,6 +1167,14 @@ def test_zshard_staged_halo_is_bit_identical(P, shape, row0, band):
         assert torch.equal(out, fused_halo_affinities(slab.own, slab.prev_tail))
     if row0 < H:
         assert int(slab._flags.max()) == 3 and int(slab._flags[: -(-(H - row0) // band)].min()) == 3   # one epoch per call
+        # the epoch wraps at 2^32: the kernel compares the signed distance flag - epoch
+        slab._epoch = 0xFFFFFFFD
+        slab._flags.fill_(-3)
+        for it in range(5):
+            buf.normal_()
+            out = staged_halo_affinities(slab, row0=row0, band_rows=band)
+            assert torch.equal(out, P.inf_embedding_loss_norm5(buf)[:, :, HALO:]), f"epoch wrap, iteration {it}"
+        assert slab._epoch == 2 and int(slab._flags[0]) == 2
 
 
 def test_fused_batch_gt_matches_oracle(P, O):
