@@ -1074,7 +1074,10 @@ def test_inference_epilogue_fused(P, O, B, D, H, W):
         assert (plain < 0).any()  # the clamp is exercised
 
 
-@pytest.mark.parametrize("B,D,H,W,seed", [(1, 18, 64, 96, 91), (2, 7, 37, 44, 92), (1, 5, 28, 28, 93)])
+# (1, 5, 28, 672): 21 tile columns -- one full block of 16 and a narrower last block of the forward kernel's tile order;
+# (2, 5, 28, 1056): 33 tile columns, two samples (the block walk restarts per sample)
+@pytest.mark.parametrize("B,D,H,W,seed", [(1, 18, 64, 96, 91), (2, 7, 37, 44, 92), (1, 5, 28, 28, 93), (1, 5, 28, 672, 94),
+                                          (2, 5, 28, 1056, 95)])
 def test_tiled3d_forward_matches_generic_and_oracle(P, O, B, D, H, W, seed):
     from pea_b200 import _ops as ops
     rng = np.random.RandomState(seed)
